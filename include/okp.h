@@ -1,0 +1,172 @@
+/* okp.h -- C ABI of libokp.so: the B200 (sm_100a) heatmap -> 3D keypoint path.
+ *
+ * This is the drop-in boundary for the inference hot path of ethz-asl/object_keypoints.
+ * The reference has no FFI for this path (it is pure Python on torch-CPU / OpenCV); each
+ * entry point below names the reference code it replaces, paths relative to the reference
+ * root. INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; every buffer is owned and sized by the caller (PyTorch in this
+ *     repo); the library allocates nothing and keeps no global state;
+ *   - pointers named *_dev / inside OkpDecodeTables are DEVICE pointers; keypoint_config,
+ *     OkpCamera and OkpDecodeParams are read on the HOST at call time;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default
+ *     stream) and the call returns without synchronising;
+ *   - return value: OKP_OK or a negative OKP_E_* code (okp_strerror). Data-dependent
+ *     conditions (table overflow, outlier votes, ...) are never errors: they are reported per
+ *     frame in OkpDecodeTables.flags -- the reference prints them (perception/pipeline.py:123);
+ *   - re-entrant: concurrent calls on different streams with different buffers are safe.
+ */
+#ifndef OKP_H
+#define OKP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OKP_VERSION_MAJOR 0
+#define OKP_VERSION_MINOR 1
+
+enum {
+    OKP_OK = 0,
+    OKP_E_NULL = -1,         /* a required pointer is NULL */
+    OKP_E_SHAPE = -2,        /* N, C, H, W, P, V ... out of the supported range */
+    OKP_E_CAPACITY = -3,     /* max_peaks / max_objects / max_votes out of range */
+    OKP_E_UNSUPPORTED = -4,  /* parameter combination not implemented (e.g. nms_size) */
+    OKP_E_CUDA = -5,         /* a CUDA runtime call or kernel launch failed */
+    OKP_E_WORKSPACE = -6     /* workspace smaller than okp_decode_workspace_bytes() */
+};
+
+/* per-frame flag bits in OkpDecodeTables.flags */
+#define OKP_FLAG_PEAK_OVERFLOW 1u     /* a map had more peaks than max_peaks; the first max_peaks (raster order) are kept */
+#define OKP_FLAG_OBJECT_OVERFLOW 2u   /* more centre peaks than max_objects */
+#define OKP_FLAG_OUTLIER_SKIPPED 4u   /* a spoke voted farther than outlier_distance from every centre (pipeline.py:121-124) */
+#define OKP_FLAG_CLUSTERED 8u         /* > cfg[t] detections, cfg[t] > 1: merged by k-means (pipeline.py:143-148) */
+#define OKP_FLAG_VOTE_OVERFLOW 16u    /* more votes for one object than max_votes */
+#define OKP_FLAG_NO_CENTERS 32u       /* empty centre map: frame has no objects (pipeline.py:105-106) */
+#define OKP_FLAG_ARGMAX_RESOLVED 64u  /* > cfg[t] detections, cfg[t] == 1: most confident kept (pipeline.py:139-142) */
+
+#define OKP_MAX_MAPS 16               /* C = 1 + number of keypoint types */
+#define OKP_MAX_PEAKS 256             /* upper bound for OkpDecodeParams.max_peaks */
+#define OKP_MAX_OBJECTS 128
+#define OKP_MAX_SLOTS 8               /* upper bound for any keypoint_config entry */
+#define OKP_MAX_VIEWS 64
+
+/* Kalibr pinhole + equidistant camera, as perception/utils/camera_utils.py:7-16,64-81 holds it
+ * (K, D, Kinv) plus the clip limits DetectionToPoint.reset derives (pipeline.py:159-162). */
+typedef struct OkpCamera {
+    double fx, fy, cx, cy;
+    double k[4];            /* equidistant distortion k1..k4 */
+    double kinv[9];         /* row-major inverse of K, computed by the caller like camera_utils.py:11 */
+    int32_t clip_x;         /* int(image_size[0]) - 1: the reference clips x with the HEIGHT (pipeline.py:162,169) */
+    int32_t clip_y;         /* int(image_size[1]) - 1 */
+} OkpCamera;
+
+typedef struct OkpDecodeParams {
+    float threshold;          /* 0.5 on the 5x5 box sum (pipeline.py:73) */
+    int32_t nms_size;         /* 5 (perception/models.py:55) */
+    int32_t box_sum;          /* 1: NMS runs on the 5x5 box sum (pipeline.py:70-72) */
+    int32_t compat_clip_bug;  /* 1: clip (x, y) with (H-1, W-1) like pipeline.py:169; 0: with (W-1, H-1) */
+    double outlier_distance;  /* 20.0 px (pipeline.py:121) */
+    int32_t max_peaks;        /* K: peak slots per (frame, map) */
+    int32_t max_objects;      /* O: object slots per frame */
+    int32_t max_votes;        /* V: vote slots per object */
+    int32_t kmeans_iterations;/* Lloyd iterations of the deterministic clustering (default 16) */
+} OkpDecodeParams;
+
+/* Fixed-capacity structure-of-arrays output. N frames, C maps, K = max_peaks, O = max_objects,
+ * S = max(1, max(keypoint_config)), V = max_votes. Map 0 is the object-centre map. All arrays are
+ * dense row-major with the shapes given; unused slots are zero / -1. */
+typedef struct OkpDecodeTables {
+    /* peaks of every map, raster (row-major y, x) order -- pipeline.py:69-79 */
+    int32_t* peak_count;    /* [N,C]      true number of peaks (may exceed K) */
+    int32_t* peak_yx;       /* [N,C,K,2]  pixel (y, x) */
+    float*   peak_score;    /* [N,C,K]    5x5 box sum at the peak */
+    float*   peak_xy;       /* [N,C,K,2]  centroid (x, y), pixel-index coordinates (pipeline.py:59,76) */
+    float*   peak_conf;     /* [N,C,K]    sum of the window's probabilities (pipeline.py:61) */
+    /* spoke -> object assignment -- pipeline.py:115-128 */
+    int32_t* peak_object;   /* [N,C,K]    object index, -1 = skipped or no centres */
+    double*  peak_vote;     /* [N,C,K,2]  predicted centre (x, y) */
+    /* objects -- pipeline.py:130-152,189-199 */
+    int32_t* n_objects;     /* [N] */
+    uint32_t* flags;        /* [N]        OKP_FLAG_* */
+    int32_t* kp_assigned;   /* [N,O,C]    detections assigned before resolution */
+    int32_t* kp_count;      /* [N,O,C]    keypoints kept: 1 for the centre, <= keypoint_config[c-1] otherwise */
+    int32_t* kp_peak;       /* [N,O,C,S]  index into the map's peak list, -1 for cluster centres */
+    float*   kp_xy;         /* [N,O,C,S,2] */
+    double*  kp_point;      /* [N,O,C,S,3] camera-frame point 'p_C' (pipeline.py:164-171) */
+    int32_t* n_votes;       /* [N,O] */
+    double*  votes;         /* [N,O,V,2]  'p_centers' in assignment order */
+} OkpDecodeTables;
+
+int okp_version(void);
+const char* okp_strerror(int code);
+
+/* Scratch bytes okp_decode_f32 / okp_extract_peaks_f32 need for this problem size. */
+size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodeParams* params);
+
+/* Replaces KeypointExtractionComponent.__call__ (perception/pipeline.py:64-91) including
+ * perception/models.py:55-58 (nms): box sum, NMS, threshold, raster-order compaction and
+ * sub-pixel centroid for every map of every frame. Fills the peak_* tables (peak_object and
+ * peak_vote are reset). heat_dev: [N,C,H,W] float32 probabilities. */
+int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W,
+                          const OkpDecodeParams* params, const OkpDecodeTables* tables,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replaces ObjectExtraction.__call__ (pipeline.py:104-153) and the DetectionToPoint loop of
+ * ObjectKeypointPipeline.__call__ (pipeline.py:189-199, 164-171; camera_utils.py:31-34,75-81)
+ * for every frame, reading the peak_* tables. depth_dev [N,C,H,W], centers_dev [N,C-1,2,H,W].
+ * camera may be NULL: then kp_point is left zero (ObjectExtraction only). */
+int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
+                          const int32_t* keypoint_config, const OkpCamera* camera,
+                          const OkpDecodeParams* params, const OkpDecodeTables* tables, void* stream);
+
+/* Replaces ObjectKeypointPipeline.__call__ (pipeline.py:182-200) for a batch of N frames:
+ * okp_extract_peaks_f32 followed by okp_group_objects_f32 on the same stream. */
+int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev,
+                   int N, int C, int H, int W, const int32_t* keypoint_config,
+                   const OkpCamera* camera, const OkpDecodeParams* params,
+                   const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
+                   void* stream);
+
+/* Replaces FisheyeCamera.undistort (camera_utils.py:75-81, cv2.fisheye.undistortPoints with
+ * P = K). xy_dev/out_dev: [n,2] float64. round_to_f32 != 0 reproduces OpenCV's float32 output
+ * for float32 input (the value is rounded to float32, stored as float64). */
+int okp_fisheye_undistort_f64(const double* xy_dev, int n, const OkpCamera* camera,
+                              int round_to_f32, double* out_dev, void* stream);
+
+/* Replaces FisheyeCamera.project (camera_utils.py:65-73, cv2.fisheye.projectPoints).
+ * X_dev [n,3] float64 world points, T_CW: 16 doubles row-major on the HOST, out_dev [n,2]. */
+int okp_fisheye_project_f64(const double* X_dev, int n, const double* T_CW, const OkpCamera* camera,
+                            double* out_dev, void* stream);
+
+/* Replaces DetectionToPoint.__call__ (pipeline.py:164-171): undistort, round, clip, depth lookup,
+ * unproject. xy_dev [n,2] float32, depth_map_dev [H,W] float32, out_dev [n,3] float64. */
+int okp_detection_to_point_f32(const float* xy_dev, int n, const float* depth_map_dev, int H, int W,
+                               const OkpCamera* camera, const OkpDecodeParams* params,
+                               double* out_dev, void* stream);
+
+/* Batched multi-view DLT. Replaces the cv2.triangulatePoints calls of StereoCamera.triangulate
+ * (camera_utils.py:103-108) and LabelingApp._triangulate (scripts/label.py:296-305) and
+ * generalises them to V views. points_dev [P,V,2] float64 UNDISTORTED pixels, valid_dev [P,V]
+ * uint8 (NULL = all valid), projections_dev [V,3,4] float64 when per_point_projections == 0,
+ * else [P,V,3,4]. out_dev [P,3]; points with fewer than two valid views get NaN. */
+int okp_triangulate_f64(const double* points_dev, const uint8_t* valid_dev,
+                        const double* projections_dev, int per_point_projections, int P, int V,
+                        double* out_dev, void* stream);
+
+/* Reprojection-error filter (absent from the reference as code; north_star names it): project
+ * X_dev [P,3] into every view (poses_dev [V,4,4] world->camera float64, one equidistant camera),
+ * write the pixel error err_dev [P,V] against the DISTORTED observations obs_dev [P,V,2], and clear
+ * valid_dev[p,v] where the error exceeds max_error_px. */
+int okp_reprojection_filter_f64(const double* X_dev, const double* obs_dev, uint8_t* valid_dev,
+                                const double* poses_dev, const OkpCamera* camera, int P, int V,
+                                double max_error_px, double* err_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OKP_H */

@@ -1,0 +1,116 @@
+"""ctypes mirror of include/okp.h: structures, table shapes and packing helpers.
+
+Pure host code (no torch, no CUDA) so that it can be unit-tested anywhere and shared by the
+library loader (``_lib.py``) and by the test-side oracle wrapper.
+"""
+import ctypes
+
+import numpy as np
+
+OKP_MAX_MAPS = 16
+OKP_MAX_PEAKS = 256
+OKP_MAX_OBJECTS = 128
+OKP_MAX_SLOTS = 8
+OKP_MAX_VIEWS = 64
+
+FLAG_PEAK_OVERFLOW = 1
+FLAG_OBJECT_OVERFLOW = 2
+FLAG_OUTLIER_SKIPPED = 4
+FLAG_CLUSTERED = 8
+FLAG_VOTE_OVERFLOW = 16
+FLAG_NO_CENTERS = 32
+FLAG_ARGMAX_RESOLVED = 64
+
+ERRORS = {0: 'OKP_OK', -1: 'OKP_E_NULL', -2: 'OKP_E_SHAPE', -3: 'OKP_E_CAPACITY',
+          -4: 'OKP_E_UNSUPPORTED', -5: 'OKP_E_CUDA', -6: 'OKP_E_WORKSPACE'}
+
+
+class OkpCamera(ctypes.Structure):
+    _fields_ = [('fx', ctypes.c_double), ('fy', ctypes.c_double), ('cx', ctypes.c_double), ('cy', ctypes.c_double),
+                ('k', ctypes.c_double * 4), ('kinv', ctypes.c_double * 9),
+                ('clip_x', ctypes.c_int32), ('clip_y', ctypes.c_int32)]
+
+
+class OkpDecodeParams(ctypes.Structure):
+    _fields_ = [('threshold', ctypes.c_float), ('nms_size', ctypes.c_int32), ('box_sum', ctypes.c_int32),
+                ('compat_clip_bug', ctypes.c_int32), ('outlier_distance', ctypes.c_double),
+                ('max_peaks', ctypes.c_int32), ('max_objects', ctypes.c_int32), ('max_votes', ctypes.c_int32),
+                ('kmeans_iterations', ctypes.c_int32)]
+
+
+# name, numpy dtype, shape as a function of the dimension dict -- order = field order in okp.h
+TABLE_LAYOUT = [
+    ('peak_count', np.int32, lambda d: (d['N'], d['C'])),
+    ('peak_yx', np.int32, lambda d: (d['N'], d['C'], d['K'], 2)),
+    ('peak_score', np.float32, lambda d: (d['N'], d['C'], d['K'])),
+    ('peak_xy', np.float32, lambda d: (d['N'], d['C'], d['K'], 2)),
+    ('peak_conf', np.float32, lambda d: (d['N'], d['C'], d['K'])),
+    ('peak_object', np.int32, lambda d: (d['N'], d['C'], d['K'])),
+    ('peak_vote', np.float64, lambda d: (d['N'], d['C'], d['K'], 2)),
+    ('n_objects', np.int32, lambda d: (d['N'],)),
+    ('flags', np.uint32, lambda d: (d['N'],)),
+    ('kp_assigned', np.int32, lambda d: (d['N'], d['O'], d['C'])),
+    ('kp_count', np.int32, lambda d: (d['N'], d['O'], d['C'])),
+    ('kp_peak', np.int32, lambda d: (d['N'], d['O'], d['C'], d['S'])),
+    ('kp_xy', np.float32, lambda d: (d['N'], d['O'], d['C'], d['S'], 2)),
+    ('kp_point', np.float64, lambda d: (d['N'], d['O'], d['C'], d['S'], 3)),
+    ('n_votes', np.int32, lambda d: (d['N'], d['O'])),
+    ('votes', np.float64, lambda d: (d['N'], d['O'], d['V'], 2)),
+]
+
+
+class OkpDecodeTables(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_void_p) for name, _, _ in TABLE_LAYOUT]
+
+
+def table_dims(N, C, keypoint_config, params):
+    return {'N': int(N), 'C': int(C), 'K': int(params.max_peaks), 'O': int(params.max_objects),
+            'S': max([1] + [int(v) for v in keypoint_config]), 'V': int(params.max_votes)}
+
+
+def table_shapes(N, C, keypoint_config, params):
+    dims = table_dims(N, C, keypoint_config, params)
+    return [(name, dtype, shape(dims)) for name, dtype, shape in TABLE_LAYOUT]
+
+
+def make_params(threshold=0.5, outlier_distance=20.0, max_peaks=32, max_objects=16, max_votes=16,
+                compat_clip_bug=True, kmeans_iterations=16):
+    if not (1 <= max_peaks <= OKP_MAX_PEAKS):
+        raise ValueError(f"max_peaks must be in [1, {OKP_MAX_PEAKS}]")
+    if not (1 <= max_objects <= OKP_MAX_OBJECTS):
+        raise ValueError(f"max_objects must be in [1, {OKP_MAX_OBJECTS}]")
+    return OkpDecodeParams(threshold=threshold, nms_size=5, box_sum=1, compat_clip_bug=int(bool(compat_clip_bug)),
+                           outlier_distance=outlier_distance, max_peaks=max_peaks, max_objects=max_objects,
+                           max_votes=max_votes, kmeans_iterations=kmeans_iterations)
+
+
+def pack_camera(camera):
+    """Camera object with K, D, Kinv, image_size (camera_utils.FisheyeCamera or the reference's
+    own class) -> OkpCamera. clip_x/clip_y follow DetectionToPoint.reset (pipeline.py:159-162):
+    ``image_size.astype(int) - 1`` = (H-1, W-1), later applied to (x, y)."""
+    K = np.asarray(camera.K, dtype=np.float64)
+    D = np.asarray(camera.D, dtype=np.float64).reshape(-1)
+    if D.size < 4:
+        raise ValueError("equidistant model needs four distortion coefficients")
+    kinv = np.asarray(getattr(camera, 'Kinv', np.linalg.inv(K)), dtype=np.float64)
+    size = np.asarray(camera.image_size)
+    out = OkpCamera(fx=K[0, 0], fy=K[1, 1], cx=K[0, 2], cy=K[1, 2],
+                    clip_x=int(size[0]) - 1, clip_y=int(size[1]) - 1)
+    for i in range(4):
+        out.k[i] = float(D[i])
+    for i in range(9):
+        out.kinv[i] = float(kinv.reshape(-1)[i])
+    return out
+
+
+def check_keypoint_config(keypoint_config):
+    """Accepts the parsed JSON dict {'keypoint_config': [...]} (what the reference passes,
+    pipeline.py:36,95) or the bare list; returns the list of ints."""
+    if isinstance(keypoint_config, dict):
+        keypoint_config = keypoint_config['keypoint_config']
+    cfg = [int(v) for v in keypoint_config]
+    if len(cfg) + 1 > OKP_MAX_MAPS:
+        raise ValueError(f"at most {OKP_MAX_MAPS - 1} keypoint types")
+    if any(v < 1 or v > OKP_MAX_SLOTS for v in cfg):
+        raise ValueError(f"keypoint_config entries must be in [1, {OKP_MAX_SLOTS}]")
+    return cfg

@@ -1,0 +1,391 @@
+"""TEST INFRASTRUCTURE -- generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, OpenCV and scikit-learn):
+
+    python -m oracle.make_goldens
+
+Every fixture stores the inputs together with what the reference returned for them, converted
+to the fixed-capacity record tables of include/okp.h so tests can compare arrays one to one.
+The GPU box has no reference; its tests read these files.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import, margins, np_oracle          # noqa: E402
+from object_keypoints_b200 import synthetic                  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+K_PEAKS, O_OBJECTS, V_VOTES = 32, 16, 16
+
+
+def reference_camera(camera_utils, size):
+    """The reference's own camera object, built the way eval_model.py:61-69 /
+    test_pipeline.py:88-90 do."""
+    camera = camera_utils.from_calibration(os.path.join(ref_import.REFERENCE_ROOT, 'config', 'calibration.yaml'))
+    if tuple(size) == (64, 64):
+        scaled = camera.scale(511.0 / 720.0)
+        offset = np.array([(scaled.image_size[1] - 511.0) / 2.0, 0.0])
+        return scaled.cut(offset).scale(64.0 / 511.0)
+    return camera.scale(size[0] / 720.0)
+
+
+def reference_tables(ref, camera, heat, depth, centers, cfg, seed=0):
+    """Run perception.pipeline.ObjectKeypointPipeline frame by frame -> record tables."""
+    N, C, H, W = heat.shape
+    S = max([1] + list(cfg))
+    K, O, V = K_PEAKS, O_OBJECTS, V_VOTES
+    pipe = ref.ObjectKeypointPipeline([H, W], None, {'keypoint_config': list(cfg)})
+    pipe.reset(camera)
+    captured = []
+    inner = pipe.keypoint_extraction._compute_points
+
+    def spy(indices, probabilities):
+        captured.append(np.array(indices.numpy(), copy=True).reshape(-1, 2))
+        return inner(indices, probabilities)
+    pipe.keypoint_extraction._compute_points = spy
+
+    t = {
+        'peak_count': np.zeros((N, C), np.int32),
+        'peak_yx': np.full((N, C, K, 2), -1, np.int32),
+        'peak_score': np.zeros((N, C, K), np.float32),
+        'peak_xy': np.zeros((N, C, K, 2), np.float32),
+        'peak_conf': np.zeros((N, C, K), np.float32),
+        'peak_object': np.full((N, C, K), -1, np.int32),
+        'peak_vote': np.zeros((N, C, K, 2), np.float64),
+        'n_objects': np.zeros((N,), np.int32),
+        'n_skipped': np.zeros((N,), np.int32),
+        'kp_assigned': np.zeros((N, O, C), np.int32),
+        'kp_count': np.zeros((N, O, C), np.int32),
+        'kp_peak': np.full((N, O, C, S), -1, np.int32),
+        'kp_xy': np.zeros((N, O, C, S, 2), np.float32),
+        'kp_point': np.zeros((N, O, C, S, 3), np.float64),
+        'n_votes': np.zeros((N, O), np.int32),
+        'votes': np.zeros((N, O, V, 2), np.float64),
+    }
+    ones = torch.ones((1, 1, 5, 5), dtype=torch.float32)
+    for n in range(N):
+        captured.clear()
+        np.random.seed(seed + n)
+        log = io.StringIO()
+        with contextlib.redirect_stdout(log):
+            objects = pipe(torch.tensor(heat[n:n + 1]), torch.tensor(depth[n:n + 1]),
+                           torch.tensor(centers[n:n + 1]))
+        t['n_skipped'][n] = log.getvalue().count('skipping point')
+        indices = [c.copy() for c in captured]
+        points, confidence = pipe.keypoint_extraction(heat[n:n + 1])
+        points, confidence = points[0], confidence[0]
+        for c in range(C):
+            k = len(indices[c])
+            assert k <= K, "golden case exceeds the peak table"
+            t['peak_count'][n, c] = k
+            score = torch.nn.functional.conv2d(torch.tensor(heat[n, c])[None, None], ones, padding=2)[0, 0].numpy()
+            for j in range(k):
+                y, x = indices[c][j]
+                t['peak_yx'][n, c, j] = (y, x)
+                t['peak_score'][n, c, j] = score[y, x]
+                t['peak_xy'][n, c, j] = points[c][j]
+                t['peak_conf'][n, c, j] = float(confidence[c][j])
+        t['n_objects'][n] = len(objects)
+        assert len(objects) <= O
+        # reconstruct the (pre-resolution) assignment from the ordered vote lists
+        p_centers = pipe.object_extraction.image_indices + centers[n]
+        cursor = [0] * len(objects)
+        for o, obj in enumerate(objects):
+            t['n_votes'][n, o] = len(obj['p_centers'])
+            for v, vote in enumerate(obj['p_centers'][:V]):
+                t['votes'][n, o, v] = vote
+            t['peak_object'][n, 0, o] = o
+        if len(objects):
+            for c in range(1, C):
+                for j in range(t['peak_count'][n, c]):
+                    xy = np.clip(points[c][j].round().astype(np.int32), pipe.object_extraction.min,
+                                 pipe.object_extraction.max)
+                    vote = p_centers[c - 1, :, xy[1], xy[0]]
+                    t['peak_vote'][n, c, j] = vote
+                    for o, obj in enumerate(objects):
+                        if cursor[o] < len(obj['p_centers']) and (obj['p_centers'][cursor[o]] == vote).all():
+                            t['peak_object'][n, c, j] = o
+                            t['kp_assigned'][n, o, c] += 1
+                            cursor[o] += 1
+                            break
+            for o, obj in enumerate(objects):
+                assert cursor[o] == len(obj['p_centers']), "vote reconstruction failed"
+        for o, obj in enumerate(objects):
+            for c in range(C):
+                kps = np.asarray(obj['keypoints'][c]).reshape(-1, 2)
+                t['kp_count'][n, o, c] = len(kps)
+                if c == 0:
+                    t['kp_assigned'][n, o, 0] = 1
+                for s in range(len(kps)):
+                    t['kp_xy'][n, o, c, s] = kps[s]
+                    t['kp_point'][n, o, c, s] = obj['p_C'][c][s]
+                    match = [j for j in range(t['peak_count'][n, c])
+                             if (t['peak_xy'][n, c, j] == kps[s].astype(np.float32)).all()]
+                    t['kp_peak'][n, o, c, s] = match[0] if match else -1
+    return t
+
+
+def camera_arrays(camera):
+    return {'cam_K': np.asarray(camera.K, np.float64), 'cam_D': np.asarray(camera.D, np.float64),
+            'cam_image_size': np.asarray(camera.image_size, np.float64)}
+
+
+def save(name, **arrays):
+    path = os.path.join(GOLDEN, name)
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {name}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def clean_frames(batch, cfg, cam_dict, wanted):
+    keep = []
+    for f in range(batch.heat.shape[0]):
+        ok, why = margins.frame_is_clean(batch.heat[f], batch.depth[f], batch.centers[f], cfg, cam_dict)
+        if ok:
+            keep.append(f)
+        if len(keep) == wanted:
+            break
+    assert len(keep) == wanted, f"only {len(keep)} clean frames"
+    return np.array(keep)
+
+
+def decode_case(ref, camera_utils, name, cfg, size, batch, wanted, seed):
+    camera = reference_camera(camera_utils, size)
+    cam_dict = np_oracle.camera_dict(camera)
+    keep = clean_frames(batch, cfg, cam_dict, wanted)
+    heat, depth, centers = batch.heat[keep], batch.depth[keep], batch.centers[keep]
+    tables = reference_tables(ref, camera, heat, depth, centers, cfg, seed)
+    save(name, heat=heat, depth=depth, centers=centers, keypoint_config=np.array(cfg, np.int32),
+         source_frames=keep, **camera_arrays(camera), **{'ref_' + k: v for k, v in tables.items()})
+    return tables
+
+
+# ----------------------------------------------------------------------------------------------
+def adversarial_frames(size=(64, 64)):
+    """Hand-built valve frames that sit ON the knife edges."""
+    H, W = size
+    cfg = [1, 3]
+    frames = []
+
+    def blank():
+        return (np.zeros((3, H, W), np.float32), np.zeros((3, H, W), np.float32),
+                np.zeros((2, 2, H, W), np.float32))
+
+    def blob(m, x, y, a=1.0, l=2.0):
+        jj = np.arange(W)[None, :]
+        ii = np.arange(H)[:, None]
+        m += (a * np.exp(-((x - jj) ** 2 + (y - ii) ** 2) / l ** 2)).astype(np.float32)
+
+    # 0: blob centred on a half pixel -> two tied peaks on the centre map
+    h, d, c = blank()
+    blob(h[0], 30.5, 20.0)
+    frames.append(('half_pixel_tie', h, d, c))
+    # 1: saturated plateau -> four tied peaks
+    h, d, c = blank()
+    blob(h[0], 40.5, 30.5, a=3.0, l=3.0)
+    np.clip(h, 0, 1, out=h)
+    frames.append(('plateau', h, d, c))
+    # 2: blobs on the border and in the corner (clipped centroid windows)
+    h, d, c = blank()
+    blob(h[0], 0.3, 0.2)
+    blob(h[1], W - 1.2, 30.0)
+    blob(h[2], 20.0, H - 0.6)
+    c[0, 0] = -30.0
+    c[0, 1] = -30.0
+    frames.append(('borders', h, d, c))
+    # 3: empty centre map but spokes present -> no objects
+    h, d, c = blank()
+    blob(h[1], 20.0, 20.0)
+    frames.append(('no_centres', h, d, c))
+    # 4: one centre, spoke votes land > 20 px away -> skipped
+    h, d, c = blank()
+    blob(h[0], 12.0, 12.0)
+    blob(h[1], 50.0, 50.0)
+    blob(h[2], 16.0, 12.0)
+    c[1, 0] = 12.0 - 16.5
+    c[1, 1] = 12.0 - 12.5
+    d[:] = 1.0
+    frames.append(('outlier_vote', h, d, c))
+    # 5: two detections of a cfg == 1 type for one object -> arg-max confidence wins
+    h, d, c = blank()
+    blob(h[0], 30.0, 30.0)
+    blob(h[1], 24.0, 30.0, a=0.9)
+    blob(h[1], 36.0, 30.0, a=0.7)
+    jj = np.arange(W)[None, :] + 0.5
+    ii = np.arange(H)[:, None] + 0.5
+    c[0, 0] = 30.0 - jj
+    c[0, 1] = 30.0 - ii
+    d[:] = 0.8
+    frames.append(('argmax_resolution', h, d, c))
+    # 6: everything exactly zero
+    h, d, c = blank()
+    frames.append(('all_zero', h, d, c))
+    # 7: constant map above threshold/25 -> interior plateau of equal sums, all kept
+    h, d, c = blank()
+    h[0, 20:28, 20:28] = 0.25
+    frames.append(('constant_patch', h, d, c))
+    names = [f[0] for f in frames]
+    heat = np.stack([f[1] for f in frames])
+    depth = np.stack([f[2] for f in frames])
+    centers = np.stack([f[3] for f in frames])
+    return names, cfg, heat, depth, centers
+
+
+def test_pipeline_frames(ref, camera_utils, video):
+    """The synthetic-heatmap recipe of test/test_pipeline.py:39-57,97-102 (valve, 180x320)."""
+    import cv2
+    params = camera_utils.load_calibration_params(os.path.join(ref_import.REFERENCE_ROOT, 'config', 'calibration.yaml'))
+    left = camera_utils.FisheyeCamera(params['K'], params['D'], params['image_size'])
+    right = camera_utils.FisheyeCamera(params['Kp'], params['Dp'], params['image_size'])
+    T_RL = params['T_RL']
+    kp = np.array([[0.0, 0.0, 1.0], [0.25, 0.15, 1.0], [-0.25, -0.25, 1.0], [0.25, -0.25, 1.0]])
+    keypoints = np.concatenate([kp.mean(axis=0)[None], kp])
+    cfg = [1, 3]
+    config = [1] + cfg
+    video.SceneDataset.kernel = video._compute_kernel(50, 25, 10.0)
+    full = np.zeros((2, len(config), 720, 1280))
+    pixels = [left.project(keypoints, np.eye(4)), right.project(keypoints, T_RL)]
+    for view in range(2):
+        current = 0
+        for m, count in enumerate(config):
+            for _ in range(count):
+                video.SceneDataset._add_kernel(full[view, m], pixels[view][current][None])
+                current += 1
+        full[view] /= full[view].max()
+    small = np.zeros((2, len(config), 180, 320), np.float32)
+    for view in range(2):
+        for m in range(len(config)):
+            small[view, m] = cv2.resize(full[view, m], (320, 180))
+    scale = 180.0 / 720.0
+    depth = np.zeros_like(small)
+    depth[0] = 1.0
+    depth[1] = 1.0
+    centers = np.zeros((2, 2, 2, 180, 320), np.float32)
+    jj = np.arange(320)[None, :] + 0.5
+    ii = np.arange(180)[:, None] + 0.5
+    for view in range(2):
+        centre_px = pixels[view][0] * scale
+        centers[view, :, 0] = centre_px[0] - jj
+        centers[view, :, 1] = centre_px[1] - ii
+    truth = np.stack(pixels) * scale
+    return cfg, small, depth, centers, truth, keypoints, left, right, T_RL
+
+
+def geometry_case(camera_utils):
+    """Projection / undistortion / two-view triangulation through the reference's camera classes
+    (OpenCV), including the golden pixel vectors of test/test_pipeline.py:26-33."""
+    import cv2
+    rng = np.random.default_rng(7)
+    stereo = camera_utils.StereoCamera.from_file(os.path.join(ref_import.REFERENCE_ROOT, 'config', 'calibration.yaml'))
+    left, right = stereo.left_camera, stereo.right_camera
+    out = {}
+    X = np.stack([rng.uniform(-0.6, 0.6, 256), rng.uniform(-0.35, 0.35, 256), rng.uniform(0.4, 2.0, 256)], axis=1)
+    T = np.eye(4)
+    T[:3, :3] = cv2.Rodrigues(np.array([0.05, -0.1, 0.02]))[0]
+    T[:3, 3] = [0.03, -0.02, 0.1]
+    out['X'] = X
+    out['T_CW'] = T
+    out['project_left'] = left.project(X, T)
+    out['project_right'] = right.project(X, stereo.T_RL @ T)
+    for cam, tag in ((left, 'full'), (left.scale(180 / 720), 'small'),
+                     (reference_camera(camera_utils, (64, 64)), 'net')):
+        H, W = np.asarray(cam.image_size)
+        px = np.stack([rng.uniform(0, W, 512), rng.uniform(0, H, 512)], axis=1)
+        out[f'undistort_in_{tag}'] = px
+        out[f'undistort_out_{tag}'] = cam.undistort(px)
+        out[f'undistort_out32_{tag}'] = cam.undistort(px.astype(np.float32))
+        out[f'K_{tag}'] = cam.K
+        out[f'D_{tag}'] = cam.D
+        out[f'image_size_{tag}'] = np.asarray(cam.image_size, np.float64)
+    # golden vectors printed in test/test_pipeline.py:9-12,26-33
+    kp = np.array([[0.0, 0.0, 1.1], [0.1, 0.0, 1.0], [-0.1, 0.0, 1.0]])
+    keypoints = np.concatenate([kp.mean(axis=0)[None], kp])
+    pl = np.array([[641.00771598, 368.16440843], [641.00771598, 368.16440843],
+                   [710.73402561, 368.16440843], [571.28140636, 368.16440843]])
+    pr = np.array([[600.68550127, 360.58934273], [603.22381954, 360.59871037],
+                   [668.67557233, 360.56260433], [530.24191134, 360.61583473]])
+    out['golden_keypoints'] = keypoints
+    out['golden_left'] = pl
+    out['golden_right'] = pr
+    out['golden_stereo_triangulate'] = stereo.triangulate(pl, pr)
+    # noisy pairs: StereoCamera.triangulate (with correctMatches) and plain DLT (label.py:296-305)
+    XL = X[:128]
+    pL = left.project(XL, np.eye(4)) + rng.normal(0, 0.3, (128, 2))
+    pR = right.project(XL, stereo.T_RL) + rng.normal(0, 0.3, (128, 2))
+    out['pairs_X'] = XL
+    out['pairs_left'] = pL
+    out['pairs_right'] = pR
+    out['pairs_stereo_triangulate'] = stereo.triangulate(pL, pR)
+    uL = left.undistort(pL)
+    uR = right.undistort(pR)
+    P1 = left.K @ np.eye(3, 4)
+    P2 = right.K @ stereo.T_RL[:3]
+    Xh = cv2.triangulatePoints(P1, P2, uL.T, uR.T).T
+    out['pairs_plain_dlt'] = Xh[:, :3] / Xh[:, 3:4]
+    cl, cr = cv2.correctMatches(stereo.F, uL[None].astype(np.float64), uR[None].astype(np.float64))
+    out['pairs_corrected_left'] = cl[0]
+    out['pairs_corrected_right'] = cr[0]
+    out['pairs_undistorted_left'] = uL
+    out['pairs_undistorted_right'] = uR
+    out['P1'] = P1
+    out['P2'] = P2
+    out['F'] = stereo.F
+    out['T_RL'] = stereo.T_RL
+    out['K_left'] = left.K
+    out['D_left'] = left.D
+    out['K_right'] = right.K
+    out['D_right'] = right.D
+    return out
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref, camera_utils, video = ref_import.load()
+
+    # 1-2: model-resolution clean sets (bit-exact parity)
+    valve = synthetic.make_batch(48, [1, 3], (64, 64), seed=1001, objects=(1, 2))
+    decode_case(ref, camera_utils, 'valve_64.npz', [1, 3], (64, 64), valve, 24, seed=11)
+    cups = synthetic.make_batch(64, [1, 1, 1], (64, 64), seed=1002, objects=(1, 4))
+    decode_case(ref, camera_utils, 'cups_64.npz', [1, 1, 1], (64, 64), cups, 24, seed=12)
+
+    # 3: 180x320, eight valves on a grid (config 3 frames)
+    grid = synthetic.make_grid_batch(6, [1, 3], (180, 320), seed=1003)
+    decode_case(ref, camera_utils, 'valve_grid_180x320.npz', [1, 3], (180, 320), grid, 2, seed=13)
+
+    # 4: knife edges -- compared with set / flag semantics
+    names, cfg, heat, depth, centers = adversarial_frames()
+    camera = reference_camera(camera_utils, (64, 64))
+    tables = reference_tables(ref, camera, heat, depth, centers, cfg, seed=14)
+    save('adversarial_64.npz', heat=heat, depth=depth, centers=centers, names=np.array(names),
+         keypoint_config=np.array(cfg, np.int32), **camera_arrays(camera),
+         **{'ref_' + k: v for k, v in tables.items()})
+
+    # 5: the reference's own test recipe (test_pipeline.py)
+    cfg, heat, depth, centers, truth, keypoints, left, right, T_RL = test_pipeline_frames(ref, camera_utils, video)
+    camera = left.scale(180 / 720)
+    tables = reference_tables(ref, camera, heat, depth, centers, cfg, seed=15)
+    save('test_pipeline_180x320.npz', heat=heat, depth=depth, centers=centers, truth_pixels=truth,
+         keypoints_3d=keypoints, T_RL=T_RL, keypoint_config=np.array(cfg, np.int32),
+         **camera_arrays(camera), **{'ref_' + k: v for k, v in tables.items()})
+
+    # 6: full box-sum maps straight from torch's conv2d (bitwise pin of the summation order)
+    ones = torch.ones((1, 1, 5, 5), dtype=torch.float32)
+    maps = np.concatenate([valve.heat[:2].reshape(-1, 64, 64), cups.heat[:1].reshape(-1, 64, 64)])
+    sums = torch.nn.functional.conv2d(torch.tensor(maps)[:, None], ones, padding=2)[:, 0].numpy()
+    big = grid.heat[0, :1]
+    big_sums = torch.nn.functional.conv2d(torch.tensor(big)[:, None], ones, padding=2)[:, 0].numpy()
+    save('boxsum.npz', maps=maps, sums=sums, big=big, big_sums=big_sums)
+
+    # 7: camera geometry and triangulation
+    save('geometry.npz', **geometry_case(camera_utils))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,353 @@
+"""TEST INFRASTRUCTURE -- NumPy restatement of the reference's heatmap -> 3D keypoint path.
+
+This module is the *checker*, never the product: only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s CPU-baseline legs may import it. Every function cites the reference lines
+(relative to /root/reference) it restates. It is pinned against outputs of the unmodified
+reference (``oracle/make_goldens.py`` -> ``tests/golden/*.npz``) by ``tests/test_oracle.py``.
+
+Arithmetic contract shared with the C oracle (``okp_oracle.c``) and the CUDA kernels:
+
+* box sum: 25 float32 additions per pixel in raster tap order (dy outer, dx inner), zero
+  outside the image -- bitwise what torch's CPU conv2d with a 5x5 ones kernel returns
+  (verified in SURVEY.md section 7 and again by make_goldens.py);
+* NMS: exact float equality with the 5x5 maximum (-inf outside), all ties kept;
+* centroid / confidence: float32, raster order over the border-clipped 5x5 window, products
+  and sums rounded separately (no FMA);
+* grouping distances, votes, undistortion, unprojection: float64.
+"""
+import numpy as np
+
+FLAG_PEAK_OVERFLOW = 1      # more peaks on a map than the table holds
+FLAG_OBJECT_OVERFLOW = 2    # more centre peaks than max_objects
+FLAG_OUTLIER_SKIPPED = 4    # a spoke voted > outlier_distance from every centre (pipeline.py:121-124)
+FLAG_CLUSTERED = 8          # > cfg[t] detections with cfg[t] > 1: resolved by clustering (pipeline.py:143-148)
+FLAG_VOTE_OVERFLOW = 16     # more votes for one object than max_votes
+FLAG_NO_CENTERS = 32        # empty centre map: no objects (pipeline.py:105-106)
+FLAG_ARGMAX_RESOLVED = 64   # > cfg[t] detections with cfg[t] == 1: kept the most confident (pipeline.py:139-142)
+
+F32 = np.float32
+
+
+# ------------------------------------------------------------------------------------------
+# A2-A4: box sum, NMS, threshold (perception/pipeline.py:69-73, perception/models.py:55-58)
+# ------------------------------------------------------------------------------------------
+def box_sum(p, size=5):
+    """conv2d(p, ones(size, size), padding=size//2) with sequential float32 accumulation."""
+    p = np.asarray(p, dtype=F32)
+    H, W = p.shape
+    r = size // 2
+    padded = np.zeros((H + 2 * r, W + 2 * r), dtype=F32)
+    padded[r:r + H, r:r + W] = p
+    acc = np.zeros((H, W), dtype=F32)
+    for dy in range(size):
+        for dx in range(size):
+            acc = acc + padded[dy:dy + H, dx:dx + W]        # one float32 rounding per tap
+    return acc
+
+
+def window_max(b, size=5):
+    """max_pool2d(b, size, stride 1, padding size//2): padding value is -inf."""
+    H, W = b.shape
+    r = size // 2
+    padded = np.full((H + 2 * r, W + 2 * r), -np.inf, dtype=F32)
+    padded[r:r + H, r:r + W] = b
+    out = np.full((H, W), -np.inf, dtype=F32)
+    for dy in range(size):
+        for dx in range(size):
+            out = np.maximum(out, padded[dy:dy + H, dx:dx + W])
+    return out
+
+
+def find_peaks(p, threshold=0.5, nms_size=5, use_box_sum=True):
+    """Pixels (y, x) in raster order whose (box-summed) value equals the window maximum and
+    exceeds the threshold; also returns the score map."""
+    score = box_sum(p) if use_box_sum else np.asarray(p, dtype=F32)
+    keep = score == window_max(score, nms_size)
+    suppressed = score * keep.astype(F32)
+    ys, xs = np.nonzero(suppressed > F32(threshold))          # np.nonzero is row-major
+    return np.stack([ys, xs], axis=1).astype(np.int32), score
+
+
+# ------------------------------------------------------------------------------------------
+# A5: sub-pixel centroid (perception/pipeline.py:46-62)
+# ------------------------------------------------------------------------------------------
+def centroid(p, y, x):
+    """Probability-weighted mean pixel index over the clipped 5x5 window -> ((x, y), conf)."""
+    H, W = p.shape
+    sy = F32(0.0)
+    sx = F32(0.0)
+    s = F32(0.0)
+    for i in range(max(y - 2, 0), min(y + 3, H)):
+        for j in range(max(x - 2, 0), min(x + 3, W)):
+            v = F32(p[i, j])
+            sy = F32(sy + F32(v * F32(i)))
+            sx = F32(sx + F32(v * F32(j)))
+            s = F32(s + v)
+    return np.array([F32(sx / s), F32(sy / s)], dtype=F32), s
+
+
+# ------------------------------------------------------------------------------------------
+# A7: equidistant undistortion, float64 (camera_utils.py:75-81 -> cv::fisheye::undistortPoints)
+# ------------------------------------------------------------------------------------------
+def undistort_point(u, v, cam):
+    fx, fy, cx, cy = cam['fx'], cam['fy'], cam['cx'], cam['cy']
+    k1, k2, k3, k4 = cam['k']
+    px = (u - cx) / fx
+    py = (v - cy) / fy
+    theta_d = np.sqrt(px * px + py * py)
+    theta_d = min(max(-np.pi / 2.0, theta_d), np.pi / 2.0)
+    theta = theta_d
+    scale = 0.0
+    converged = False
+    if abs(theta_d) > 1e-8:
+        for _ in range(10):
+            t2 = theta * theta
+            t4 = t2 * t2
+            t6 = t4 * t2
+            t8 = t6 * t2
+            a, b, c, d = k1 * t2, k2 * t4, k3 * t6, k4 * t8
+            fix = (theta * (1 + a + b + c + d) - theta_d) / (1 + 3 * a + 5 * b + 7 * c + 9 * d)
+            theta = theta - fix
+            if abs(fix) < 1e-8:
+                converged = True
+                break
+        scale = np.tan(theta) / theta_d
+    else:
+        converged = True
+    flipped = (theta_d < 0 and theta > 0) or (theta_d > 0 and theta < 0)
+    if converged and not flipped:
+        return fx * (px * scale) + cx, fy * (py * scale) + cy
+    return -1000000.0, -1000000.0
+
+
+def camera_dict(camera):
+    """Pack a camera object (K, D, Kinv, image_size) into the plain dict the oracle uses."""
+    size = np.asarray(camera.image_size)
+    return {
+        'fx': float(camera.K[0, 0]), 'fy': float(camera.K[1, 1]),
+        'cx': float(camera.K[0, 2]), 'cy': float(camera.K[1, 2]),
+        'k': [float(v) for v in np.asarray(camera.D)[:4]],
+        'kinv': np.asarray(camera.Kinv, dtype=np.float64).copy(),
+        # pipeline.py:161-162: max_index = image_size.astype(int) - 1, i.e. (H-1, W-1),
+        # later applied to (x, y) -- x is clipped with the HEIGHT.
+        'clip_x': int(size[0]) - 1, 'clip_y': int(size[1]) - 1,
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# A8: DetectionToPoint (pipeline.py:155-171) + PinholeCamera.unproject (camera_utils.py:31-34)
+# ------------------------------------------------------------------------------------------
+def detection_to_point(xy, depth_map, cam, compat_clip_bug=True):
+    """xy float32 (x, y) -> camera-frame point float64 [3]."""
+    H, W = depth_map.shape
+    ux, uy = undistort_point(float(xy[0]), float(xy[1]), cam)
+    ux, uy = F32(ux), F32(uy)                     # OpenCV returns float32 for float32 input
+    xi = int(np.rint(ux))
+    yi = int(np.rint(uy))
+    if compat_clip_bug:
+        xi = min(max(xi, 0), cam['clip_x'])
+        yi = min(max(yi, 0), cam['clip_y'])
+    # the reference would raise IndexError beyond the map; stay inside it
+    xi = min(max(xi, 0), W - 1)
+    yi = min(max(yi, 0), H - 1)
+    z = float(depth_map[yi, xi])
+    kinv = cam['kinv']
+    hx, hy = float(ux), float(uy)
+    ray = np.array([kinv[r, 0] * hx + kinv[r, 1] * hy + kinv[r, 2] for r in range(3)])
+    return ray * z
+
+
+# ------------------------------------------------------------------------------------------
+# deterministic replacement for the unseeded KMeans(init='random') of pipeline.py:146-148
+# ------------------------------------------------------------------------------------------
+def cluster_detections(points, k, iters=16):
+    """Lloyd's algorithm from every k-subset of the detections as initial centres; the
+    partition with the smallest inertia wins (first subset on ties). For the handful of
+    detections this branch ever sees that is the global k-means optimum, which is what the
+    reference's 10 random restarts converge to on well separated input. float64 arithmetic,
+    centres returned in order of their initial detections. PARITY UNPINNED (nondeterministic
+    in the reference)."""
+    from itertools import combinations
+    pts = np.asarray(points, dtype=np.float64)
+    n = pts.shape[0]
+    best = None
+    for subset in combinations(range(n), k):
+        cen = pts[list(subset)].copy()
+        assign = None
+        for _ in range(iters):
+            d = ((pts[:, None, :] - cen[None, :, :]) ** 2).sum(axis=2)
+            new_assign = d.argmin(axis=1)
+            if assign is not None and (new_assign == assign).all():
+                break
+            assign = new_assign
+            for c in range(k):
+                members = pts[assign == c]
+                if len(members):
+                    cen[c] = members.sum(axis=0) / len(members)
+        d = ((pts[:, None, :] - cen[None, :, :]) ** 2).sum(axis=2)
+        inertia = d.min(axis=1).sum()
+        if best is None or inertia < best[0]:
+            best = (inertia, cen.copy())
+    return best[1].astype(F32)
+
+
+# ------------------------------------------------------------------------------------------
+# A0/A6: the whole decode for a batch of frames -> fixed-capacity record tables
+# ------------------------------------------------------------------------------------------
+def decode(heat, depth, centers, keypoint_config, cam, max_peaks=32, max_objects=16,
+           max_votes=16, threshold=0.5, outlier_distance=20.0, compat_clip_bug=True,
+           with_points=True):
+    """heat [N,C,H,W], depth [N,C,H,W], centers [N,T,2,H,W] (float32) -> dict of arrays laid
+    out exactly like the device record tables (include/okp.h)."""
+    heat = np.asarray(heat, dtype=F32)
+    N, C, H, W = heat.shape
+    T = C - 1
+    cfg = [1] + list(keypoint_config)                       # pipeline.py:36
+    assert len(cfg) == C
+    S = max(cfg)
+    K, O, V = max_peaks, max_objects, max_votes
+    out = {
+        'peak_count': np.zeros((N, C), np.int32),
+        'peak_yx': np.full((N, C, K, 2), -1, np.int32),
+        'peak_score': np.zeros((N, C, K), F32),
+        'peak_xy': np.zeros((N, C, K, 2), F32),
+        'peak_conf': np.zeros((N, C, K), F32),
+        'peak_object': np.full((N, C, K), -1, np.int32),
+        'peak_vote': np.zeros((N, C, K, 2), np.float64),
+        'n_objects': np.zeros((N,), np.int32),
+        'flags': np.zeros((N,), np.uint32),
+        'kp_assigned': np.zeros((N, O, C), np.int32),
+        'kp_count': np.zeros((N, O, C), np.int32),
+        'kp_peak': np.full((N, O, C, S), -1, np.int32),
+        'kp_xy': np.zeros((N, O, C, S, 2), F32),
+        'kp_point': np.zeros((N, O, C, S, 3), np.float64),
+        'n_votes': np.zeros((N, O), np.int32),
+        'votes': np.zeros((N, O, V, 2), np.float64),
+    }
+    for n in range(N):
+        flags = 0
+        # ---- peaks (A2-A5), every map -------------------------------------------------------
+        for c in range(C):
+            yx, score = find_peaks(heat[n, c], threshold)
+            out['peak_count'][n, c] = len(yx)
+            if len(yx) > K:
+                flags |= FLAG_PEAK_OVERFLOW
+            for k, (y, x) in enumerate(yx[:K]):
+                xy, conf = centroid(heat[n, c], int(y), int(x))
+                out['peak_yx'][n, c, k] = (y, x)
+                out['peak_score'][n, c, k] = score[y, x]
+                out['peak_xy'][n, c, k] = xy
+                out['peak_conf'][n, c, k] = conf
+        # ---- objects = centre peaks (pipeline.py:105-114) ------------------------------------
+        n_center = min(int(out['peak_count'][n, 0]), K)
+        if n_center == 0:
+            flags |= FLAG_NO_CENTERS
+            out['flags'][n] = flags
+            continue
+        if n_center > O:
+            flags |= FLAG_OBJECT_OVERFLOW
+        n_obj = min(n_center, O)
+        out['n_objects'][n] = n_obj
+        center_xy = out['peak_xy'][n, 0, :n_obj].astype(np.float64)
+        members = [[[] for _ in range(C)] for _ in range(n_obj)]
+        for o in range(n_obj):
+            members[o][0].append(o)
+            out['peak_object'][n, 0, o] = o
+        # ---- spoke assignment (pipeline.py:115-128) ------------------------------------------
+        for t in range(T):
+            c = 1 + t
+            for k in range(min(int(out['peak_count'][n, c]), K)):
+                px, py = out['peak_xy'][n, c, k]
+                xi = min(max(int(np.rint(px)), 0), W - 1)              # np.round: half to even
+                yi = min(max(int(np.rint(py)), 0), H - 1)
+                vote = np.array([xi + 0.5 + float(centers[n, t, 0, yi, xi]),
+                                 yi + 0.5 + float(centers[n, t, 1, yi, xi])])
+                out['peak_vote'][n, c, k] = vote
+                dx = center_xy[:, 0] - vote[0]
+                dy = center_xy[:, 1] - vote[1]
+                dist = np.sqrt(dx * dx + dy * dy)
+                if dist.min() > outlier_distance:
+                    flags |= FLAG_OUTLIER_SKIPPED
+                    continue
+                o = int(dist.argmin())                                  # first minimum
+                out['peak_object'][n, c, k] = o
+                members[o][c].append(k)
+                if out['n_votes'][n, o] < V:
+                    out['votes'][n, o, out['n_votes'][n, o]] = vote
+                else:
+                    flags |= FLAG_VOTE_OVERFLOW
+                out['n_votes'][n, o] += 1
+        # ---- per (object, type) resolution (pipeline.py:130-152) + 3D (pipeline.py:190-194) --
+        for o in range(n_obj):
+            for c in range(C):
+                idx = members[o][c]
+                out['kp_assigned'][n, o, c] = len(idx)
+                if len(idx) == 0:
+                    continue
+                if len(idx) > cfg[c]:
+                    if cfg[c] == 1:
+                        conf = out['peak_conf'][n, c, idx]
+                        idx = [idx[int(conf.argmax())]]                  # first maximum
+                        flags |= FLAG_ARGMAX_RESOLVED
+                        pts = out['peak_xy'][n, c, idx]
+                    else:
+                        flags |= FLAG_CLUSTERED
+                        pts = cluster_detections(out['peak_xy'][n, c, idx], cfg[c])
+                        idx = [-1] * cfg[c]
+                else:
+                    pts = out['peak_xy'][n, c, idx]
+                out['kp_count'][n, o, c] = len(idx)
+                for s, (k, xy) in enumerate(zip(idx, pts)):
+                    out['kp_peak'][n, o, c, s] = k
+                    out['kp_xy'][n, o, c, s] = xy
+                    if with_points:
+                        out['kp_point'][n, o, c, s] = detection_to_point(
+                            xy, depth[n, c], cam, compat_clip_bug)
+        out['flags'][n] = flags
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# A11: equidistant projection (camera_utils.py:65-73 -> cv::fisheye::projectPoints)
+# ------------------------------------------------------------------------------------------
+def project_points(X, T_CW, cam):
+    X = np.asarray(X, dtype=np.float64)
+    Xc = X @ np.asarray(T_CW)[:3, :3].T + np.asarray(T_CW)[:3, 3]
+    a = Xc[:, 0] / Xc[:, 2]
+    b = Xc[:, 1] / Xc[:, 2]
+    r = np.sqrt(a * a + b * b)
+    theta = np.arctan(r)
+    t2 = theta * theta
+    k1, k2, k3, k4 = cam['k']
+    theta_d = theta * (1.0 + k1 * t2 + k2 * t2 ** 2 + k3 * t2 ** 3 + k4 * t2 ** 4)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        s = np.where(r > 1e-8, theta_d / r, 1.0)
+    return np.stack([cam['fx'] * (a * s) + cam['cx'], cam['fy'] * (b * s) + cam['cy']], axis=1)
+
+
+# ------------------------------------------------------------------------------------------
+# A12/A14: DLT triangulation (camera_utils.py:103-108, scripts/label.py:296-305), any V >= 2
+# ------------------------------------------------------------------------------------------
+def triangulate_dlt(points, valid, projections):
+    """points [P,V,2] undistorted pixels, valid [P,V] bool, projections [V,3,4] (or [P,V,3,4])
+    -> X [P,3]: right singular vector of the smallest singular value of the stacked
+    (x P[2] - P[0], y P[2] - P[1]) rows, dehomogenised. cv2.triangulatePoints at V = 2."""
+    points = np.asarray(points, dtype=np.float64)
+    Pn, Vn = points.shape[:2]
+    projections = np.asarray(projections, dtype=np.float64)
+    X = np.full((Pn, 3), np.nan)
+    for p in range(Pn):
+        rows = []
+        for v in range(Vn):
+            if not valid[p, v]:
+                continue
+            M = projections[p, v] if projections.ndim == 4 else projections[v]
+            x, y = points[p, v]
+            rows.append(x * M[2] - M[0])
+            rows.append(y * M[2] - M[1])
+        if len(rows) < 4:
+            continue
+        _, _, vt = np.linalg.svd(np.array(rows))
+        h = vt[-1]
+        X[p] = h[:3] / h[3]
+    return X

@@ -1,0 +1,120 @@
+"""The oracle is only worth something if it is pinned to the reference: these tests compare
+both restatements (NumPy, C) with fixtures produced by the UNMODIFIED reference pipeline
+(oracle/make_goldens.py) and with each other. CPU only."""
+import numpy as np
+import pytest
+
+from helpers import (load_golden, golden_camera, reference_tables, assert_tables_match)
+from oracle import np_oracle, c_oracle
+
+DECODE_FIXTURES = ['valve_64.npz', 'cups_64.npz', 'valve_grid_180x320.npz', 'test_pipeline_180x320.npz',
+                   'adversarial_64.npz']
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def test_box_sum_is_bitwise_torch_conv2d():
+    """Summation order contract: 25 sequential float32 adds == torch CPU conv2d with ones(5,5)."""
+    g = load_golden('boxsum.npz')
+    for m, s in zip(g['maps'], g['sums']):
+        assert np.array_equal(bits(np_oracle.box_sum(m)), bits(s))
+    assert np.array_equal(bits(np_oracle.box_sum(g['big'][0])), bits(g['big_sums'][0]))
+
+
+@pytest.mark.parametrize('name', DECODE_FIXTURES)
+def test_numpy_oracle_matches_reference(name):
+    g = load_golden(name)
+    cam = np_oracle.camera_dict(golden_camera(g))
+    got = np_oracle.decode(g['heat'], g['depth'], g['centers'], list(g['keypoint_config']), cam)
+    assert_tables_match(got, reference_tables(g))
+
+
+@pytest.mark.parametrize('name', DECODE_FIXTURES)
+def test_c_oracle_matches_reference_and_numpy(name):
+    g = load_golden(name)
+    camera = golden_camera(g)
+    cfg = list(g['keypoint_config'])
+    got = c_oracle.decode(g['heat'], g['depth'], g['centers'], cfg, camera)
+    assert_tables_match(got, reference_tables(g))
+    again = np_oracle.decode(g['heat'], g['depth'], g['centers'], cfg, np_oracle.camera_dict(camera))
+    for key, value in got.items():
+        assert np.array_equal(bits(value), bits(again[key])), f"C and NumPy oracle differ on {key}"
+
+
+def test_adversarial_flags_and_counts():
+    g = load_golden('adversarial_64.npz')
+    names = [str(n) for n in g['names']]
+    got = c_oracle.decode(g['heat'], g['depth'], g['centers'], list(g['keypoint_config']), golden_camera(g))
+    ref = reference_tables(g)
+    by = {n: i for i, n in enumerate(names)}
+    assert got['peak_count'][by['half_pixel_tie'], 0] == 2          # both tied pixels kept
+    assert got['peak_count'][by['plateau'], 0] == 4
+    assert got['peak_count'][by['constant_patch'], 0] == 16         # every pixel of the plateau
+    assert got['flags'][by['no_centres']] & np_oracle.FLAG_NO_CENTERS
+    assert got['flags'][by['all_zero']] & np_oracle.FLAG_NO_CENTERS
+    assert got['flags'][by['argmax_resolution']] & np_oracle.FLAG_ARGMAX_RESOLVED
+    # the reference prints one line per skipped vote (pipeline.py:123)
+    skipped = ((got['peak_object'][:, 1:] == -1) &
+               (np.arange(got['peak_object'].shape[2])[None, None] < got['peak_count'][:, 1:, None])).sum(axis=(1, 2))
+    has_objects = got['n_objects'] > 0
+    np.testing.assert_array_equal(skipped[has_objects], ref['n_skipped'][has_objects])
+    assert (got['flags'][ref['n_skipped'] > 0] & np_oracle.FLAG_OUTLIER_SKIPPED).all()
+
+
+def test_centroid_is_much_tighter_than_tolerance():
+    g = load_golden('valve_64.npz')
+    got = c_oracle.decode(g['heat'], g['depth'], g['centers'], list(g['keypoint_config']), golden_camera(g))
+    ref = reference_tables(g)
+    assert np.abs(got['peak_xy'] - ref['peak_xy']).max() < 5e-5
+
+
+def test_geometry_against_opencv_goldens():
+    from object_keypoints_b200 import camera_utils
+    g = load_golden('geometry.npz')
+    left = camera_utils.FisheyeCamera(g['K_left'], g['D_left'], [720, 1280])
+    right = camera_utils.FisheyeCamera(g['K_right'], g['D_right'], [720, 1280])
+    assert np.abs(c_oracle.project(g['X'], g['T_CW'], left) - g['project_left']).max() < 1e-9
+    assert np.abs(c_oracle.project(g['X'], g['T_RL'] @ g['T_CW'], right) - g['project_right']).max() < 1e-9
+    assert np.abs(left.project(g['X'], g['T_CW']) - g['project_left']).max() < 1e-9
+    for tag in ['full', 'small', 'net']:
+        cam = camera_utils.FisheyeCamera(g[f'K_{tag}'], g[f'D_{tag}'], g[f'image_size_{tag}'])
+        assert np.abs(c_oracle.undistort(g[f'undistort_in_{tag}'], cam) - g[f'undistort_out_{tag}']).max() < 1e-9
+        assert np.abs(cam.undistort(g[f'undistort_in_{tag}']) - g[f'undistort_out_{tag}']).max() < 1e-9
+        out32 = c_oracle.undistort(g[f'undistort_in_{tag}'].astype(np.float32).astype(np.float64), cam, round_to_f32=True)
+        assert np.array_equal(out32.astype(np.float32), g[f'undistort_out32_{tag}'])
+
+
+def test_dlt_against_opencv_goldens():
+    g = load_golden('geometry.npz')
+    pts = np.stack([g['pairs_undistorted_left'], g['pairs_undistorted_right']], axis=1)
+    proj = np.stack([g['P1'], g['P2']])
+    want = g['pairs_plain_dlt']
+    for got in (np_oracle.triangulate_dlt(pts, np.ones(pts.shape[:2], bool), proj),
+                c_oracle.triangulate(pts, None, proj)):
+        rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert rel.max() < 1e-9
+
+
+def test_golden_pixel_vectors_of_reference_test_suite():
+    """test/test_pipeline.py:26-33,171-177: triangulating the printed pixel vectors gives the
+    3D points back within 1e-3 m."""
+    from object_keypoints_b200 import camera_utils
+    g = load_golden('geometry.npz')
+    left = camera_utils.FisheyeCamera(g['K_left'], g['D_left'], [720, 1280])
+    right = camera_utils.FisheyeCamera(g['K_right'], g['D_right'], [720, 1280])
+    uL = c_oracle.undistort(g['golden_left'], left)
+    uR = c_oracle.undistort(g['golden_right'], right)
+    X = c_oracle.triangulate(np.stack([uL, uR], axis=1), None, np.stack([g['P1'], g['P2']]))
+    assert np.linalg.norm(X - g['golden_keypoints'], axis=1).max() < 1e-3
+    # and the pixels themselves are the projections of those points (re-derived to all digits)
+    assert np.abs(c_oracle.project(g['golden_keypoints'], np.eye(4), left) - g['golden_left']).max() < 1e-7
+    assert np.abs(c_oracle.project(g['golden_keypoints'], g['T_RL'], right) - g['golden_right']).max() < 1e-7
+
+
+def test_kmeans_stand_in_merges_double_detection():
+    pts = np.array([[10.0, 10.0], [10.6, 10.2], [20.0, 10.0], [10.0, 22.0]], np.float32)
+    cen = np_oracle.cluster_detections(pts, 3)
+    want = np.array([[10.3, 10.1], [20.0, 10.0], [10.0, 22.0]])
+    assert np.abs(np.sort(cen, axis=0) - np.sort(want, axis=0)).max() < 1e-5
