@@ -1,0 +1,228 @@
+// okp_api.cu -- the extern "C" surface of libokp.so (declared in include/okp.h): argument
+// checking, launch planning, kernel launches. No allocation, no global state, no implicit sync.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "okp_common.cuh"
+#include "okp_peaks.cuh"
+#include "okp_peaks_strip.cuh"
+#include "okp_geometry.cuh"
+#include "okp_group.cuh"
+#include "okp_dlt.cuh"
+
+namespace {
+
+constexpr int kSmCount = 148;            // B200: 2 dies x 74 SMs
+
+struct PeakPlan {
+    int kernel;                          // 0 = generic tile kernel, 1 = strip kernel
+    OkpTileGeometry geo;
+    size_t smem_bytes;
+    int grid;
+    int tiles_per_map;
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+PeakPlan plan_peaks(int maps, int H, int W, int K) {
+    PeakPlan p;
+    memset(&p, 0, sizeof(p));
+    p.geo.H = H; p.geo.W = W; p.geo.maps = maps;
+    if (okp_strip_plan(maps, H, W, K, &p.geo, &p.smem_bytes)) {
+        p.kernel = 1;
+    } else {
+        p.kernel = 0;
+        p.geo.TW = W <= 64 ? round_up(W, 8) : 64;
+        p.geo.TH = H <= 64 ? H : 32;
+        p.geo.tiles_x = (W + p.geo.TW - 1) / p.geo.TW;
+        p.geo.tiles_y = (H + p.geo.TH - 1) / p.geo.TH;
+        p.smem_bytes = sizeof(float) * ((size_t)(p.geo.TH + 8) * (p.geo.TW + 8) + (size_t)(p.geo.TH + 4) * (p.geo.TW + 4)) +
+                       sizeof(int32_t) * 2 * (size_t)K;
+    }
+    p.tiles_per_map = p.geo.tiles_x * p.geo.tiles_y;
+    const long long work = (long long)maps * p.tiles_per_map;
+    const long long resident = (long long)kSmCount * 8;
+    p.grid = (int)(work < resident ? work : resident);
+    if (p.grid < 1) p.grid = 1;
+    return p;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_params(const OkpDecodeParams* prm) {
+    if (!prm) return OKP_E_NULL;
+    if (prm->max_peaks < 1 || prm->max_peaks > OKP_MAX_PEAKS) return OKP_E_CAPACITY;
+    if (prm->max_objects < 1 || prm->max_objects > OKP_MAX_OBJECTS) return OKP_E_CAPACITY;
+    if (prm->max_votes < 1 || prm->max_votes > 4096) return OKP_E_CAPACITY;
+    if (prm->nms_size != 5 || prm->box_sum != 1) return OKP_E_UNSUPPORTED;
+    return OKP_OK;
+}
+
+int check_shape(int N, int C, int H, int W) {
+    if (N < 0 || C < 1 || C > OKP_MAX_MAPS || H < 1 || W < 1) return OKP_E_SHAPE;
+    if ((long long)H * W > (1LL << 30)) return OKP_E_SHAPE;      // the raster key y * W + x is an int32
+    return OKP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int okp_version(void) { return OKP_VERSION_MAJOR * 1000 + OKP_VERSION_MINOR; }
+
+const char* okp_strerror(int code) {
+    switch (code) {
+        case OKP_OK: return "ok";
+        case OKP_E_NULL: return "a required pointer is NULL";
+        case OKP_E_SHAPE: return "shape out of the supported range";
+        case OKP_E_CAPACITY: return "max_peaks / max_objects / max_votes out of range";
+        case OKP_E_UNSUPPORTED: return "parameter combination not implemented";
+        case OKP_E_CUDA: return "CUDA runtime call or kernel launch failed";
+        case OKP_E_WORKSPACE: return "workspace too small (see okp_decode_workspace_bytes)";
+        default: return "unknown error code";
+    }
+}
+
+size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodeParams* params) {
+    if (check_params(params) != OKP_OK || check_shape(N, C, H, W) != OKP_OK) return 0;
+    const PeakPlan p = plan_peaks(N * C, H, W, params->max_peaks);
+    const size_t tiles = (size_t)N * C * p.tiles_per_map;
+    return align_up(tiles * sizeof(int32_t), 256) + tiles * params->max_peaks * sizeof(OkpPeakRecord) + 256;
+}
+
+int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
+                          const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    int rc = check_params(params);
+    if (rc != OKP_OK) return rc;
+    rc = check_shape(N, C, H, W);
+    if (rc != OKP_OK) return rc;
+    if (N == 0) return OKP_OK;
+    if (!heat_dev || !tables || !workspace_dev) return OKP_E_NULL;
+    if (!tables->peak_count || !tables->peak_yx || !tables->peak_score || !tables->peak_xy || !tables->peak_conf ||
+        !tables->peak_object || !tables->peak_vote)
+        return OKP_E_NULL;
+    if (workspace_bytes < okp_decode_workspace_bytes(N, C, H, W, params)) return OKP_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int K = params->max_peaks;
+    const int maps = N * C;
+    const PeakPlan p = plan_peaks(maps, H, W, K);
+    const size_t tiles = (size_t)maps * p.tiles_per_map;
+    uintptr_t base = align_up((uintptr_t)workspace_dev, 256);
+    int32_t* tile_count = (int32_t*)base;
+    OkpPeakRecord* tile_peaks = (OkpPeakRecord*)(base + align_up(tiles * sizeof(int32_t), 256));
+
+    if (p.kernel == 1) {
+        rc = okp_strip_launch(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks, p.smem_bytes, s);
+        if (rc != OKP_OK) return rc;
+    } else {
+        auto kernel = okp_peaks_generic_kernel<256>;
+        OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        kernel<<<p.grid, 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks);
+        OKP_CUDA_CHECK(cudaGetLastError());
+    }
+    const int warps_per_block = 4;
+    okp_merge_peaks_kernel<<<(maps + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
+        tile_count, tile_peaks, maps, p.tiles_per_map, W, K, *tables);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
+                          const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                          const OkpDecodeTables* tables, void* stream) {
+    int rc = check_params(params);
+    if (rc != OKP_OK) return rc;
+    rc = check_shape(N, C, H, W);
+    if (rc != OKP_OK) return rc;
+    if (N == 0) return OKP_OK;
+    if (!tables || (C > 1 && (!centers_dev || !keypoint_config))) return OKP_E_NULL;
+    if (camera && !depth_dev) return OKP_E_NULL;
+    const void* const* fields = (const void* const*)tables;
+    for (size_t i = 0; i < sizeof(OkpDecodeTables) / sizeof(void*); ++i)
+        if (!fields[i]) return OKP_E_NULL;
+    OkpConfig config;
+    memset(&config, 0, sizeof(config));
+    config.cfg[0] = 1;                                  // pipeline.py:36: centre map first
+    int S = 1;
+    for (int i = 0; i < C - 1; ++i) {
+        if (keypoint_config[i] < 1 || keypoint_config[i] > OKP_MAX_SLOTS) return OKP_E_CAPACITY;
+        config.cfg[1 + i] = keypoint_config[i];
+        if (keypoint_config[i] > S) S = keypoint_config[i];
+    }
+    OkpCamera cam;
+    memset(&cam, 0, sizeof(cam));
+    if (camera) cam = *camera;
+    okp_group_kernel<128><<<N, 128, 0, (cudaStream_t)stream>>>(depth_dev, centers_dev, N, C, H, W, config, cam,
+                                                               camera != nullptr, *params, S, *tables);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
+                   const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                   const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    int rc = okp_extract_peaks_f32(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
+    if (rc != OKP_OK) return rc;
+    return okp_group_objects_f32(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, stream);
+}
+
+int okp_fisheye_undistort_f64(const double* xy_dev, int n, const OkpCamera* camera, int round_to_f32,
+                              double* out_dev, void* stream) {
+    if (n < 0) return OKP_E_SHAPE;
+    if (n == 0) return OKP_OK;
+    if (!xy_dev || !camera || !out_dev) return OKP_E_NULL;
+    okp_undistort_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(xy_dev, n, *camera, round_to_f32, out_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_fisheye_project_f64(const double* X_dev, int n, const double* T_CW, const OkpCamera* camera, double* out_dev,
+                            void* stream) {
+    if (n < 0) return OKP_E_SHAPE;
+    if (n == 0) return OKP_OK;
+    if (!X_dev || !T_CW || !camera || !out_dev) return OKP_E_NULL;
+    OkpPose pose;
+    for (int i = 0; i < 12; ++i) pose.m[i] = T_CW[i];
+    okp_project_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(X_dev, n, pose, *camera, out_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_detection_to_point_f32(const float* xy_dev, int n, const float* depth_map_dev, int H, int W,
+                               const OkpCamera* camera, const OkpDecodeParams* params, double* out_dev, void* stream) {
+    if (n < 0 || H < 1 || W < 1) return OKP_E_SHAPE;
+    if (n == 0) return OKP_OK;
+    if (!xy_dev || !depth_map_dev || !camera || !params || !out_dev) return OKP_E_NULL;
+    okp_detection_to_point_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        xy_dev, n, depth_map_dev, H, W, *camera, params->compat_clip_bug, out_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_triangulate_f64(const double* points_dev, const uint8_t* valid_dev, const double* projections_dev,
+                        int per_point_projections, int P, int V, double* out_dev, void* stream) {
+    if (P < 0 || V < 1 || V > OKP_MAX_VIEWS) return OKP_E_SHAPE;
+    if (P == 0) return OKP_OK;
+    if (!points_dev || !projections_dev || !out_dev) return OKP_E_NULL;
+    const size_t smem = per_point_projections ? 0 : sizeof(double) * 12 * (size_t)V;
+    okp_triangulate_kernel<<<(P + 127) / 128, 128, smem, (cudaStream_t)stream>>>(
+        points_dev, valid_dev, projections_dev, per_point_projections, P, V, out_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_reprojection_filter_f64(const double* X_dev, const double* obs_dev, uint8_t* valid_dev, const double* poses_dev,
+                                const OkpCamera* camera, int P, int V, double max_error_px, double* err_dev,
+                                void* stream) {
+    if (P < 0 || V < 1 || V > OKP_MAX_VIEWS) return OKP_E_SHAPE;
+    if (P == 0) return OKP_OK;
+    if (!X_dev || !obs_dev || !valid_dev || !poses_dev || !camera || !err_dev) return OKP_E_NULL;
+    const long long total = (long long)P * V;
+    okp_reprojection_filter_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        X_dev, obs_dev, valid_dev, poses_dev, *camera, P, V, max_error_px, err_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+}  // extern "C"

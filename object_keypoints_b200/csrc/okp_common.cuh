@@ -1,0 +1,30 @@
+// okp_common.cuh -- shared device helpers for libokp.so (sm_100a).
+//
+// Arithmetic contract (kept identical to oracle/np_oracle.py and oracle/okp_oracle.c):
+// the library is compiled with -fmad=false so every float/double product and sum is rounded
+// separately, exactly like the reference's NumPy / torch-CPU arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/okp.h"
+
+#define OKP_CUDA_CHECK(expr)                         \
+    do {                                             \
+        cudaError_t _e = (expr);                     \
+        if (_e != cudaSuccess) return OKP_E_CUDA;    \
+    } while (0)
+
+// One candidate peak as the tile kernels hand it to the merge step (32 bytes).
+struct OkpPeakRecord {
+    int32_t key;     // y * W + x: raster order
+    float score;     // box sum at the peak
+    float cx, cy;    // centroid (x, y)
+    float conf;      // sum of the window's probabilities
+    int32_t pad[3];
+};
+
+__device__ __forceinline__ int okp_min(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int okp_max(int a, int b) { return a > b ? a : b; }
+__device__ __forceinline__ int okp_clamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -1,0 +1,116 @@
+// okp_dlt.cuh -- K5: batched multi-view DLT triangulation, one thread per 3D point, float64,
+// everything in registers.
+//
+// The reference triangulates two views with cv2.triangulatePoints (camera_utils.py:103-108,
+// scripts/label.py:296-305): the homogeneous point is the right singular vector of the
+// smallest singular value of A, whose rows are x P[2] - P[0] and y P[2] - P[1] per view. This
+// kernel does the same for V >= 2 views without ever forming A^T A (which would square the
+// condition number): the rows are streamed through Givens rotations into a 4x4 upper
+// triangular R (A = Q R shares its right singular vectors with R), then a one-sided Jacobi SVD
+// of R yields the vector.
+#pragma once
+#include "okp_common.cuh"
+
+__device__ __forceinline__ void okp_givens_append(double (&R)[4][4], double (&a)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (a[j] == 0.0) continue;
+        const double r = hypot(R[j][j], a[j]);
+        const double c = R[j][j] / r, s = a[j] / r;
+#pragma unroll
+        for (int k = j; k < 4; ++k) {
+            const double rk = R[j][k], ak = a[k];
+            R[j][k] = c * rk + s * ak;
+            a[k] = c * ak - s * rk;
+        }
+    }
+}
+
+// Smallest right singular vector of the 4x4 matrix R (destroyed). One-sided (Hestenes) Jacobi.
+__device__ __forceinline__ void okp_smallest_right_singular_vector(double (&R)[4][4], double (&h)[4]) {
+    double Vm[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    alpha += R[r][p] * R[r][p];
+                    beta += R[r][q] * R[r][q];
+                    gamma += R[r][p] * R[r][q];
+                }
+                if (fabs(gamma) <= 1e-300 || fabs(gamma) <= 2.3e-16 * sqrt(alpha * beta)) continue;
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const double ap = R[r][p], aq = R[r][q];
+                    R[r][p] = cs * ap - sn * aq;
+                    R[r][q] = sn * ap + cs * aq;
+                    const double vp = Vm[r][p], vq = Vm[r][q];
+                    Vm[r][p] = cs * vp - sn * vq;
+                    Vm[r][q] = sn * vp + cs * vq;
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    int arg = 0;
+    double smallest = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double nrm = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) nrm += R[r][c] * R[r][c];
+        if (c == 0 || nrm < smallest) { smallest = nrm; arg = c; }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        // select column `arg` without dynamic register indexing
+        h[r] = arg == 0 ? Vm[r][0] : (arg == 1 ? Vm[r][1] : (arg == 2 ? Vm[r][2] : Vm[r][3]));
+    }
+}
+
+__global__ void __launch_bounds__(128)
+okp_triangulate_kernel(const double* __restrict__ points, const uint8_t* __restrict__ valid,
+                       const double* __restrict__ projections, int per_point, int P, int V,
+                       double* __restrict__ out) {
+    extern __shared__ double s_proj[];                 // [V][12] when the projections are shared
+    if (!per_point) {
+        for (int i = threadIdx.x; i < V * 12; i += blockDim.x) s_proj[i] = projections[i];
+        __syncthreads();
+    }
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double R[4][4] = {};
+    int views = 0;
+    for (int v = 0; v < V; ++v) {
+        const size_t pv = (size_t)p * V + v;
+        if (valid && !valid[pv]) continue;
+        const double* M = per_point ? projections + pv * 12 : s_proj + v * 12;
+        const double x = points[2 * pv], y = points[2 * pv + 1];
+        double row[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) row[c] = x * M[8 + c] - M[c];
+        okp_givens_append(R, row);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) row[c] = y * M[8 + c] - M[4 + c];
+        okp_givens_append(R, row);
+        ++views;
+    }
+    if (views < 2) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        out[3 * (size_t)p] = nan; out[3 * (size_t)p + 1] = nan; out[3 * (size_t)p + 2] = nan;
+        return;
+    }
+    double h[4];
+    okp_smallest_right_singular_vector(R, h);
+    out[3 * (size_t)p] = h[0] / h[3];
+    out[3 * (size_t)p + 1] = h[1] / h[3];
+    out[3 * (size_t)p + 2] = h[2] / h[3];
+}

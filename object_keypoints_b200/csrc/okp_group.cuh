@@ -1,0 +1,239 @@
+// okp_group.cuh -- K3 + K4: centre-vector voting into object instances, over-detection
+// resolution and 3D points. One CTA per frame; everything it touches is a few hundred bytes of
+// peak records plus 3 gathered floats per spoke peak (2 centre-vector components, 1 depth).
+//
+// Replaces ObjectExtraction.__call__ (perception/pipeline.py:104-153) and the DetectionToPoint
+// loop of ObjectKeypointPipeline.__call__ (pipeline.py:189-199).
+#pragma once
+#include "okp_common.cuh"
+#include "okp_geometry.cuh"
+
+#define OKP_KMEANS_MAX_INITS 256
+
+struct OkpConfig { int32_t cfg[OKP_MAX_MAPS]; };    // cfg[0] = 1 (centre map), then keypoint_config
+
+// Deterministic stand-in for the reference's unseeded KMeans(init='random') (pipeline.py:146-148):
+// Lloyd's algorithm from every k-subset of the detections (lexicographic, at most
+// OKP_KMEANS_MAX_INITS), lowest inertia wins. Same statement as oracle/okp_oracle.c.
+// xy: the map's peak_xy table; idx[0..n): the detections of this (object, type). Points are re-read
+// from the table instead of being copied, to keep the per-thread stack small.
+__device__ __noinline__ void okp_cluster_detections(const float* __restrict__ xy, const unsigned char* idx, int n, int k,
+                                                    int iters, float* out) {
+#define OKP_PT(i, d) ((double)xy[2 * (int)idx[(i)] + (d)])
+    double cen[OKP_MAX_SLOTS][2], best_cen[OKP_MAX_SLOTS][2];
+    int subset[OKP_MAX_SLOTS];
+    unsigned char assign[OKP_MAX_PEAKS], new_assign[OKP_MAX_PEAKS];
+    double best = 0.0;
+    bool have_best = false;
+    for (int c = 0; c < k; ++c) subset[c] = c;
+    for (int init = 0; init < OKP_KMEANS_MAX_INITS; ++init) {
+        for (int c = 0; c < k; ++c) { cen[c][0] = OKP_PT(subset[c], 0); cen[c][1] = OKP_PT(subset[c], 1); }
+        bool have_assign = false;
+        for (int it = 0; it < iters; ++it) {
+            bool same = have_assign;
+            for (int i = 0; i < n; ++i) {
+                int arg = 0;
+                double dmin = 0.0;
+                for (int c = 0; c < k; ++c) {
+                    const double dx = OKP_PT(i, 0) - cen[c][0], dy = OKP_PT(i, 1) - cen[c][1];
+                    const double d = dx * dx + dy * dy;
+                    if (c == 0 || d < dmin) { dmin = d; arg = c; }
+                }
+                new_assign[i] = (unsigned char)arg;
+                if (have_assign && assign[i] != arg) same = false;
+            }
+            if (same) break;
+            for (int i = 0; i < n; ++i) assign[i] = new_assign[i];
+            have_assign = true;
+            for (int c = 0; c < k; ++c) {
+                double sx = 0.0, sy = 0.0;
+                int m = 0;
+                for (int i = 0; i < n; ++i)
+                    if (assign[i] == c) { sx += OKP_PT(i, 0); sy += OKP_PT(i, 1); ++m; }
+                if (m) { cen[c][0] = sx / m; cen[c][1] = sy / m; }
+            }
+        }
+        double inertia = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double dmin = 0.0;
+            for (int c = 0; c < k; ++c) {
+                const double dx = OKP_PT(i, 0) - cen[c][0], dy = OKP_PT(i, 1) - cen[c][1];
+                const double d = dx * dx + dy * dy;
+                if (c == 0 || d < dmin) dmin = d;
+            }
+            inertia += dmin;
+        }
+        if (!have_best || inertia < best) {
+            best = inertia;
+            have_best = true;
+            for (int c = 0; c < k; ++c) { best_cen[c][0] = cen[c][0]; best_cen[c][1] = cen[c][1]; }
+        }
+        int c = k - 1;
+        while (c >= 0 && subset[c] == n - k + c) --c;
+        if (c < 0) break;
+        ++subset[c];
+        for (int j = c + 1; j < k; ++j) subset[j] = subset[j - 1] + 1;
+    }
+    for (int c = 0; c < k; ++c) { out[2 * c] = (float)best_cen[c][0]; out[2 * c + 1] = (float)best_cen[c][1]; }
+#undef OKP_PT
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+okp_group_kernel(const float* __restrict__ depth, const float* __restrict__ centers, int N, int C, int H, int W,
+                 OkpConfig config, OkpCamera cam, int have_camera, OkpDecodeParams prm, int S, OkpDecodeTables t) {
+    const int n = blockIdx.x;
+    if (n >= N) return;
+    const int K = prm.max_peaks, O = prm.max_objects, V = prm.max_votes, T = C - 1;
+    const size_t HW = (size_t)H * W;
+    __shared__ double s_center[OKP_MAX_OBJECTS][2];
+    __shared__ unsigned int s_flags;
+    __shared__ int s_counts[OKP_MAX_MAPS];
+
+    if (threadIdx.x == 0) s_flags = 0;
+    if (threadIdx.x < C) {
+        const int c = t.peak_count[(size_t)n * C + threadIdx.x];
+        s_counts[threadIdx.x] = c < K ? c : K;
+    }
+    // reset this frame's object tables
+    for (int i = threadIdx.x; i < O * C; i += THREADS) {
+        const size_t oc = (size_t)n * O * C + i;
+        t.kp_assigned[oc] = 0;
+        t.kp_count[oc] = 0;
+        for (int s = 0; s < S; ++s) {
+            t.kp_peak[oc * S + s] = -1;
+            t.kp_xy[(oc * S + s) * 2] = 0.0f; t.kp_xy[(oc * S + s) * 2 + 1] = 0.0f;
+            t.kp_point[(oc * S + s) * 3] = 0.0; t.kp_point[(oc * S + s) * 3 + 1] = 0.0; t.kp_point[(oc * S + s) * 3 + 2] = 0.0;
+        }
+    }
+    for (int i = threadIdx.x; i < O; i += THREADS) t.n_votes[(size_t)n * O + i] = 0;
+    for (int i = threadIdx.x; i < O * V * 2; i += THREADS) t.votes[(size_t)n * O * V * 2 + i] = 0.0;
+    __syncthreads();
+    if (threadIdx.x < C && t.peak_count[(size_t)n * C + threadIdx.x] > K) atomicOr(&s_flags, OKP_FLAG_PEAK_OVERFLOW);
+
+    const size_t m0 = (size_t)n * C;
+    const int n_center = s_counts[0];
+    if (n_center == 0) {                                   // pipeline.py:105-106
+        __syncthreads();
+        if (threadIdx.x == 0) { t.n_objects[n] = 0; t.flags[n] = s_flags | OKP_FLAG_NO_CENTERS; }
+        return;
+    }
+    const int n_obj = n_center < O ? n_center : O;
+    if (threadIdx.x == 0 && n_center > O) atomicOr(&s_flags, OKP_FLAG_OBJECT_OVERFLOW);
+    for (int o = threadIdx.x; o < n_obj; o += THREADS) {   // pipeline.py:109-114: one object per centre peak
+        s_center[o][0] = (double)t.peak_xy[(m0 * K + o) * 2];
+        s_center[o][1] = (double)t.peak_xy[(m0 * K + o) * 2 + 1];
+        t.peak_object[m0 * K + o] = o;
+    }
+    __syncthreads();
+
+    // ---- spoke peaks vote for a centre (pipeline.py:115-128) ----
+    for (int i = threadIdx.x; i < T * K; i += THREADS) {
+        const int c = 1 + i / K, k = i - (c - 1) * K;
+        if (k >= s_counts[c]) continue;
+        const size_t s = ((size_t)n * C + c) * K + k;
+        const float px = t.peak_xy[2 * s], py = t.peak_xy[2 * s + 1];
+        const int xi = okp_clamp(__float2int_rn(px), 0, W - 1);      // np.round = half to even
+        const int yi = okp_clamp(__float2int_rn(py), 0, H - 1);
+        const float* cmap = centers + ((size_t)n * T + (c - 1)) * 2 * HW;
+        const double vx = ((double)xi + 0.5) + (double)__ldg(cmap + (size_t)yi * W + xi);
+        const double vy = ((double)yi + 0.5) + (double)__ldg(cmap + HW + (size_t)yi * W + xi);
+        t.peak_vote[2 * s] = vx;
+        t.peak_vote[2 * s + 1] = vy;
+        int arg = 0;
+        double dmin = 0.0;
+        for (int o = 0; o < n_obj; ++o) {
+            const double dx = s_center[o][0] - vx, dy = s_center[o][1] - vy;
+            const double d = sqrt(dx * dx + dy * dy);
+            if (o == 0 || d < dmin) { dmin = d; arg = o; }             // first minimum, like np.argmin
+        }
+        if (dmin > prm.outlier_distance) {
+            atomicOr(&s_flags, OKP_FLAG_OUTLIER_SKIPPED);              // the reference prints and skips
+            t.peak_object[s] = -1;
+        } else {
+            t.peak_object[s] = arg;
+        }
+    }
+    __syncthreads();
+
+    // ---- votes per object, in assignment order (type-major, raster order inside a type) ----
+    for (int o = threadIdx.x; o < n_obj; o += THREADS) {
+        const size_t ob = (size_t)n * O + o;
+        int nv = 0;
+        for (int c = 1; c < C; ++c) {
+            const size_t m = (size_t)n * C + c;
+            for (int k = 0; k < s_counts[c]; ++k) {
+                if (t.peak_object[m * K + k] != o) continue;
+                if (nv < V) {
+                    t.votes[(ob * V + nv) * 2] = t.peak_vote[(m * K + k) * 2];
+                    t.votes[(ob * V + nv) * 2 + 1] = t.peak_vote[(m * K + k) * 2 + 1];
+                } else {
+                    atomicOr(&s_flags, OKP_FLAG_VOTE_OVERFLOW);
+                }
+                ++nv;
+            }
+        }
+        t.n_votes[ob] = nv;
+    }
+
+    // ---- per (object, map): resolve over-detection, then lift to 3D ----
+    for (int i = threadIdx.x; i < n_obj * C; i += THREADS) {
+        const int o = i / C, c = i - o * C;
+        const size_t m = (size_t)n * C + c;
+        const size_t oc = ((size_t)n * O + o) * C + c;
+        const int limit = config.cfg[c];
+        int cnt = 0;
+        for (int k = 0; k < s_counts[c]; ++k) cnt += (t.peak_object[m * K + k] == o);
+        t.kp_assigned[oc] = cnt;
+        if (cnt == 0) continue;                            // pipeline.py:150-152: empty array
+        float pts[OKP_MAX_SLOTS][2];
+        int ids[OKP_MAX_SLOTS];
+        int kept = 0;
+        if (cnt <= limit) {
+            for (int k = 0; k < s_counts[c]; ++k)
+                if (t.peak_object[m * K + k] == o) {
+                    ids[kept] = k;
+                    pts[kept][0] = t.peak_xy[(m * K + k) * 2];
+                    pts[kept][1] = t.peak_xy[(m * K + k) * 2 + 1];
+                    ++kept;
+                }
+        } else if (limit == 1) {                           // pipeline.py:139-142: most confident detection
+            int arg = -1;
+            float best = 0.0f;
+            for (int k = 0; k < s_counts[c]; ++k)
+                if (t.peak_object[m * K + k] == o) {
+                    const float conf = t.peak_conf[m * K + k];
+                    if (arg < 0 || conf > best) { best = conf; arg = k; }   // first maximum, like np.argmax
+                }
+            ids[0] = arg;
+            pts[0][0] = t.peak_xy[(m * K + arg) * 2];
+            pts[0][1] = t.peak_xy[(m * K + arg) * 2 + 1];
+            kept = 1;
+            atomicOr(&s_flags, OKP_FLAG_ARGMAX_RESOLVED);
+        } else {                                           // pipeline.py:143-148: cluster
+            unsigned char members[OKP_MAX_PEAKS];
+            int g = 0;
+            for (int k = 0; k < s_counts[c]; ++k)
+                if (t.peak_object[m * K + k] == o) members[g++] = (unsigned char)k;
+            kept = limit;
+            okp_cluster_detections(t.peak_xy + m * K * 2, members, g, kept, prm.kmeans_iterations, &pts[0][0]);
+            for (int s = 0; s < kept; ++s) ids[s] = -1;
+            atomicOr(&s_flags, OKP_FLAG_CLUSTERED);
+        }
+        t.kp_count[oc] = kept;
+        for (int s = 0; s < kept; ++s) {
+            t.kp_peak[oc * S + s] = ids[s];
+            t.kp_xy[(oc * S + s) * 2] = pts[s][0];
+            t.kp_xy[(oc * S + s) * 2 + 1] = pts[s][1];
+            if (have_camera) {
+                double p3[3];
+                okp_detection_to_point(pts[s][0], pts[s][1], depth + m * HW, H, W, cam, prm.compat_clip_bug, p3);
+                t.kp_point[(oc * S + s) * 3] = p3[0];
+                t.kp_point[(oc * S + s) * 3 + 1] = p3[1];
+                t.kp_point[(oc * S + s) * 3 + 2] = p3[2];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { t.n_objects[n] = n_obj; t.flags[n] = s_flags; }
+}

@@ -1,0 +1,228 @@
+// okp_peaks.cuh -- K1: 5x5 box sum + 5x5 max-pool NMS + threshold + ordered compaction +
+// sub-pixel centroid (replaces perception/pipeline.py:46-79 and perception/models.py:55-58).
+//
+// Work decomposition: every map (frame n, channel c) is cut into tiles; one CTA processes one
+// tile at a time (persistent grid-stride loop). A tile is staged in shared memory with a 4 px
+// halo (2 for the box sum + 2 for the max pool of box sums). Peaks of a tile are written, sorted
+// in raster order, to a per-tile slot list; okp_merge_peaks_kernel concatenates the tiles of a map
+// into the final table (raster order is what the reference's boolean-mask indexing returns,
+// pipeline.py:73).
+#pragma once
+#include "okp_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Generic tile kernel ("v0"): any H, W, any tile size. One thread per pixel, shared-memory taps.
+// Slow but obviously right; kept as the in-library cross-check of the tuned kernels and as the
+// path for shapes the tuned kernels do not cover.
+// ---------------------------------------------------------------------------------------------
+struct OkpTileGeometry {
+    int H, W;            // map size
+    int TH, TW;          // tile size (outputs)
+    int tiles_y, tiles_x;
+    int maps;            // N * C
+};
+
+__device__ __forceinline__ void okp_centroid_from_smem(const float* raw, int pitch, int ry, int rx, int gy, int gx,
+                                                       float* cx, float* cy, float* conf) {
+    // raw(ry, rx) is the peak pixel inside the staged tile; (gy, gx) its image coordinates.
+    // Pixels outside the image were staged as +0, which leaves every partial sum unchanged, so
+    // summing the full 5x5 window in raster order equals the reference's border-clipped window.
+    float sy = 0.0f, sx = 0.0f, sp = 0.0f;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) {
+            const float q = raw[(ry + dy) * pitch + rx + dx];
+            sy = __fadd_rn(sy, __fmul_rn(q, (float)(gy + dy)));
+            sx = __fadd_rn(sx, __fmul_rn(q, (float)(gx + dx)));
+            sp = __fadd_rn(sp, q);
+        }
+    }
+    *cx = __fdiv_rn(sx, sp);
+    *cy = __fdiv_rn(sy, sp);
+    *conf = sp;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+okp_peaks_generic_kernel(const float* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
+                         int32_t* __restrict__ tile_count, OkpPeakRecord* __restrict__ tile_peaks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int RP = g.TW + 8;                 // raw pitch
+    const int SP = g.TW + 4;                 // score pitch
+    float* raw = reinterpret_cast<float*>(smem_raw);
+    float* score = raw + (g.TH + 8) * RP;
+    int32_t* keys = reinterpret_cast<int32_t*>(score + (g.TH + 4) * SP);
+    int32_t* sorted = keys + K;
+    __shared__ int s_count;
+
+    const int tiles_per_map = g.tiles_y * g.tiles_x;
+    const long long work_items = (long long)g.maps * tiles_per_map;
+    for (long long work = blockIdx.x; work < work_items; work += gridDim.x) {
+        const int map = (int)(work / tiles_per_map);
+        const int tile = (int)(work - (long long)map * tiles_per_map);
+        const int ty0 = (tile / g.tiles_x) * g.TH;
+        const int tx0 = (tile % g.tiles_x) * g.TW;
+        const float* src = heat + (size_t)map * g.H * g.W;
+        if (threadIdx.x == 0) s_count = 0;
+        // ---- stage the tile + 4 px halo, zero outside the image (conv2d zero padding) ----
+        for (int i = threadIdx.x; i < (g.TH + 8) * RP; i += THREADS) {
+            const int ry = i / RP, rx = i - ry * RP;
+            const int gy = ty0 - 4 + ry, gx = tx0 - 4 + rx;
+            float v = 0.0f;
+            if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) v = __ldg(src + (size_t)gy * g.W + gx);
+            raw[i] = v;
+        }
+        __syncthreads();
+        // ---- box sum on the tile + 2 px halo: 25 sequential adds, raster tap order ----
+        for (int i = threadIdx.x; i < (g.TH + 4) * SP; i += THREADS) {
+            const int sy = i / SP, sx = i - sy * SP;
+            const int gy = ty0 - 2 + sy, gx = tx0 - 2 + sx;
+            float acc = -INFINITY;           // max_pool2d pads with -inf
+            if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) {
+                acc = 0.0f;
+#pragma unroll
+                for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 5; ++dx) acc = __fadd_rn(acc, raw[(sy + dy) * RP + sx + dx]);
+            }
+            score[i] = acc;
+        }
+        __syncthreads();
+        // ---- NMS + threshold; unordered append ----
+        for (int i = threadIdx.x; i < g.TH * g.TW; i += THREADS) {
+            const int py = i / g.TW, px = i - py * g.TW;
+            const int gy = ty0 + py, gx = tx0 + px;
+            if (gy >= g.H || gx >= g.W) continue;
+            const float v = score[(py + 2) * SP + px + 2];
+            if (!(v > threshold)) continue;
+            float m = v;
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
+            if (v == m) {
+                const int slot = atomicAdd(&s_count, 1);
+                if (slot < K) keys[slot] = gy * g.W + gx;
+            }
+        }
+        __syncthreads();
+        const int total = s_count;
+        if (total > K) {
+            // Overflow: the table keeps the FIRST K peaks in raster order. Redo the scan in order
+            // with one warp (rare path: only maps with more peaks than the table holds).
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                int filled = 0;
+                for (int base = 0; base < g.TH * g.TW && filled < K; base += 32) {
+                    const int i = base + threadIdx.x;
+                    bool is_peak = false;
+                    int key = 0;
+                    if (i < g.TH * g.TW) {
+                        const int py = i / g.TW, px = i - py * g.TW;
+                        const int gy = ty0 + py, gx = tx0 + px;
+                        if (gy < g.H && gx < g.W) {
+                            const float v = score[(py + 2) * SP + px + 2];
+                            if (v > threshold) {
+                                float m = v;
+                                for (int dy = 0; dy < 5; ++dy)
+                                    for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
+                                is_peak = (v == m);
+                                key = gy * g.W + gx;
+                            }
+                        }
+                    }
+                    const unsigned ballot = __ballot_sync(0xffffffffu, is_peak);
+                    const int slot = filled + __popc(ballot & ((1u << threadIdx.x) - 1u));
+                    if (is_peak && slot < K) keys[slot] = key;
+                    filled += __popc(ballot);
+                }
+            }
+            __syncthreads();
+        }
+        const int n = total < K ? total : K;
+        // ---- order by raster key (rank sort; n is tiny) ----
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const int key = keys[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += (keys[j] < key);
+            sorted[rank] = key;
+        }
+        __syncthreads();
+        OkpPeakRecord* out = tile_peaks + (size_t)work * K;
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const int key = sorted[i];
+            const int gy = key / g.W, gx = key - gy * g.W;
+            const int ry = gy - ty0 + 4, rx = gx - tx0 + 4;
+            OkpPeakRecord rec;
+            rec.key = key;
+            rec.score = score[(ry - 2) * SP + rx - 2];
+            okp_centroid_from_smem(raw, RP, ry, rx, gy, gx, &rec.cx, &rec.cy, &rec.conf);
+            rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+            out[i] = rec;
+        }
+        if (threadIdx.x == 0) tile_count[work] = total;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge the per-tile lists of a map into the final raster-ordered table. One warp per map.
+// Also resets the assignment columns (peak_object, peak_vote) and clears unused slots, so the
+// tables never need a separate memset.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakRecord* __restrict__ tile_peaks,
+                       int maps, int tiles_per_map, int W, int K, OkpDecodeTables t) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= maps) return;
+    const int m = warp;
+    int total = 0;       // true number of peaks
+    int kept = 0;        // candidates available (each tile contributes at most K)
+    for (int tile = 0; tile < tiles_per_map; ++tile) {
+        const int c = tile_count[(size_t)m * tiles_per_map + tile];
+        total += c;
+        kept += c < K ? c : K;
+    }
+    const int n_out = kept < K ? kept : K;
+    // clear every slot first (lanes stride over K)
+    for (int k = lane; k < K; k += 32) {
+        const size_t s = (size_t)m * K + k;
+        if (k >= n_out) {
+            t.peak_yx[2 * s] = -1; t.peak_yx[2 * s + 1] = -1;
+            t.peak_score[s] = 0.0f;
+            t.peak_xy[2 * s] = 0.0f; t.peak_xy[2 * s + 1] = 0.0f;
+            t.peak_conf[s] = 0.0f;
+        }
+        t.peak_object[s] = -1;
+        t.peak_vote[2 * s] = 0.0; t.peak_vote[2 * s + 1] = 0.0;
+    }
+    // rank of every candidate among all candidates of the map
+    for (int tile = 0; tile < tiles_per_map; ++tile) {
+        const int c = okp_min(tile_count[(size_t)m * tiles_per_map + tile], K);
+        const OkpPeakRecord* mine = tile_peaks + ((size_t)m * tiles_per_map + tile) * K;
+        for (int i = lane; i < c; i += 32) {
+            const OkpPeakRecord rec = mine[i];
+            int rank = 0;
+            if (tiles_per_map == 1) {
+                rank = i;                            // already sorted inside the tile
+            } else {
+                for (int other = 0; other < tiles_per_map; ++other) {
+                    const int oc = okp_min(tile_count[(size_t)m * tiles_per_map + other], K);
+                    const OkpPeakRecord* theirs = tile_peaks + ((size_t)m * tiles_per_map + other) * K;
+                    for (int j = 0; j < oc; ++j) rank += (theirs[j].key < rec.key);
+                }
+            }
+            if (rank < K) {
+                const size_t s = (size_t)m * K + rank;
+                const int y = rec.key / W;
+                t.peak_yx[2 * s] = y; t.peak_yx[2 * s + 1] = rec.key - y * W;
+                t.peak_score[s] = rec.score;
+                t.peak_xy[2 * s] = rec.cx; t.peak_xy[2 * s + 1] = rec.cy;
+                t.peak_conf[s] = rec.conf;
+            }
+        }
+    }
+    if (lane == 0) t.peak_count[m] = total;
+}

@@ -1,0 +1,398 @@
+"""Drop-in for the reference's ``perception/pipeline.py`` on a B200.
+
+Same class names, constructor / ``reset`` / ``__call__`` signatures and return structures as
+the reference (file:line cited per class); the arithmetic runs in libokp.so (CUDA, sm_100a)
+through the C ABI of include/okp.h. PyTorch only owns device memory and streams.
+
+Two levels:
+
+* ``KeypointDecoder`` -- the batched device API (no batch-1 limit, tensors stay in HBM,
+  fixed-capacity record tables come back as tensors);
+* ``KeypointExtractionComponent``, ``ObjectExtraction``, ``DetectionToPoint``,
+  ``ObjectKeypointPipeline``, ``LearnedKeypointTrackingPipeline`` -- the reference's
+  interface, converting the tables to the reference's nested lists / dicts.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _abi, _lib
+
+_TORCH_DTYPES = {np.dtype(np.int32): torch.int32, np.dtype(np.uint32): torch.int32,
+                 np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("object_keypoints_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    if device is None:
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream_handle(stream=None):
+    stream = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
+def _as_device_f32(x, device):
+    """NumPy array / CPU tensor / CUDA tensor -> contiguous float32 CUDA tensor."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.device != device:
+        x = x.to(device, non_blocking=True)
+    return x.contiguous()
+
+
+class DecodeTables:
+    """The OkpDecodeTables record as torch tensors on one device (layout: include/okp.h)."""
+
+    def __init__(self, N, C, keypoint_config, params, device):
+        self.N, self.C = N, C
+        self.tensors = {}
+        for name, dtype, shape in _abi.table_shapes(N, C, keypoint_config, params):
+            self.tensors[name] = torch.zeros(shape, dtype=_TORCH_DTYPES[np.dtype(dtype)], device=device)
+        self.struct = _abi.OkpDecodeTables(**{k: v.data_ptr() for k, v in self.tensors.items()})
+
+    def __getitem__(self, name):
+        return self.tensors[name]
+
+    def numpy(self):
+        """Synchronising copy of every table to host NumPy arrays (flags as uint32)."""
+        out = {k: v.cpu().numpy() for k, v in self.tensors.items()}
+        out['flags'] = out['flags'].view(np.uint32)
+        return out
+
+
+class KeypointDecoder:
+    """Batched heatmap -> grouped 2D keypoints -> 3D points on the GPU.
+
+    keypoint_config: the parsed JSON dict {'keypoint_config': [...]} or the bare list.
+    prediction_size: (H, W) of the network output.
+    """
+
+    def __init__(self, keypoint_config, prediction_size, camera=None, device=None, max_peaks=32, max_objects=16,
+                 max_votes=16, threshold=0.5, outlier_distance=20.0, compat_clip_bug=True):
+        self.cfg = _abi.check_keypoint_config(keypoint_config)
+        self.C = 1 + len(self.cfg)
+        self.H, self.W = int(prediction_size[0]), int(prediction_size[1])
+        self.params = _abi.make_params(threshold=threshold, outlier_distance=outlier_distance, max_peaks=max_peaks,
+                                       max_objects=max_objects, max_votes=max_votes, compat_clip_bug=compat_clip_bug)
+        self.device = _device(device)
+        self._cfg_array = (ctypes.c_int32 * max(len(self.cfg), 1))(*self.cfg)
+        self._camera = None
+        self._tables = {}
+        self._workspace = None
+        self._lib = _lib.lib()
+        if camera is not None:
+            self.reset(camera)
+
+    def reset(self, camera):
+        """camera: object exposing K, D, Kinv, image_size (camera_utils.FisheyeCamera or the
+        reference's own class), as DetectionToPoint.reset receives it (pipeline.py:159-162)."""
+        self._camera = _abi.pack_camera(camera)
+
+    def tables(self, N):
+        if N not in self._tables:
+            self._tables[N] = DecodeTables(N, self.C, self.cfg, self.params, self.device)
+        return self._tables[N]
+
+    def _workspace_for(self, N):
+        need = self._lib.okp_decode_workspace_bytes(N, self.C, self.H, self.W, ctypes.byref(self.params))
+        if need == 0:
+            raise ValueError("unsupported shape or parameters")
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def _check(self, heat):
+        if heat.dim() != 4 or heat.shape[1] != self.C or heat.shape[2] != self.H or heat.shape[3] != self.W:
+            raise ValueError(f"heatmap must be [N,{self.C},{self.H},{self.W}], got {tuple(heat.shape)}")
+
+    def extract_peaks(self, heat, tables=None, stream=None):
+        """K1 only: fills the peak_* tables. Asynchronous on the current (or given) stream."""
+        heat = _as_device_f32(heat, self.device)
+        self._check(heat)
+        N = heat.shape[0]
+        tables = self.tables(N) if tables is None else tables
+        ws = self._workspace_for(N)
+        rc = self._lib.okp_extract_peaks_f32(heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params),
+                                             ctypes.byref(tables.struct), ws.data_ptr(), ws.numel(),
+                                             _stream_handle(stream))
+        _lib.check(rc, 'okp_extract_peaks_f32')
+        return tables
+
+    def decode_batch(self, heat, depth, centers, tables=None, stream=None):
+        """heat [N,C,H,W], depth [N,C,H,W], centers [N,C-1,2,H,W] (float32; CUDA tensors are used in
+        place, host arrays are copied) -> DecodeTables on the device. No synchronisation."""
+        heat = _as_device_f32(heat, self.device)
+        self._check(heat)
+        depth = _as_device_f32(depth, self.device)
+        centers = _as_device_f32(centers, self.device)
+        N = heat.shape[0]
+        if tuple(depth.shape) != tuple(heat.shape):
+            raise ValueError("depth must have the heatmap's shape")
+        if tuple(centers.shape) != (N, self.C - 1, 2, self.H, self.W):
+            raise ValueError(f"centers must be [N,{self.C - 1},2,{self.H},{self.W}], got {tuple(centers.shape)}")
+        tables = self.tables(N) if tables is None else tables
+        ws = self._workspace_for(N)
+        cam = ctypes.byref(self._camera) if self._camera is not None else None
+        rc = self._lib.okp_decode_f32(heat.data_ptr(), depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W,
+                                      self._cfg_array, cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                                      ws.data_ptr(), ws.numel(), _stream_handle(stream))
+        _lib.check(rc, 'okp_decode_f32')
+        return tables
+
+    HOST_RESULT_TABLES = ('n_objects', 'flags', 'kp_count', 'kp_xy', 'kp_point')
+
+    def decode_host_batch(self, heat, depth, centers, chunk_frames=256):
+        """End-to-end form for HOST inputs: heat/depth/centers are CPU tensors (pinned memory makes
+        the copies asynchronous). The batch is cut into chunks; chunk i+1 is copied host->device on
+        a copy stream while chunk i is decoded, and the object tables of every chunk are copied back
+        into pinned host tensors. Returns a dict of CPU tensors (synchronised)."""
+        N = int(heat.shape[0])
+        chunk = max(1, min(chunk_frames, N))
+        key = ('host', N, chunk)
+        if key not in self._tables:
+            staging = []
+            for _ in range(2):
+                staging.append({
+                    'heat': torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device),
+                    'depth': torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device),
+                    'centers': torch.empty((chunk, self.C - 1, 2, self.H, self.W), dtype=torch.float32, device=self.device),
+                    'tables': DecodeTables(chunk, self.C, self.cfg, self.params, self.device),
+                    'ready': torch.cuda.Event(), 'done': torch.cuda.Event(),
+                })
+            like = staging[0]['tables']
+            result = {name: torch.empty((N,) + tuple(like[name].shape[1:]), dtype=like[name].dtype).pin_memory()
+                      for name in self.HOST_RESULT_TABLES}
+            self._tables[key] = (staging, result, torch.cuda.Stream(device=self.device))
+        staging, result, copy_stream = self._tables[key]
+        compute = torch.cuda.current_stream()
+        for index, f0 in enumerate(range(0, N, chunk)):
+            f1 = min(f0 + chunk, N)
+            n = f1 - f0
+            slot = staging[index % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(slot['done'])          # the slot's previous decode + read-back finished
+                slot['heat'][:n].copy_(heat[f0:f1], non_blocking=True)
+                slot['depth'][:n].copy_(depth[f0:f1], non_blocking=True)
+                slot['centers'][:n].copy_(centers[f0:f1], non_blocking=True)
+                slot['ready'].record(copy_stream)
+            compute.wait_event(slot['ready'])
+            if n == chunk:
+                tables = slot['tables']
+                self.decode_batch(slot['heat'], slot['depth'], slot['centers'], tables=tables)
+            else:
+                tables = self.decode_batch(slot['heat'][:n], slot['depth'][:n], slot['centers'][:n])
+            for name in self.HOST_RESULT_TABLES:
+                result[name][f0:f1].copy_(tables[name][:n], non_blocking=True)
+            slot['done'].record(compute)
+        compute.synchronize()
+        return result
+
+    def group_objects(self, depth, centers, tables, stream=None):
+        """K3 + K4 on peak tables that are already filled (ObjectExtraction + DetectionToPoint)."""
+        N = tables.N
+        centers = _as_device_f32(centers, self.device)
+        depth_ptr = None
+        cam = None
+        if depth is not None and self._camera is not None:
+            depth = _as_device_f32(depth, self.device)
+            depth_ptr = depth.data_ptr()
+            cam = ctypes.byref(self._camera)
+        rc = self._lib.okp_group_objects_f32(depth_ptr, centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array,
+                                             cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                                             _stream_handle(stream))
+        _lib.check(rc, 'okp_group_objects_f32')
+        return tables
+
+
+# ------------------------------------------------------------------------------------------------
+# conversion of record tables to the reference's Python structures
+# ------------------------------------------------------------------------------------------------
+def tables_to_keypoints(t, n):
+    """-> (keypoints[C][k] of (2,) float32 (x, y), confidence[C][k]) like
+    KeypointExtractionComponent._extract_keypoints (pipeline.py:64-79)."""
+    C, K = t['peak_count'].shape[1], t['peak_xy'].shape[2]
+    points, confidence = [], []
+    for c in range(C):
+        k = min(int(t['peak_count'][n, c]), K)
+        points.append([t['peak_xy'][n, c, j].copy() for j in range(k)])
+        confidence.append([t['peak_conf'][n, c, j] for j in range(k)])
+    return points, confidence
+
+
+def tables_to_objects(t, n, with_points=True):
+    """-> list of dicts with the keys ObjectKeypointPipeline.__call__ returns (pipeline.py:195-199)."""
+    C = t['kp_count'].shape[2]
+    V = t['votes'].shape[2]
+    objects = []
+    for o in range(int(t['n_objects'][n])):
+        keypoints, points = [], []
+        for c in range(C):
+            cnt = int(t['kp_count'][n, o, c])
+            if cnt == 0:
+                keypoints.append(np.array([]))                 # pipeline.py:152
+                points.append(None)                            # pipeline.py:165-166
+            else:
+                keypoints.append(t['kp_xy'][n, o, c, :cnt].copy())
+                points.append(t['kp_point'][n, o, c, :cnt].copy())
+        votes = [t['votes'][n, o, v].copy() for v in range(min(int(t['n_votes'][n, o]), V))]
+        obj = {'p_centers': votes, 'keypoints': keypoints}
+        if with_points:
+            obj['p_C'] = points
+        objects.append(obj)
+    return objects
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's interface
+# ------------------------------------------------------------------------------------------------
+class InferenceComponent:
+    """TorchScript model runner (pipeline.py:13-28). Unlike the reference it leaves the three
+    outputs on the device: the decode kernels read them in place."""
+    name = "inference"
+
+    def __init__(self, model, cuda=True):
+        self.cuda = cuda
+        self.model = torch.jit.load(model) if isinstance(model, (str, bytes)) else model
+        self.model = self.model.cuda() if cuda else self.model.cpu().float()
+
+    def __call__(self, frames):
+        if self.cuda:
+            frames = frames.cuda(non_blocking=True)
+        with torch.no_grad():
+            heatmaps, depth, centers = self.model(frames)
+        return heatmaps, depth, centers
+
+
+class KeypointExtractionComponent:
+    """pipeline.py:30-91. ``__call__(frames[N,C,H,W])`` -> ``(keypoints, confidence)`` nested
+    lists [N][C][k]; keypoints are (2,) float32 (x, y)."""
+    name = "keypoints"
+    PROBABILITY_CUTOFF = 0.1
+
+    def __init__(self, keypoint_config, prediction_size, bandwidth=1.0, **decoder_options):
+        self.keypoint_config = [1] + _abi.check_keypoint_config(keypoint_config)
+        self.n_keypoints = sum(self.keypoint_config)
+        self.decoder = KeypointDecoder(keypoint_config, prediction_size, **decoder_options)
+
+    def __call__(self, frames):
+        tables = self.decoder.extract_peaks(frames).numpy()
+        keypoints, confidence = [], []
+        for n in range(tables['peak_count'].shape[0]):
+            kp, conf = tables_to_keypoints(tables, n)
+            keypoints.append(kp)
+            confidence.append(conf)
+        return keypoints, confidence
+
+
+class ObjectExtraction:
+    """pipeline.py:93-153. ``__call__(keypoints[C][k], confidence[C][k], centers[T,2,H,W])`` for one
+    frame -> list of dicts with 'center', 'heatmap_points', 'p_centers', 'confidence'."""
+
+    def __init__(self, keypoint_config, prediction_size, **decoder_options):
+        self.keypoint_config = _abi.check_keypoint_config(keypoint_config)
+        self.prediction_size = prediction_size
+        self.decoder = KeypointDecoder(keypoint_config, prediction_size, **decoder_options)
+
+    def __call__(self, keypoints, confidence, centers):
+        if len(keypoints[0]) == 0:
+            return []
+        d = self.decoder
+        K = d.params.max_peaks
+        tables = DecodeTables(1, d.C, d.cfg, d.params, d.device)
+        count = np.zeros((1, d.C), np.int32)
+        xy = np.zeros((1, d.C, K, 2), np.float32)
+        conf = np.zeros((1, d.C, K), np.float32)
+        for c in range(d.C):
+            count[0, c] = len(keypoints[c])
+            for j in range(min(len(keypoints[c]), K)):
+                xy[0, c, j] = np.asarray(keypoints[c][j], dtype=np.float32)
+                conf[0, c, j] = float(confidence[c][j])
+        tables['peak_count'].copy_(torch.from_numpy(count))
+        tables['peak_xy'].copy_(torch.from_numpy(xy))
+        tables['peak_conf'].copy_(torch.from_numpy(conf))
+        tables['peak_object'].fill_(-1)
+        centers = np.asarray(centers, dtype=np.float32)[None]
+        t = d.group_objects(None, centers, tables).numpy()
+        objects = []
+        for o in range(int(t['n_objects'][0])):
+            obj = {'center': t['kp_xy'][0, o, 0, 0].copy(), 'heatmap_points': [], 'confidence': [],
+                   'p_centers': [t['votes'][0, o, v].copy() for v in range(min(int(t['n_votes'][0, o]), t['votes'].shape[2]))]}
+            for c in range(1, d.C):
+                cnt = int(t['kp_count'][0, o, c])
+                obj['heatmap_points'].append(t['kp_xy'][0, o, c, :cnt].copy() if cnt else np.array([]))
+                members = [j for j in range(min(int(t['peak_count'][0, c]), K)) if t['peak_object'][0, c, j] == o]
+                obj['confidence'].append([t['peak_conf'][0, c, j] for j in members])
+            objects.append(obj)
+        return objects
+
+
+class DetectionToPoint:
+    """pipeline.py:155-171. ``reset(camera)``, ``__call__(xy[n,2], depth_map[H,W])`` -> [n,3]
+    float64 camera-frame points (None for empty input)."""
+
+    def __init__(self, compat_clip_bug=True, device=None):
+        self.params = _abi.make_params(compat_clip_bug=compat_clip_bug)
+        self.device = None if device is None else torch.device(device)
+        self.camera = None
+        self._packed = None
+
+    def reset(self, camera):
+        self.camera = camera
+        self._packed = _abi.pack_camera(camera)
+
+    def __call__(self, xy, p_depth):
+        xy = np.asarray(xy)
+        if xy.shape[0] == 0:
+            return None
+        device = _device(self.device)
+        xy_dev = _as_device_f32(xy.astype(np.float32), device)
+        depth_dev = _as_device_f32(p_depth, device)
+        out = torch.empty((xy_dev.shape[0], 3), dtype=torch.float64, device=device)
+        rc = _lib.lib().okp_detection_to_point_f32(xy_dev.data_ptr(), xy_dev.shape[0], depth_dev.data_ptr(),
+                                                   depth_dev.shape[0], depth_dev.shape[1], ctypes.byref(self._packed),
+                                                   ctypes.byref(self.params), out.data_ptr(), _stream_handle())
+        _lib.check(rc, 'okp_detection_to_point_f32')
+        return out.cpu().numpy()
+
+
+class ObjectKeypointPipeline:
+    """pipeline.py:173-200. ``ObjectKeypointPipeline(prediction_size, points_3d, keypoint_config)``,
+    ``reset(camera)``, ``__call__(heatmap[1,C,H,W], p_depth[1,C,H,W], p_centers[1,C-1,2,H,W])`` ->
+    list of {'p_centers', 'keypoints', 'p_C'} per object. ``decode_batch`` is the batched form."""
+
+    def __init__(self, prediction_size, points_3d, keypoint_config, **decoder_options):
+        self.decoder = KeypointDecoder(keypoint_config, prediction_size, **decoder_options)
+        self.points_3d = points_3d                     # unused by the reference as well (pipeline.py:174)
+
+    def reset(self, camera):
+        self.decoder.reset(camera)
+
+    def decode_batch(self, heatmap, p_depth, p_centers, stream=None):
+        """Any batch size, device tables out (no host round trip)."""
+        return self.decoder.decode_batch(heatmap, p_depth, p_centers, stream=stream)
+
+    def __call__(self, heatmap, p_depth, p_centers):
+        assert heatmap.shape[0] == 1, "One at the time, please."
+        if self.decoder._camera is None:
+            raise RuntimeError("call reset(camera) first")
+        tables = self.decoder.decode_batch(heatmap, p_depth, p_centers).numpy()
+        return tables_to_objects(tables, 0)
+
+
+class LearnedKeypointTrackingPipeline(ObjectKeypointPipeline):
+    """pipeline.py:202-209: model + decode; returns (objects, heatmap)."""
+
+    def __init__(self, model, cuda=True, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.inference = InferenceComponent(model, cuda)
+
+    def __call__(self, frame):
+        heatmap, depth, centers = self.inference(frame)
+        return super().__call__(heatmap, depth, centers), heatmap

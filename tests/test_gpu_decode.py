@@ -1,0 +1,226 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against (1) fixtures produced by the
+unmodified reference, (2) the C oracle on fresh seeded inputs, (3) size-independent properties
+at full benchmark sizes. Bit-exact: peak pixels, raster order, box sums, assignments, kept
+keypoints, flags. Tolerance: sub-pixel <= 1e-3 px, 3D <= 1e-4 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from helpers import (load_golden, golden_camera, reference_tables, assert_tables_match, TOL_PIXELS, TOL_METRES_REL)
+
+pytestmark = pytest.mark.gpu
+
+DECODE_FIXTURES = ['valve_64.npz', 'cups_64.npz', 'valve_grid_180x320.npz', 'test_pipeline_180x320.npz',
+                   'adversarial_64.npz']
+
+
+def gpu_decode(heat, depth, centers, cfg, camera, **options):
+    from object_keypoints_b200 import KeypointDecoder
+    decoder = KeypointDecoder(cfg, heat.shape[2:], camera=camera, **options)
+    return decoder.decode_batch(heat, depth, centers).numpy()
+
+
+def assert_matches_oracle(got, want):
+    """GPU vs C oracle on the same input: integer tables and flags identical; the oracle and the
+    kernels share one arithmetic contract, so float32 tables are compared bitwise too; float64
+    3D points within 1e-4 relative (CUDA's tan/atan are not the host libm's)."""
+    for key in ['peak_count', 'peak_yx', 'peak_object', 'n_objects', 'flags', 'kp_assigned', 'kp_count', 'kp_peak',
+                'n_votes']:
+        np.testing.assert_array_equal(got[key], want[key], err_msg=key)
+    for key in ['peak_score', 'peak_xy', 'peak_conf', 'kp_xy']:
+        np.testing.assert_array_equal(got[key].view(np.uint32), want[key].view(np.uint32), err_msg=key + " (bitwise)")
+    np.testing.assert_array_equal(got['peak_vote'], want['peak_vote'])
+    np.testing.assert_array_equal(got['votes'], want['votes'])
+    scale = np.maximum(np.linalg.norm(want['kp_point'], axis=-1), 1e-9)
+    assert (np.linalg.norm(got['kp_point'] - want['kp_point'], axis=-1) <= TOL_METRES_REL * scale + 1e-12).all()
+
+
+@pytest.mark.parametrize('name', DECODE_FIXTURES)
+def test_cuda_matches_reference_fixture(name):
+    g = load_golden(name)
+    got = gpu_decode(g['heat'], g['depth'], g['centers'], list(g['keypoint_config']), golden_camera(g))
+    assert_tables_match(got, reference_tables(g))
+
+
+@pytest.mark.parametrize('name', DECODE_FIXTURES)
+def test_cuda_matches_oracle_on_fixture_inputs(name):
+    from oracle import c_oracle
+    g = load_golden(name)
+    cfg, camera = list(g['keypoint_config']), golden_camera(g)
+    got = gpu_decode(g['heat'], g['depth'], g['centers'], cfg, camera)
+    assert_matches_oracle(got, c_oracle.decode(g['heat'], g['depth'], g['centers'], cfg, camera))
+
+
+@pytest.mark.parametrize('cfg,size,frames,objects', [
+    ([1, 3], (64, 64), 96, (1, 2)),          # config 1/4 shape: valve at the model resolution
+    ([1, 1, 1], (64, 64), 128, (1, 4)),      # config 2: cups, 64 stereo pairs
+    ([1, 3], (180, 320), 12, (1, 6)),        # test_pipeline shape
+    ([2], (40, 56), 8, (1, 1)),              # odd sizes, ragged tiles
+    ([1, 3], (37, 93), 8, (1, 1)),           # sizes that are not multiples of anything
+])
+def test_cuda_matches_oracle_on_seeded_batches(cfg, size, frames, objects):
+    from oracle import c_oracle
+    from object_keypoints_b200 import synthetic
+    layout = {}
+    if size[0] < 64:
+        layout = dict(center_separation=18.0, spoke_radius=(4.0, 6.0), peak_separation=5.0, border=3.0)
+    batch = synthetic.make_batch(frames, cfg, size, seed=2000 + size[0], objects=objects, **layout)
+    camera = synthetic.default_camera((64, 64)) if size == (64, 64) else \
+        synthetic.default_camera((180, 320)) if size == (180, 320) else \
+        __import__('object_keypoints_b200').camera_utils.FisheyeCamera(
+            np.array([[50.0, 0, size[1] / 2], [0, 50.0, size[0] / 2], [0, 0, 1]]), np.array([0.1, 0.01, -0.02, 0.003]), size)
+    got = gpu_decode(batch.heat, batch.depth, batch.centers, cfg, camera)
+    assert_matches_oracle(got, c_oracle.decode(batch.heat, batch.depth, batch.centers, cfg, camera))
+    assert got['n_objects'].sum() > 0
+
+
+def test_empty_batch_and_single_map():
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    from oracle import c_oracle
+    camera = synthetic.default_camera((64, 64))
+    decoder = KeypointDecoder([1, 3], (64, 64), camera=camera)
+    empty = decoder.decode_batch(np.zeros((0, 3, 64, 64), np.float32), np.zeros((0, 3, 64, 64), np.float32),
+                                 np.zeros((0, 2, 2, 64, 64), np.float32)).numpy()
+    assert empty['n_objects'].shape == (0,)
+    # C = 1: only the centre map, no spokes
+    batch = synthetic.make_batch(4, [], (64, 64), seed=9, objects=(1, 3))
+    got = gpu_decode(batch.heat, batch.depth, batch.centers, [], camera)
+    assert_matches_oracle(got, c_oracle.decode(batch.heat, batch.depth, batch.centers, [], camera))
+
+
+def test_capacity_overflow_keeps_first_peaks_in_raster_order():
+    """Random-init network output (config 5): ~0.5 everywhere, dozens of noise peaks per map. The
+    table keeps the first max_peaks in raster order and raises the overflow flags."""
+    from oracle import c_oracle, np_oracle
+    from object_keypoints_b200 import synthetic
+    rng = np.random.default_rng(5)
+    heat = (0.5 + 0.002 * rng.standard_normal((3, 3, 64, 64))).astype(np.float32)
+    depth = np.ones_like(heat)
+    centers = rng.normal(0, 3, (3, 2, 2, 64, 64)).astype(np.float32)
+    camera = synthetic.default_camera((64, 64))
+    options = dict(max_peaks=16, max_objects=8, max_votes=4)
+    got = gpu_decode(heat, depth, centers, [1, 3], camera, **options)
+    want = c_oracle.decode(heat, depth, centers, [1, 3], camera, **options)
+    assert (want['peak_count'] > 16).all()
+    assert (got['flags'] & np_oracle.FLAG_PEAK_OVERFLOW).all() and (got['flags'] & np_oracle.FLAG_OBJECT_OVERFLOW).all()
+    assert_matches_oracle(got, want)
+    # and with room for everything the clustering branch (cfg > 1 overflow) is exercised identically
+    options = dict(max_peaks=128, max_objects=128, max_votes=16)
+    got = gpu_decode(heat, depth, centers, [1, 3], camera, **options)
+    want = c_oracle.decode(heat, depth, centers, [1, 3], camera, **options)
+    assert (got['flags'] & np_oracle.FLAG_CLUSTERED).any()
+    for key in ['peak_count', 'peak_yx', 'peak_object', 'n_objects', 'flags', 'kp_assigned', 'kp_count', 'kp_peak']:
+        np.testing.assert_array_equal(got[key], want[key], err_msg=key)
+    assert np.abs(got['kp_xy'] - want['kp_xy']).max() <= TOL_PIXELS
+
+
+def test_non_square_clip_rule_and_its_switch():
+    """pipeline.py:162,169 clips x with H-1: at 180x320 a keypoint at x = 250 reads depth column 179."""
+    from oracle import c_oracle
+    from object_keypoints_b200 import synthetic
+    H, W = 180, 320
+    heat = np.zeros((1, 2, H, W), np.float32)
+    jj, ii = np.arange(W)[None, :], np.arange(H)[:, None]
+    for c, (x, y) in enumerate([(250.0, 90.0), (256.0, 92.0)]):
+        heat[0, c] = np.exp(-((x - jj) ** 2 + (y - ii) ** 2) / 4.0)
+    depth = np.tile(np.arange(W, dtype=np.float32)[None, None, None, :] / 100.0 + 0.5, (1, 2, H, 1))
+    centers = np.zeros((1, 1, 2, H, W), np.float32)
+    centers[0, 0, 0] = 250.0 - (jj + 0.5)
+    centers[0, 0, 1] = 90.0 - (ii + 0.5)
+    camera = synthetic.default_camera((H, W))
+    for bug in (True, False):
+        got = gpu_decode(heat, depth, centers, [1], camera, compat_clip_bug=bug)
+        want = c_oracle.decode(heat, depth, centers, [1], camera, compat_clip_bug=bug)
+        assert_matches_oracle(got, want)
+        z = got['kp_point'][0, 0, 0, 0, 2]
+        assert abs(z - (1.79 + 0.5 if bug else depth[0, 0, 90, int(round(got['kp_point'][0, 0, 0, 0, 0] / z * camera.K[0, 0] + camera.K[0, 2]))])) < 1e-5
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 4 size (4096 frames) is too big for the oracle in a test: check invariants
+    instead -- every frame finds its 8 objects with complete keypoint sets, results do not depend on
+    batch composition (decode of a sub-batch is identical), and repeated runs are deterministic."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    N = 4096
+    heat, depth, centers, n_obj = synthetic.torch_grid_batch(N, [1, 3], (64, 128), seed=3, grid=(4, 2), device='cuda')
+    camera = synthetic.default_camera((180, 320))
+    decoder = KeypointDecoder([1, 3], (64, 128), camera=camera)
+    t = decoder.decode_batch(heat, depth, centers)
+    full = {k: v.clone() for k, v in t.tensors.items()}
+    assert (full['n_objects'] == n_obj).float().mean() > 0.99
+    ok = full['n_objects'] == n_obj
+    assert (full['kp_count'][ok][:, :n_obj].sum(dim=(1, 2)) == n_obj * 5).float().mean() > 0.95
+    # sub-batch independence and determinism
+    sub = slice(1000, 1064)
+    t2 = KeypointDecoder([1, 3], (64, 128), camera=camera).decode_batch(heat[sub], depth[sub], centers[sub])
+    for key in full:
+        assert torch.equal(t2[key], full[key][sub]), key
+    t3 = decoder.decode_batch(heat, depth, centers)
+    for key in full:
+        a, b = t3[key], full[key]
+        assert torch.equal(a, b) or (a.dtype.is_floating_point and torch.equal(a.isnan(), b.isnan())), key
+
+
+def test_reference_style_api_returns_reference_structures():
+    """ObjectKeypointPipeline(prediction_size, points_3d, keypoint_config).reset(camera)(heat, depth, centers)
+    -> list of dicts with 'p_centers', 'keypoints', 'p_C' shaped like pipeline.py:195-199."""
+    import torch
+    from object_keypoints_b200 import ObjectKeypointPipeline
+    g = load_golden('valve_64.npz')
+    ref = reference_tables(g)
+    pipeline = ObjectKeypointPipeline([64, 64], None, {'keypoint_config': [1, 3]})
+    pipeline.reset(golden_camera(g))
+    with pytest.raises(AssertionError):
+        pipeline(torch.tensor(g['heat'][:2]), torch.tensor(g['depth'][:2]), torch.tensor(g['centers'][:2]))
+    for n in range(4):
+        objects = pipeline(torch.tensor(g['heat'][n:n + 1]), torch.tensor(g['depth'][n:n + 1]),
+                           torch.tensor(g['centers'][n:n + 1]))
+        assert len(objects) == ref['n_objects'][n]
+        for o, obj in enumerate(objects):
+            assert set(obj) == {'p_centers', 'keypoints', 'p_C'}
+            assert len(obj['keypoints']) == 3 and len(obj['p_C']) == 3
+            assert obj['keypoints'][0].shape == (1, 2) and obj['keypoints'][0].dtype == np.float32
+            assert obj['p_C'][0].shape == (1, 3) and obj['p_C'][0].dtype == np.float64
+            for c in range(3):
+                cnt = ref['kp_count'][n, o, c]
+                assert obj['keypoints'][c].shape[0] == cnt
+                assert np.abs(obj['keypoints'][c] - ref['kp_xy'][n, o, c, :cnt]).max() <= TOL_PIXELS
+                want = ref['kp_point'][n, o, c, :cnt]
+                assert np.abs(obj['p_C'][c] - want).max() <= TOL_METRES_REL * np.abs(want).max()
+            assert len(obj['p_centers']) == ref['n_votes'][n, o]
+
+
+def test_component_level_api():
+    from object_keypoints_b200 import KeypointExtractionComponent, ObjectExtraction, DetectionToPoint
+    from oracle import c_oracle
+    g = load_golden('cups_64.npz')
+    ref = reference_tables(g)
+    cfg = {'keypoint_config': [1, 1, 1]}
+    extraction = KeypointExtractionComponent(cfg, [64, 64])
+    keypoints, confidence = extraction(g['heat'][:3])
+    assert len(keypoints) == 3 and len(keypoints[0]) == 4
+    for n in range(3):
+        for c in range(4):
+            k = ref['peak_count'][n, c]
+            assert len(keypoints[n][c]) == k
+            for j in range(k):
+                assert np.abs(keypoints[n][c][j] - ref['peak_xy'][n, c, j]).max() <= TOL_PIXELS
+                assert abs(float(confidence[n][c][j]) - ref['peak_conf'][n, c, j]) <= 1e-5 * ref['peak_conf'][n, c, j]
+    grouping = ObjectExtraction(cfg, [64, 64])
+    objects = grouping(keypoints[0], confidence[0], g['centers'][0])
+    assert len(objects) == ref['n_objects'][0]
+    for o, obj in enumerate(objects):
+        assert set(obj) >= {'center', 'heatmap_points', 'p_centers'}
+        assert np.abs(obj['center'] - ref['kp_xy'][0, o, 0, 0]).max() <= TOL_PIXELS
+        for c in range(1, 4):
+            cnt = ref['kp_count'][0, o, c]
+            assert np.asarray(obj['heatmap_points'][c - 1]).reshape(-1, 2).shape[0] == cnt
+    assert ObjectExtraction(cfg, [64, 64])([[], [], [], []], [[], [], [], []], g['centers'][0]) == []
+    to_point = DetectionToPoint()
+    camera = golden_camera(g)
+    to_point.reset(camera)
+    assert to_point(np.zeros((0, 2)), g['depth'][0, 0]) is None
+    xy = ref['kp_xy'][0, 0, 1, :1]
+    got = to_point(xy, g['depth'][0, 1])
+    want = c_oracle.detection_to_point(xy, g['depth'][0, 1], camera)
+    assert np.abs(got - want).max() <= TOL_METRES_REL * np.abs(want).max()

@@ -1,0 +1,112 @@
+"""Camera geometry and triangulation kernels against OpenCV goldens and the C oracle."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, TOL_METRES_REL
+
+pytestmark = pytest.mark.gpu
+
+
+def cameras(g):
+    from object_keypoints_b200 import camera_utils
+    left = camera_utils.FisheyeCamera(g['K_left'], g['D_left'], [720, 1280])
+    right = camera_utils.FisheyeCamera(g['K_right'], g['D_right'], [720, 1280])
+    return left, right
+
+
+def test_project_and_undistort_match_opencv():
+    from object_keypoints_b200 import project_points, undistort_points, camera_utils
+    g = load_golden('geometry.npz')
+    left, right = cameras(g)
+    assert np.abs(project_points(g['X'], g['T_CW'], left).cpu().numpy() - g['project_left']).max() < 1e-8
+    assert np.abs(project_points(g['X'], g['T_RL'] @ g['T_CW'], right).cpu().numpy() - g['project_right']).max() < 1e-8
+    for tag in ['full', 'small', 'net']:
+        cam = camera_utils.FisheyeCamera(g[f'K_{tag}'], g[f'D_{tag}'], g[f'image_size_{tag}'])
+        out = undistort_points(g[f'undistort_in_{tag}'], cam).cpu().numpy()
+        assert np.abs(out - g[f'undistort_out_{tag}']).max() < 1e-8
+        out32 = undistort_points(g[f'undistort_in_{tag}'].astype(np.float32).astype(np.float64), cam, round_to_f32=True)
+        diff = np.abs(out32.cpu().numpy().astype(np.float32) - g[f'undistort_out32_{tag}'])
+        assert diff.max() <= 1.5e-4 and (diff > 0).mean() < 0.01        # float32 ulp at ~1e3 px, rare
+
+
+def test_two_view_dlt_matches_cv2_triangulate_points():
+    from object_keypoints_b200 import triangulate
+    g = load_golden('geometry.npz')
+    pts = np.stack([g['pairs_undistorted_left'], g['pairs_undistorted_right']], axis=1)
+    X = triangulate(pts, np.stack([g['P1'], g['P2']])).cpu().numpy()
+    rel = np.linalg.norm(X - g['pairs_plain_dlt'], axis=1) / np.linalg.norm(g['pairs_plain_dlt'], axis=1)
+    assert rel.max() < 1e-8
+
+
+def test_golden_pixel_vectors_of_reference_tests():
+    """test/test_pipeline.py:171-177 through the TriangulationComponent API."""
+    from object_keypoints_b200 import TriangulationComponent, camera_utils
+    g = load_golden('geometry.npz')
+    left, right = cameras(g)
+    stereo = camera_utils.StereoCamera(left, right, g['T_RL'])
+    triangulation = TriangulationComponent()
+    triangulation.reset(stereo)
+    p_W = triangulation(g['golden_left'], g['golden_right'])
+    np.testing.assert_array_less(np.linalg.norm(p_W - g['golden_keypoints'], axis=1), 1e-3)
+
+
+def test_multiview_dlt_matches_oracle_and_recovers_points():
+    """Config 3 shape: 40 points x 16 views, 0.3 px noise, 5% gross outliers, 2 px gate."""
+    from object_keypoints_b200 import triangulate, triangulate_multiview, synthetic
+    from oracle import c_oracle, np_oracle
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(1003)
+    camera = synthetic.default_camera((180, 320)).scale(4.0)      # 720x1280 camera
+    P, V = 40, 16
+    X = np.stack([rng.uniform(-0.3, 0.3, P), rng.uniform(-0.2, 0.2, P), rng.uniform(-0.05, 0.05, P)], axis=1)
+    poses = np.zeros((V, 4, 4))
+    for v in range(V):
+        R = Rotation.from_rotvec(rng.normal(0, 0.25, 3)).as_matrix()
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = -R @ np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), -rng.uniform(0.6, 1.0)])
+        poses[v] = T
+    obs = np.stack([camera.project(X, poses[v]) for v in range(V)], axis=1) + rng.normal(0, 0.3, (P, V, 2))
+    outliers = rng.uniform(size=(P, V)) < 0.05
+    obs[outliers] += rng.normal(0, 20.0, (int(outliers.sum()), 2))
+    # plain V-view DLT: CUDA vs both oracles
+    undist = np.stack([camera.undistort(obs[:, v]) for v in range(V)], axis=1)
+    proj = np.stack([camera.K @ poses[v][:3] for v in range(V)])
+    valid = np.ones((P, V), np.uint8)
+    got = triangulate(undist, proj, valid).cpu().numpy()
+    for want in (c_oracle.triangulate(undist, valid, proj), np_oracle.triangulate_dlt(undist, valid.astype(bool), proj)):
+        assert (np.linalg.norm(got - want, axis=1) <= 1e-7 * np.linalg.norm(want, axis=1) + 1e-10).all()
+    # gate + re-solve
+    Xf, valid_f, err = triangulate_multiview(obs, None, poses, camera, max_error_px=2.0, rounds=2)
+    Xf, valid_f, err = Xf.cpu().numpy(), valid_f.cpu().numpy(), err.cpu().numpy()
+    v0, e0 = c_oracle.reprojection_filter(got, obs, valid, poses, camera, 2.0)
+    assert np.linalg.norm(Xf - X, axis=1).max() < 5e-3
+    assert np.linalg.norm(Xf - X, axis=1).mean() < np.linalg.norm(got - X, axis=1).mean()
+    assert valid_f[outliers & (np.linalg.norm(obs - np.stack([camera.project(X, poses[v]) for v in range(V)], axis=1), axis=2) > 6)].sum() == 0
+    # per-point projections and masks
+    per_point = np.broadcast_to(proj[None], (P, V, 3, 4)).copy()
+    got2 = triangulate(undist, per_point, valid).cpu().numpy()
+    np.testing.assert_allclose(got2, got, rtol=1e-12, atol=1e-14)
+    few = valid.copy()
+    few[0, 1:] = 0
+    assert np.isnan(triangulate(undist, proj, few).cpu().numpy()[0]).all()
+
+
+def test_stereo_pipeline_end_to_end_like_reference_test():
+    """test/test_pipeline.py:179-206: extraction on both views + triangulation within 5e-2 m."""
+    from object_keypoints_b200 import KeypointExtractionComponent, TriangulationComponent, camera_utils
+    g = load_golden('test_pipeline_180x320.npz')
+    geo = load_golden('geometry.npz')
+    left, right = cameras(geo)
+    stereo_small = camera_utils.StereoCamera(left.scale(180 / 720), right.scale(180 / 720), g['T_RL'])
+    extraction = KeypointExtractionComponent({'keypoint_config': [1, 3]}, [180, 320])
+    keypoints, _ = extraction(g['heat'])
+    triangulation = TriangulationComponent()
+    triangulation.reset(stereo_small)
+    for c, count in enumerate([1, 1, 3]):
+        L, R = np.stack(keypoints[0][c]), np.stack(keypoints[1][c])
+        assert L.shape[0] == R.shape[0] == count
+        X = triangulation(L, R)
+        assert X.shape == (count, 3)
+    X0 = triangulation(np.stack(keypoints[0][0]), np.stack(keypoints[1][0]))
+    assert np.linalg.norm(X0[0] - g['keypoints_3d'][0]) < 5e-2
