@@ -166,6 +166,18 @@ int okp_reprojection_filter_f64(const double* X_dev, const double* obs_dev, uint
                                 const double* poses_dev, const OkpCamera* camera, int P, int V,
                                 double max_error_px, double* err_dev, void* stream);
 
+/* Robust multi-view triangulation, K5 and K6 fused (north_star: "batched multi-view DLT ... and
+ * reprojection-error filtering"; the reference stops at two views, scripts/label.py:285-305).
+ * Per point: undistort the valid observations (camera_utils.py:75-81), V-view DLT with the
+ * projections K * poses[v][:3] (camera_utils.py:125-130), reprojection error of every view; while
+ * the worst valid view is farther than max_error_px, more than two views remain and fewer than
+ * max_rounds views were dropped: drop it and solve again. obs_dev [P,V,2] DISTORTED pixels,
+ * valid_dev [P,V] in/out (NULL = all valid, nothing written back), poses_dev [V,4,4] world->camera,
+ * out_dev [P,3], err_dev [P,V] error against the final point, dropped_dev [P] (may be NULL). */
+int okp_triangulate_robust_f64(const double* obs_dev, uint8_t* valid_dev, const double* poses_dev,
+                               const OkpCamera* camera, int P, int V, double max_error_px, int max_rounds,
+                               double* out_dev, double* err_dev, int32_t* dropped_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -225,4 +225,17 @@ int okp_reprojection_filter_f64(const double* X_dev, const double* obs_dev, uint
     return OKP_OK;
 }
 
+int okp_triangulate_robust_f64(const double* obs_dev, uint8_t* valid_dev, const double* poses_dev,
+                               const OkpCamera* camera, int P, int V, double max_error_px, int max_rounds,
+                               double* out_dev, double* err_dev, int32_t* dropped_dev, void* stream) {
+    if (P < 0 || V < 1 || V > OKP_MAX_VIEWS || max_rounds < 0) return OKP_E_SHAPE;
+    if (P == 0) return OKP_OK;
+    if (!obs_dev || !poses_dev || !camera || !out_dev || !err_dev) return OKP_E_NULL;
+    const size_t smem = sizeof(double) * 24 * (size_t)V;
+    okp_triangulate_robust_kernel<<<(P + 127) / 128, 128, smem, (cudaStream_t)stream>>>(
+        obs_dev, valid_dev, poses_dev, *camera, P, V, max_error_px, max_rounds, out_dev, err_dev, dropped_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
 }  // extern "C"

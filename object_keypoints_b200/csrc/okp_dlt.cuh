@@ -10,6 +10,7 @@
 // of R yields the vector.
 #pragma once
 #include "okp_common.cuh"
+#include "okp_geometry.cuh"
 
 __device__ __forceinline__ void okp_givens_append(double (&R)[4][4], double (&a)[4]) {
 #pragma unroll
@@ -113,4 +114,78 @@ okp_triangulate_kernel(const double* __restrict__ points, const uint8_t* __restr
     out[3 * (size_t)p] = h[0] / h[3];
     out[3 * (size_t)p + 1] = h[1] / h[3];
     out[3 * (size_t)p + 2] = h[2] / h[3];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 + K6 fused: robust multi-view triangulation, one thread per 3D point.
+//   repeat: V-view DLT over the valid views -> reprojection error of every view (distorted
+//   pixels, okp_project_point) -> if the worst valid view is farther than max_error and more
+//   than two views remain, drop it and solve again (at most max_rounds drops).
+// The reference has no N-view code: the statement of record is
+// oracle/np_oracle.py::triangulate_robust. The valid mask lives in one 64-bit register.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+okp_triangulate_robust_kernel(const double* __restrict__ obs, uint8_t* __restrict__ valid,
+                              const double* __restrict__ poses, OkpCamera cam, int P, int V, double max_error,
+                              int max_rounds, double* __restrict__ out, double* __restrict__ err,
+                              int32_t* __restrict__ dropped) {
+    extern __shared__ double s_pose[];                 // [V][12] world -> camera, then [V][12] K * pose
+    double* s_proj = s_pose + 12 * V;
+    for (int i = threadIdx.x; i < V * 12; i += blockDim.x) s_pose[i] = poses[(i / 12) * 16 + (i % 12)];
+    __syncthreads();
+    for (int i = threadIdx.x; i < V * 12; i += blockDim.x) {          // camera_utils.py:125-130: K @ T[:3]
+        const int v = i / 12, r = (i % 12) / 4, c = i % 4;
+        const double* T = s_pose + 12 * v;
+        s_proj[i] = r == 0 ? cam.fx * T[c] + cam.cx * T[8 + c] : (r == 1 ? cam.fy * T[4 + c] + cam.cy * T[8 + c] : T[8 + c]);
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    unsigned long long mask = 0;
+    for (int v = 0; v < V; ++v)
+        if (!valid || valid[(size_t)p * V + v]) mask |= 1ull << v;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double X[3] = {nan, nan, nan};
+    int drops = 0;
+    for (;;) {
+        double R[4][4] = {};
+        const int views = __popcll(mask);
+        if (views < 2) { X[0] = X[1] = X[2] = nan; break; }
+        for (int v = 0; v < V; ++v) {
+            if (!((mask >> v) & 1ull)) continue;
+            const size_t pv = (size_t)p * V + v;
+            double x, y;
+            okp_undistort_point(obs[2 * pv], obs[2 * pv + 1], cam, &x, &y);
+            const double* M = s_proj + v * 12;
+            double row[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) row[c] = x * M[8 + c] - M[c];
+            okp_givens_append(R, row);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) row[c] = y * M[8 + c] - M[4 + c];
+            okp_givens_append(R, row);
+        }
+        double h[4];
+        okp_smallest_right_singular_vector(R, h);
+        X[0] = h[0] / h[3]; X[1] = h[1] / h[3]; X[2] = h[2] / h[3];
+        int worst = -1;
+        double worst_err = 0.0;
+        for (int v = 0; v < V; ++v) {
+            const size_t pv = (size_t)p * V + v;
+            double uu, vv;
+            okp_project_point(X, s_pose + 12 * v, cam, &uu, &vv);
+            const double dx = uu - obs[2 * pv], dy = vv - obs[2 * pv + 1];
+            const double e = sqrt(dx * dx + dy * dy);
+            err[pv] = e;
+            const double rank = e == e ? e : INFINITY;                 // a NaN error counts as the worst
+            if (((mask >> v) & 1ull) && (worst < 0 || rank > worst_err)) { worst = v; worst_err = rank; }   // first maximum
+        }
+        if (!(worst_err > max_error) || views <= 2 || drops >= max_rounds) break;
+        mask &= ~(1ull << worst);
+        ++drops;
+    }
+    if (valid)
+        for (int v = 0; v < V; ++v) valid[(size_t)p * V + v] = (uint8_t)((mask >> v) & 1ull);
+    out[3 * (size_t)p] = X[0]; out[3 * (size_t)p + 1] = X[1]; out[3 * (size_t)p + 2] = X[2];
+    if (dropped) dropped[p] = drops;
 }

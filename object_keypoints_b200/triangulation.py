@@ -90,26 +90,34 @@ def reprojection_filter(X, observations, valid, poses, camera, max_error_px, dev
     return valid, err
 
 
-def triangulate_multiview(observations, valid, poses, camera, max_error_px=2.0, rounds=1, device=None):
-    """Config-3 path: observations [P,V,2] distorted pixels seen from poses [V,4,4] (world->camera)
-    with one equidistant camera. Undistort, V-view DLT, drop views whose reprojection error exceeds
-    max_error_px, solve again. Returns (X [P,3], valid [P,V], error [P,V]) CUDA tensors."""
+def triangulate_multiview(observations, valid, poses, camera, max_error_px=2.0, max_rounds=None, device=None,
+                          return_dropped=False):
+    """Config-3 path in ONE kernel (okp_triangulate_robust_f64): observations [P,V,2] distorted pixels
+    seen from poses [V,4,4] (world->camera) with one equidistant camera. Per point: undistort, V-view
+    DLT, reprojection error per view; while the worst valid view is farther than max_error_px (and
+    more than two views remain, at most max_rounds drops) drop it and solve again.
+    Returns (X [P,3], valid [P,V] uint8, error [P,V]) CUDA tensors."""
     device = _device(device)
     observations = _as_f64(observations, device)
     P, V = int(observations.shape[0]), int(observations.shape[1])
     poses_t = _as_f64(poses, device)
-    K = torch.from_numpy(np.asarray(camera.K, dtype=np.float64)).to(device)
-    projections = K @ poses_t[:, :3, :]                              # camera_utils.py:125-130
-    undistorted = undistort_points(observations.reshape(-1, 2), camera, device=device).reshape(P, V, 2)
     if valid is None:
         valid = torch.ones((P, V), dtype=torch.uint8, device=device)
-    X = triangulate(undistorted, projections, valid, device=device)
-    err = None
-    for _ in range(rounds):
-        valid, err = reprojection_filter(X, observations, valid, poses_t, camera, max_error_px, device=device)
-        X = triangulate(undistorted, projections, valid, device=device)
-    if err is None:
-        _, err = reprojection_filter(X, observations, valid, poses_t, camera, float('inf'), device=device)
+    else:
+        if isinstance(valid, np.ndarray):
+            valid = torch.from_numpy(np.ascontiguousarray(valid))
+        valid = valid.to(device=device, dtype=torch.uint8).contiguous().clone()
+    X = torch.empty((P, 3), dtype=torch.float64, device=device)
+    err = torch.empty((P, V), dtype=torch.float64, device=device)
+    dropped = torch.zeros((P,), dtype=torch.int32, device=device)
+    cam = _abi.pack_camera(camera)
+    rounds = V if max_rounds is None else int(max_rounds)
+    rc = _lib.lib().okp_triangulate_robust_f64(observations.data_ptr(), valid.data_ptr(), poses_t.data_ptr(),
+                                               ctypes.byref(cam), P, V, float(max_error_px), rounds, X.data_ptr(),
+                                               err.data_ptr(), dropped.data_ptr(), _stream_handle())
+    _lib.check(rc, 'okp_triangulate_robust_f64')
+    if return_dropped:
+        return X, valid, err, dropped
     return X, valid, err
 
 

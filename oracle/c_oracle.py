@@ -28,6 +28,7 @@ def lib():
         _LIB = ctypes.CDLL(path)
         _LIB.okp_oracle_decode_f32.restype = ctypes.c_int
         _LIB.okp_oracle_triangulate_f64.restype = ctypes.c_int
+        _LIB.okp_oracle_triangulate_robust_f64.restype = ctypes.c_int
         _LIB.okp_oracle_max_threads.restype = ctypes.c_int
     return _LIB
 
@@ -122,3 +123,20 @@ def reprojection_filter(X, obs, valid, poses, camera, max_error_px):
     lib().okp_oracle_reprojection_filter_f64(_ptr(X), _ptr(obs), _ptr(valid), _ptr(poses), ctypes.byref(cam),
                                              P, V, ctypes.c_double(max_error_px), _ptr(err))
     return valid, err
+
+
+def triangulate_robust(obs, valid, poses, camera, max_error_px, max_rounds):
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    P, V = obs.shape[:2]
+    valid = np.ones((P, V), np.uint8) if valid is None else np.ascontiguousarray(valid, dtype=np.uint8).copy()
+    poses = np.ascontiguousarray(poses, dtype=np.float64)
+    X = np.empty((P, 3), dtype=np.float64)
+    err = np.empty((P, V), dtype=np.float64)
+    dropped = np.zeros((P,), dtype=np.int32)
+    cam = _abi.pack_camera(camera)
+    rc = lib().okp_oracle_triangulate_robust_f64(_ptr(obs), _ptr(valid), _ptr(poses), ctypes.byref(cam), P, V,
+                                                 ctypes.c_double(max_error_px), int(max_rounds), _ptr(X), _ptr(err),
+                                                 _ptr(dropped))
+    if rc != 0:
+        raise RuntimeError(f"oracle triangulate_robust failed: {_abi.ERRORS.get(rc, rc)}")
+    return X, valid, err, dropped

@@ -351,3 +351,43 @@ def triangulate_dlt(points, valid, projections):
         h = vt[-1]
         X[p] = h[:3] / h[3]
     return X
+
+
+# ------------------------------------------------------------------------------------------
+# north_star K5 + K6 (no reference code beyond two views): robust V-view triangulation
+# ------------------------------------------------------------------------------------------
+def triangulate_robust(obs, valid, poses, cam, K, max_error_px=2.0, max_rounds=None):
+    """obs [P,V,2] DISTORTED pixels, valid [P,V], poses [V,4,4] world->camera, cam = camera_dict,
+    K = 3x3 camera matrix. Per point: DLT over the valid views of the undistorted observations with
+    projections K @ poses[v][:3]; reprojection error (distorted pixels) of every view; while the
+    worst valid view (first maximum) exceeds max_error_px, more than two views remain and fewer
+    than max_rounds were dropped: drop it and solve again. PARITY UNPINNED (absent from the
+    reference); reduces to triangulate_dlt when nothing exceeds the gate.
+    -> (X [P,3], valid [P,V] uint8, err [P,V], dropped [P])"""
+    obs = np.asarray(obs, dtype=np.float64)
+    P, V = obs.shape[:2]
+    max_rounds = V if max_rounds is None else max_rounds
+    mask = np.ones((P, V), bool) if valid is None else np.asarray(valid).astype(bool).copy()
+    proj = np.stack([np.asarray(K) @ np.asarray(poses[v])[:3] for v in range(V)])
+    und = np.array([[undistort_point(obs[p, v, 0], obs[p, v, 1], cam) for v in range(V)] for p in range(P)])
+    X = np.full((P, 3), np.nan)
+    err = np.zeros((P, V))
+    dropped = np.zeros(P, np.int32)
+    for p in range(P):
+        while True:
+            views = int(mask[p].sum())
+            if views < 2:
+                X[p] = np.nan
+                break
+            X[p] = triangulate_dlt(und[p:p + 1], mask[p:p + 1], proj)[0]
+            for v in range(V):
+                uv = project_points(X[p:p + 1], poses[v], cam)[0]
+                err[p, v] = np.hypot(uv[0] - obs[p, v, 0], uv[1] - obs[p, v, 1])
+            rank = np.where(np.isnan(err[p]), np.inf, err[p])
+            rank = np.where(mask[p], rank, -1.0)
+            worst = int(rank.argmax())
+            if not (rank[worst] > max_error_px) or views <= 2 or dropped[p] >= max_rounds:
+                break
+            mask[p, worst] = False
+            dropped[p] += 1
+    return X, mask.astype(np.uint8), err, dropped

@@ -488,3 +488,56 @@ int okp_oracle_reprojection_filter_f64(const double* X, const double* obs, uint8
         }
     return OKP_OK;
 }
+
+/* robust V-view triangulation: DLT, reprojection errors, drop the worst view above the gate, repeat
+ * (north_star K5 + K6; no reference code -- same statement as np_oracle.triangulate_robust) */
+int okp_oracle_triangulate_robust_f64(const double* obs, uint8_t* valid, const double* poses, const OkpCamera* cam,
+                                      int P, int V, double max_error_px, int max_rounds, double* out, double* err,
+                                      int32_t* dropped) {
+    if (!obs || !poses || !cam || !out || !err) return OKP_E_NULL;
+    if (V < 1 || V > OKP_MAX_VIEWS || P < 0) return OKP_E_SHAPE;
+    double proj[OKP_MAX_VIEWS * 12];
+    for (int v = 0; v < V; ++v) {
+        const double* T = poses + (size_t)v * 16;
+        for (int c = 0; c < 4; ++c) {
+            proj[v * 12 + c] = cam->fx * T[c] + cam->cx * T[8 + c];
+            proj[v * 12 + 4 + c] = cam->fy * T[4 + c] + cam->cy * T[8 + c];
+            proj[v * 12 + 8 + c] = T[8 + c];
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < P; ++p) {
+        uint8_t mask[OKP_MAX_VIEWS];
+        double und[OKP_MAX_VIEWS * 2];
+        for (int v = 0; v < V; ++v) {
+            mask[v] = valid ? (valid[(size_t)p * V + v] != 0) : 1;
+            okp_oracle_undistort_f64(obs + ((size_t)p * V + v) * 2, 1, cam, 0, und + 2 * v);
+        }
+        int drops = 0;
+        double X[3] = {NAN, NAN, NAN};
+        for (;;) {
+            int views = 0;
+            for (int v = 0; v < V; ++v) views += mask[v];
+            if (views < 2) { X[0] = X[1] = X[2] = NAN; break; }
+            okp_oracle_triangulate_f64(und, mask, proj, 0, 1, V, X);
+            int worst = -1;
+            double worst_err = 0.0;
+            for (int v = 0; v < V; ++v) {
+                double uv[2];
+                okp_oracle_project_f64(X, 1, poses + (size_t)v * 16, cam, uv);
+                const double dx = uv[0] - obs[((size_t)p * V + v) * 2], dy = uv[1] - obs[((size_t)p * V + v) * 2 + 1];
+                const double e = sqrt(dx * dx + dy * dy);
+                err[(size_t)p * V + v] = e;
+                const double rank = e == e ? e : INFINITY;
+                if (mask[v] && (worst < 0 || rank > worst_err)) { worst = v; worst_err = rank; }
+            }
+            if (!(worst_err > max_error_px) || views <= 2 || drops >= max_rounds) break;
+            mask[worst] = 0;
+            ++drops;
+        }
+        if (valid) for (int v = 0; v < V; ++v) valid[(size_t)p * V + v] = mask[v];
+        out[3 * p] = X[0]; out[3 * p + 1] = X[1]; out[3 * p + 2] = X[2];
+        if (dropped) dropped[p] = drops;
+    }
+    return OKP_OK;
+}

@@ -76,13 +76,29 @@ def test_multiview_dlt_matches_oracle_and_recovers_points():
     got = triangulate(undist, proj, valid).cpu().numpy()
     for want in (c_oracle.triangulate(undist, valid, proj), np_oracle.triangulate_dlt(undist, valid.astype(bool), proj)):
         assert (np.linalg.norm(got - want, axis=1) <= 1e-7 * np.linalg.norm(want, axis=1) + 1e-10).all()
-    # gate + re-solve
-    Xf, valid_f, err = triangulate_multiview(obs, None, poses, camera, max_error_px=2.0, rounds=2)
-    Xf, valid_f, err = Xf.cpu().numpy(), valid_f.cpu().numpy(), err.cpu().numpy()
-    v0, e0 = c_oracle.reprojection_filter(got, obs, valid, poses, camera, 2.0)
+    # robust form (one kernel): drop the worst view above the 2 px gate, solve again -- vs both oracles
+    Xf, valid_f, err, dropped = triangulate_multiview(obs, None, poses, camera, max_error_px=2.0, return_dropped=True)
+    Xf, valid_f, err, dropped = Xf.cpu().numpy(), valid_f.cpu().numpy(), err.cpu().numpy(), dropped.cpu().numpy()
+    Xc, valid_c, err_c, dropped_c = c_oracle.triangulate_robust(obs, None, poses, camera, 2.0, V)
+    np.testing.assert_array_equal(valid_f, valid_c)
+    np.testing.assert_array_equal(dropped, dropped_c)
+    assert (np.linalg.norm(Xf - Xc, axis=1) <= 1e-7 * np.linalg.norm(Xc, axis=1) + 1e-10).all()
+    np.testing.assert_allclose(err, err_c, rtol=0, atol=1e-6)
+    Xn, valid_n, _, _ = np_oracle.triangulate_robust(obs, None, poses, np_oracle.camera_dict(camera), camera.K, 2.0)
+    np.testing.assert_array_equal(valid_f, valid_n)
+    assert (np.linalg.norm(Xf - Xn, axis=1) <= 1e-7 * np.linalg.norm(Xn, axis=1) + 1e-10).all()
+    assert np.isfinite(Xf).all()
     assert np.linalg.norm(Xf - X, axis=1).max() < 5e-3
     assert np.linalg.norm(Xf - X, axis=1).mean() < np.linalg.norm(got - X, axis=1).mean()
-    assert valid_f[outliers & (np.linalg.norm(obs - np.stack([camera.project(X, poses[v]) for v in range(V)], axis=1), axis=2) > 6)].sum() == 0
+    true_err = np.linalg.norm(obs - np.stack([camera.project(X, poses[v]) for v in range(V)], axis=1), axis=2)
+    assert valid_f[outliers & (true_err > 6)].sum() == 0
+    assert (err[valid_f.astype(bool)] <= 2.0).all()
+    # the plain gate (every view above the threshold at once) against the C oracle
+    from object_keypoints_b200 import reprojection_filter
+    v1, e1 = reprojection_filter(got, obs, valid, poses, camera, 2.0)
+    v0, e0 = c_oracle.reprojection_filter(got, obs, valid, poses, camera, 2.0)
+    np.testing.assert_array_equal(v1.cpu().numpy(), v0)
+    np.testing.assert_allclose(e1.cpu().numpy(), e0, rtol=0, atol=1e-8)
     # per-point projections and masks
     per_point = np.broadcast_to(proj[None], (P, V, 3, 4)).copy()
     got2 = triangulate(undist, per_point, valid).cpu().numpy()

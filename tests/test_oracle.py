@@ -118,3 +118,46 @@ def test_kmeans_stand_in_merges_double_detection():
     cen = np_oracle.cluster_detections(pts, 3)
     want = np.array([[10.3, 10.1], [20.0, 10.0], [10.0, 22.0]])
     assert np.abs(np.sort(cen, axis=0) - np.sort(want, axis=0)).max() < 1e-5
+
+
+def _multiview_scene(seed=1003, P=40, V=16):
+    """BASELINE config 3 shape: P points seen from V poses, 0.3 px noise, 5 % gross outliers."""
+    from object_keypoints_b200 import synthetic
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    camera = synthetic.default_camera((180, 320)).scale(4.0)
+    X = np.stack([rng.uniform(-0.3, 0.3, P), rng.uniform(-0.2, 0.2, P), rng.uniform(-0.05, 0.05, P)], axis=1)
+    poses = np.zeros((V, 4, 4))
+    for v in range(V):
+        R = Rotation.from_rotvec(rng.normal(0, 0.25, 3)).as_matrix()
+        poses[v] = np.eye(4)
+        poses[v][:3, :3] = R
+        poses[v][:3, 3] = -R @ np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), -rng.uniform(0.6, 1.0)])
+    clean = np.stack([camera.project(X, poses[v]) for v in range(V)], axis=1)
+    obs = clean + rng.normal(0, 0.3, (P, V, 2))
+    outliers = rng.uniform(size=(P, V)) < 0.05
+    obs[outliers] += rng.normal(0, 20.0, (int(outliers.sum()), 2))
+    return camera, X, poses, obs, clean, outliers
+
+
+def test_robust_multiview_oracles_agree_and_recover_points():
+    camera, X, poses, obs, clean, outliers = _multiview_scene()
+    P, V = obs.shape[:2]
+    Xc, valid_c, err_c, dropped_c = c_oracle.triangulate_robust(obs, None, poses, camera, 2.0, V)
+    Xn, valid_n, err_n, dropped_n = np_oracle.triangulate_robust(obs, None, poses, np_oracle.camera_dict(camera),
+                                                                 camera.K, 2.0)
+    np.testing.assert_array_equal(valid_c, valid_n)
+    np.testing.assert_array_equal(dropped_c, dropped_n)
+    assert (np.linalg.norm(Xc - Xn, axis=1) <= 1e-7 * np.linalg.norm(Xn, axis=1) + 1e-10).all()
+    np.testing.assert_allclose(err_c, err_n, rtol=0, atol=1e-6)
+    assert np.isfinite(Xc).all() and np.linalg.norm(Xc - X, axis=1).max() < 5e-3
+    gross = outliers & (np.linalg.norm(obs - clean, axis=2) > 6)
+    assert gross.sum() > 0 and valid_c[gross].sum() == 0
+    # nothing above the gate -> plain DLT
+    quiet = clean + np.random.default_rng(1).normal(0, 0.02, clean.shape)
+    Xq, valid_q, _, dropped_q = c_oracle.triangulate_robust(quiet, None, poses, camera, 2.0, V)
+    assert dropped_q.sum() == 0 and valid_q.all()
+    und = np.stack([camera.undistort(quiet[:, v]) for v in range(V)], axis=1)
+    proj = np.stack([camera.K @ poses[v][:3] for v in range(V)])
+    plain = c_oracle.triangulate(und, None, proj)
+    assert (np.linalg.norm(Xq - plain, axis=1) <= 1e-9 * np.linalg.norm(plain, axis=1) + 1e-12).all()
