@@ -16,8 +16,9 @@ namespace {
 constexpr int kSmCount = 148;            // B200: 2 dies x 74 SMs
 
 struct PeakPlan {
-    int kernel;                          // 0 = generic tile kernel, 1 = strip kernel
-    OkpTileGeometry geo;
+    bool strip;                          // tuned strip kernel + overflow path, else generic tile kernel + merge
+    OkpStripPlan sp;
+    OkpTileGeometry geo;                 // generic tiles (also the strip kernel's overflow path)
     size_t smem_bytes;
     int grid;
     int tiles_per_map;
@@ -28,18 +29,14 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 PeakPlan plan_peaks(int maps, int H, int W, int K) {
     PeakPlan p;
     memset(&p, 0, sizeof(p));
+    p.strip = okp_strip_plan(maps, H, W, K, &p.sp);
     p.geo.H = H; p.geo.W = W; p.geo.maps = maps;
-    if (okp_strip_plan(maps, H, W, K, &p.geo, &p.smem_bytes)) {
-        p.kernel = 1;
-    } else {
-        p.kernel = 0;
-        p.geo.TW = W <= 64 ? round_up(W, 8) : 64;
-        p.geo.TH = H <= 64 ? H : 32;
-        p.geo.tiles_x = (W + p.geo.TW - 1) / p.geo.TW;
-        p.geo.tiles_y = (H + p.geo.TH - 1) / p.geo.TH;
-        p.smem_bytes = sizeof(float) * ((size_t)(p.geo.TH + 8) * (p.geo.TW + 8) + (size_t)(p.geo.TH + 4) * (p.geo.TW + 4)) +
-                       sizeof(int32_t) * 2 * (size_t)K;
-    }
+    p.geo.TW = W <= 64 ? round_up(W, 8) : 64;
+    p.geo.TH = H <= 64 ? H : 32;
+    p.geo.tiles_x = (W + p.geo.TW - 1) / p.geo.TW;
+    p.geo.tiles_y = (H + p.geo.TH - 1) / p.geo.TH;
+    p.smem_bytes = sizeof(float) * ((size_t)(p.geo.TH + 8) * (p.geo.TW + 8) + (size_t)(p.geo.TH + 4) * (p.geo.TW + 4)) +
+                   sizeof(int32_t) * 2 * (size_t)K;
     p.tiles_per_map = p.geo.tiles_x * p.geo.tiles_y;
     const long long work = (long long)maps * p.tiles_per_map;
     const long long resident = (long long)kSmCount * 8;
@@ -65,6 +62,14 @@ int check_shape(int N, int C, int H, int W) {
     return OKP_OK;
 }
 
+inline int overflow_grid(int maps) { return (maps + 255) / 256 < kSmCount ? (maps + 255) / 256 : kSmCount; }
+
+// tile lists: one per (map, tile) for the generic kernels, one per (overflow CTA, tile) for the strip path
+size_t workspace_for(const PeakPlan& p, int maps, int K, bool strip) {
+    const size_t tiles = strip ? (size_t)overflow_grid(maps) * p.tiles_per_map : (size_t)maps * p.tiles_per_map;
+    return align_up(tiles * sizeof(int32_t), 256) + tiles * K * sizeof(OkpPeakRecord) + 256;
+}
+
 }  // namespace
 
 extern "C" {
@@ -86,9 +91,9 @@ const char* okp_strerror(int code) {
 
 size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodeParams* params) {
     if (check_params(params) != OKP_OK || check_shape(N, C, H, W) != OKP_OK) return 0;
+    if (N == 0) return 256;
     const PeakPlan p = plan_peaks(N * C, H, W, params->max_peaks);
-    const size_t tiles = (size_t)N * C * p.tiles_per_map;
-    return align_up(tiles * sizeof(int32_t), 256) + tiles * params->max_peaks * sizeof(OkpPeakRecord) + 256;
+    return workspace_for(p, N * C, params->max_peaks, p.strip);
 }
 
 int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
@@ -102,20 +107,28 @@ int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, con
     if (!tables->peak_count || !tables->peak_yx || !tables->peak_score || !tables->peak_xy || !tables->peak_conf ||
         !tables->peak_object || !tables->peak_vote)
         return OKP_E_NULL;
-    if (workspace_bytes < okp_decode_workspace_bytes(N, C, H, W, params)) return OKP_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     const int K = params->max_peaks;
     const int maps = N * C;
     const PeakPlan p = plan_peaks(maps, H, W, K);
-    const size_t tiles = (size_t)maps * p.tiles_per_map;
+    const bool strip = p.strip && ((uintptr_t)heat_dev & 15u) == 0;      // TMA needs a 16-byte aligned base
+    if (workspace_bytes < workspace_for(p, maps, K, strip)) return OKP_E_WORKSPACE;
+    const size_t tiles = strip ? (size_t)overflow_grid(maps) * p.tiles_per_map : (size_t)maps * p.tiles_per_map;
     uintptr_t base = align_up((uintptr_t)workspace_dev, 256);
     int32_t* tile_count = (int32_t*)base;
     OkpPeakRecord* tile_peaks = (OkpPeakRecord*)(base + align_up(tiles * sizeof(int32_t), 256));
 
-    if (p.kernel == 1) {
-        rc = okp_strip_launch(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks, p.smem_bytes, s);
+    if (strip) {
+        rc = okp_strip_launch(heat_dev, p.sp, params->threshold, *tables, s);
         if (rc != OKP_OK) return rc;
-    } else {
+        // maps with more than K peaks ("first K in raster order") are redone here; a no-op otherwise
+        auto kernel = okp_peaks_overflow_kernel<256>;
+        OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        kernel<<<overflow_grid(maps), 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks, *tables);
+        OKP_CUDA_CHECK(cudaGetLastError());
+        return OKP_OK;
+    }
+    {
         auto kernel = okp_peaks_generic_kernel<256>;
         OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
         kernel<<<p.grid, 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks);

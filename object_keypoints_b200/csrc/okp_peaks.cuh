@@ -43,22 +43,22 @@ __device__ __forceinline__ void okp_centroid_from_smem(const float* raw, int pit
     *conf = sp;
 }
 
+// Processes one (map, tile) work item with the whole CTA; shared memory as laid out by the kernels below.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-okp_peaks_generic_kernel(const float* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
-                         int32_t* __restrict__ tile_count, OkpPeakRecord* __restrict__ tile_peaks) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void okp_generic_tile(const float* __restrict__ heat, const OkpTileGeometry& g, float threshold,
+                                                 int K, long long work, long long out_index,
+                                                 int32_t* __restrict__ tile_count,
+                                                 OkpPeakRecord* __restrict__ tile_peaks, unsigned char* smem_raw,
+                                                 int* s_count_ptr) {
     const int RP = g.TW + 8;                 // raw pitch
     const int SP = g.TW + 4;                 // score pitch
     float* raw = reinterpret_cast<float*>(smem_raw);
     float* score = raw + (g.TH + 8) * RP;
     int32_t* keys = reinterpret_cast<int32_t*>(score + (g.TH + 4) * SP);
     int32_t* sorted = keys + K;
-    __shared__ int s_count;
-
+    int& s_count = *s_count_ptr;
     const int tiles_per_map = g.tiles_y * g.tiles_x;
-    const long long work_items = (long long)g.maps * tiles_per_map;
-    for (long long work = blockIdx.x; work < work_items; work += gridDim.x) {
+    {
         const int map = (int)(work / tiles_per_map);
         const int tile = (int)(work - (long long)map * tiles_per_map);
         const int ty0 = (tile / g.tiles_x) * g.TH;
@@ -149,7 +149,7 @@ okp_peaks_generic_kernel(const float* __restrict__ heat, OkpTileGeometry g, floa
             sorted[rank] = key;
         }
         __syncthreads();
-        OkpPeakRecord* out = tile_peaks + (size_t)work * K;
+        OkpPeakRecord* out = tile_peaks + (size_t)out_index * K;
         for (int i = threadIdx.x; i < n; i += THREADS) {
             const int key = sorted[i];
             const int gy = key / g.W, gx = key - gy * g.W;
@@ -161,9 +161,20 @@ okp_peaks_generic_kernel(const float* __restrict__ heat, OkpTileGeometry g, floa
             rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
             out[i] = rec;
         }
-        if (threadIdx.x == 0) tile_count[work] = total;
+        if (threadIdx.x == 0) tile_count[out_index] = total;
         __syncthreads();
     }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+okp_peaks_generic_kernel(const float* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
+                         int32_t* __restrict__ tile_count, OkpPeakRecord* __restrict__ tile_peaks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_count;
+    const long long work_items = (long long)g.maps * g.tiles_y * g.tiles_x;
+    for (long long work = blockIdx.x; work < work_items; work += gridDim.x)
+        okp_generic_tile<THREADS>(heat, g, threshold, K, work, work, tile_count, tile_peaks, smem_raw, &s_count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -171,17 +182,13 @@ okp_peaks_generic_kernel(const float* __restrict__ heat, OkpTileGeometry g, floa
 // Also resets the assignment columns (peak_object, peak_vote) and clears unused slots, so the
 // tables never need a separate memset.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakRecord* __restrict__ tile_peaks,
-                       int maps, int tiles_per_map, int W, int K, OkpDecodeTables t) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= maps) return;
-    const int m = warp;
+// m: map (row of the tables); lists: index of the map's first tile list in tile_count / tile_peaks.
+__device__ __forceinline__ void okp_merge_map(const int32_t* tile_count, const OkpPeakRecord* tile_peaks, int m, size_t lists,
+                                              int lane, int tiles_per_map, int W, int K, const OkpDecodeTables& t) {
     int total = 0;       // true number of peaks
     int kept = 0;        // candidates available (each tile contributes at most K)
     for (int tile = 0; tile < tiles_per_map; ++tile) {
-        const int c = tile_count[(size_t)m * tiles_per_map + tile];
+        const int c = tile_count[lists + tile];
         total += c;
         kept += c < K ? c : K;
     }
@@ -200,8 +207,8 @@ okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakReco
     }
     // rank of every candidate among all candidates of the map
     for (int tile = 0; tile < tiles_per_map; ++tile) {
-        const int c = okp_min(tile_count[(size_t)m * tiles_per_map + tile], K);
-        const OkpPeakRecord* mine = tile_peaks + ((size_t)m * tiles_per_map + tile) * K;
+        const int c = okp_min(tile_count[lists + tile], K);
+        const OkpPeakRecord* mine = tile_peaks + (lists + tile) * K;
         for (int i = lane; i < c; i += 32) {
             const OkpPeakRecord rec = mine[i];
             int rank = 0;
@@ -209,8 +216,8 @@ okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakReco
                 rank = i;                            // already sorted inside the tile
             } else {
                 for (int other = 0; other < tiles_per_map; ++other) {
-                    const int oc = okp_min(tile_count[(size_t)m * tiles_per_map + other], K);
-                    const OkpPeakRecord* theirs = tile_peaks + ((size_t)m * tiles_per_map + other) * K;
+                    const int oc = okp_min(tile_count[lists + other], K);
+                    const OkpPeakRecord* theirs = tile_peaks + (lists + other) * K;
                     for (int j = 0; j < oc; ++j) rank += (theirs[j].key < rec.key);
                 }
             }
@@ -225,4 +232,49 @@ okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakReco
         }
     }
     if (lane == 0) t.peak_count[m] = total;
+}
+
+__global__ void __launch_bounds__(128)
+okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakRecord* __restrict__ tile_peaks,
+                       int maps, int tiles_per_map, int W, int K, OkpDecodeTables t) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= maps) return;
+    okp_merge_map(tile_count, tile_peaks, warp, (size_t)warp * tiles_per_map, threadIdx.x & 31, tiles_per_map, W, K, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Overflow path of the strip kernel (okp_peaks_strip.cuh): maps with more peaks than the table
+// holds need the FIRST K in raster order. Every CTA looks at a slice of peak_count; a map that
+// overflowed is redone tile by tile with the generic routine (tile lists in the CTA's own slice of
+// the workspace) and merged by warp 0. With no
+// overflow the kernel is one coalesced read of peak_count.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+okp_peaks_overflow_kernel(const float* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
+                          int32_t* __restrict__ tile_count, OkpPeakRecord* __restrict__ tile_peaks, OkpDecodeTables t) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_count;
+    __shared__ int s_over[THREADS];
+    const int tiles_per_map = g.tiles_y * g.tiles_x;
+    for (int base = blockIdx.x * THREADS; base < g.maps; base += gridDim.x * THREADS) {
+        const int mine = base + threadIdx.x;
+        const int over = (mine < g.maps && t.peak_count[mine] > K) ? 1 : 0;
+        s_over[threadIdx.x] = over;
+        if (!__syncthreads_or(over)) continue;
+        for (int i = 0; i < THREADS && base + i < g.maps; ++i) {
+            if (!s_over[i]) continue;                     // uniform: shared flag
+            const int m = base + i;
+            for (int tile = 0; tile < tiles_per_map; ++tile)
+                okp_generic_tile<THREADS>(heat, g, threshold, K, (long long)m * tiles_per_map + tile,
+                                          (long long)blockIdx.x * tiles_per_map + tile, tile_count, tile_peaks, smem_raw,
+                                          &s_count);
+            __threadfence_block();
+            __syncthreads();
+            if (threadIdx.x < 32)
+                okp_merge_map(tile_count, tile_peaks, m, (size_t)blockIdx.x * tiles_per_map, threadIdx.x, tiles_per_map, g.W, K, t);
+            __syncthreads();
+        }
+        __syncthreads();
+    }
 }

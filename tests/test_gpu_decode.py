@@ -224,3 +224,38 @@ def test_component_level_api():
     got = to_point(xy, g['depth'][0, 1])
     want = c_oracle.detection_to_point(xy, g['depth'][0, 1], camera)
     assert np.abs(got - want).max() <= TOL_METRES_REL * np.abs(want).max()
+
+
+@pytest.mark.parametrize('H,W,N,C,K', [
+    (64, 64, 37, 3, 32),       # maps not a multiple of the maps-per-CTA group
+    (3, 4, 5, 2, 8),           # tiny map: every window is clipped
+    (1, 8, 3, 1, 8),
+    (7, 252, 3, 2, 64),        # widest single TMA box
+    (9, 256, 2, 3, 64),        # narrowest two-box row
+    (33, 320, 2, 3, 16),       # two boxes, K small: most maps overflow -> overflow path
+    (12, 504, 2, 2, 256),      # widest supported row
+    (21, 508, 1, 2, 64),       # too wide for the strip kernel -> generic kernel
+    (30, 66, 2, 2, 32),        # W % 4 != 0 -> generic kernel
+])
+def test_peak_extraction_shapes_noise_and_overflow(H, W, N, C, K):
+    """Dense random maps (a peak every ~25 pixels, ties included through quantised values): the peak
+    tables of the strip kernel / overflow path / generic kernel are bitwise the oracle's."""
+    from oracle import c_oracle
+    from object_keypoints_b200 import KeypointDecoder
+    rng = np.random.default_rng(H * 1000 + W)
+    heat = rng.uniform(0, 0.2, (N, C, H, W)).astype(np.float32)
+    heat[0, 0] = np.round(heat[0, 0] * 8) / 8                    # exact ties
+    if N > 1:
+        heat[1, C - 1] = 0.001                                    # below threshold everywhere: no peaks
+    cfg = [1] * (C - 1)
+    decoder = KeypointDecoder(cfg, (H, W), max_peaks=K, max_objects=16)
+    got = decoder.extract_peaks(heat).numpy()
+    want = c_oracle.decode(heat, np.zeros_like(heat), np.zeros((N, C - 1, 2, H, W), np.float32), cfg, None,
+                           max_peaks=K, max_objects=16)
+    np.testing.assert_array_equal(got['peak_count'], want['peak_count'])
+    np.testing.assert_array_equal(got['peak_yx'], want['peak_yx'])
+    for key in ['peak_score', 'peak_xy', 'peak_conf']:
+        np.testing.assert_array_equal(got[key].view(np.uint32), want[key].view(np.uint32), err_msg=key)
+    assert (got['peak_object'] == -1).all()
+    if (H, W) == (33, 320):                                       # both the overflow path and the fast path
+        assert (want['peak_count'] > K).any() and (want['peak_count'] <= K).any()
