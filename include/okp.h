@@ -118,11 +118,20 @@ int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W,
 
 /* Replaces ObjectExtraction.__call__ (pipeline.py:104-153) and the DetectionToPoint loop of
  * ObjectKeypointPipeline.__call__ (pipeline.py:189-199, 164-171; camera_utils.py:31-34,75-81)
- * for every frame, reading the peak_* tables. depth_dev [N,C,H,W], centers_dev [N,C-1,2,H,W].
+ * for every frame, reading the peak_* tables. depth_dev [N,C,H,W], centers_dev [N,C-1,2,H,W]:
+ * device memory or okp_host_alias() of pinned host memory (gather-only, see below).
  * camera may be NULL: then kp_point is left zero (ObjectExtraction only). */
 int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
                           const int32_t* keypoint_config, const OkpCamera* camera,
                           const OkpDecodeParams* params, const OkpDecodeTables* tables, void* stream);
+
+/* Device-side alias of a page-locked HOST buffer (cudaHostAlloc / cudaHostRegister, e.g. a
+ * torch pinned tensor). okp_group_objects_f32 only GATHERS from depth and centers (3 floats per
+ * spoke peak), so a caller holding those maps in pinned host memory -- the reference hands
+ * ObjectKeypointPipeline.__call__ CPU tensors, pipeline.py:24-28,184-186 -- passes the alias as
+ * depth_dev / centers_dev instead of copying 2/3 of the frame's bytes to HBM. Writes the alias to
+ * *dev_ptr_out; OKP_E_UNSUPPORTED if the buffer is pageable or not mapped into the current device. */
+int okp_host_alias(const void* host_ptr, void** dev_ptr_out);
 
 /* Replaces ObjectKeypointPipeline.__call__ (pipeline.py:182-200) for a batch of N frames:
  * okp_extract_peaks_f32 followed by okp_group_objects_f32 on the same stream. */

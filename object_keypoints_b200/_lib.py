@@ -16,7 +16,7 @@ EXPORTS = [
     'okp_version', 'okp_strerror', 'okp_decode_workspace_bytes', 'okp_extract_peaks_f32',
     'okp_group_objects_f32', 'okp_decode_f32', 'okp_fisheye_undistort_f64', 'okp_fisheye_project_f64',
     'okp_detection_to_point_f32', 'okp_triangulate_f64', 'okp_reprojection_filter_f64',
-    'okp_triangulate_robust_f64',
+    'okp_triangulate_robust_f64', 'okp_host_alias',
 ]
 
 
@@ -75,6 +75,8 @@ def lib():
     L.okp_decode_f32.restype = i32
     L.okp_decode_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, P(ctypes.c_int32), P(_abi.OkpCamera),
                                  P(_abi.OkpDecodeParams), P(_abi.OkpDecodeTables), vp, sz, vp]
+    L.okp_host_alias.restype = i32
+    L.okp_host_alias.argtypes = [vp, P(vp)]
     L.okp_fisheye_undistort_f64.restype = i32
     L.okp_fisheye_undistort_f64.argtypes = [vp, i32, P(_abi.OkpCamera), i32, vp, vp]
     L.okp_fisheye_project_f64.restype = i32

@@ -172,6 +172,18 @@ int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int 
     return OKP_OK;
 }
 
+int okp_host_alias(const void* host_ptr, void** dev_ptr_out) {
+    if (!host_ptr || !dev_ptr_out) return OKP_E_NULL;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return OKP_E_UNSUPPORTED;
+    }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return OKP_E_UNSUPPORTED;
+    *dev_ptr_out = attr.devicePointer;
+    return OKP_OK;
+}
+
 int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
                    const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
                    const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {

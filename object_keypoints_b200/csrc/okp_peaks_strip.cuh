@@ -1,33 +1,37 @@
-// okp_peaks_strip.cuh -- tuned K1 for sm_100a: TMA-fed, register-window box sum.
+// okp_peaks_strip.cuh -- tuned K1 for sm_100a: TMA-fed strip kernel, bounded filter + exact check.
 //
 // Replaces perception/pipeline.py:46-79 + perception/models.py:55-58 for every map of a batch.
 //
-// Why this shape. The box sum has to be the 25 float32 additions of the reference in raster tap
-// order (torch's CPU conv2d is bitwise that), so it cannot be made separable
-// or reassociated: 24 dependent-order FADDs per pixel. At B200's measured FADD rate
-// (profiles/r01_fp32_issue_microbench.txt: ~36.7e12 adds/s) that is 1.53e12 pixel/s = 6.1 TB/s of
-// heatmap bytes, i.e. the kernel sits just under the HBM roofline and is bound by FADD *issue*.
-// Everything else is therefore organised to cost as few issue slots as possible:
+// Why this shape. A peak is a pixel whose 5x5 box sum S (25 float32 additions in raster tap order,
+// torch's CPU conv2d is bitwise that) exceeds the threshold and equals the
+// maximum of S over its 5x5 neighbourhood. Computing S exactly for every pixel costs 24
+// dependent-order FADDs per pixel and made the first version of this kernel issue-bound at 0.31 of
+// the HBM roofline (profiles/r01a_k1_strip_ncu.md). Peaks are rare, so the stream now computes a
+// cheap BOUND instead and the exact arithmetic runs only where the bound cannot decide:
 //
-//   * heatmap rows arrive in shared memory by TMA (cp.async.bulk.tensor, one elected thread, no
-//     per-thread load/store instructions); the tensor map's out-of-bounds zero fill IS conv2d's zero
-//     padding (rows -2,-1,H,H+1 and columns -2,-1,W,W+1 cost nothing). TMA wants the innermost start
-//     coordinate 16-byte aligned (tools/microbench/tma_probe.cu: column -2 is an illegal instruction),
-//     so the box starts at column -4 and the strips are shifted instead: strip s produces the pixels
-//     x = 4s-2 .. 4s+1, whose window is the columns 4s-4 .. 4s+3 = two aligned LDS.128 (the price is
-//     one extra strip per row: 81 instead of 80 at W = 320);
-//   * a thread owns a 4-pixel-wide column strip of one map and slides down it, keeping the 5x8
-//     window in registers: per row step 2 LDS.128, 96 FADD, 1 STS.128 (box sums to a ring), 3 FMNMX
-//     and one compare -- no halo is recomputed, no row is read twice;
-//   * pixels whose box sum exceeds the threshold are rare: they set a bit in a row-indexed bitmap
-//     ring; after each 5-row batch (one __syncthreads) the set bits are tested against their 5x5
-//     neighbourhood in the box-sum ring (nearest neighbours first, early exit), peaks get their
-//     centroid from L2 and are appended to the map's list, which is sorted by raster key and
-//     written to the final tables at the end (no separate merge pass, no workspace traffic).
+//   * every pixel gets the separable sum S~ (horizontal 5-sums shared between the 4 pixels of a
+//     strip, vertical 5-sum from running pair sums: 5.25 FADD per pixel). For non-negative inputs
+//     any summation order of the same 25 terms is within gamma_24 * sum|x| of the true sum, so
+//     |S - S~| <= 2.9e-6 * S~. With tie = 1 + 2e-5: S~(p) <= threshold * (1 - 1e-5) proves
+//     S(p) <= threshold, and S~(q) > tie * S~(p) proves S(q) > S(p). Pixels that survive both tests
+//     against their whole neighbourhood are CANDIDATES (true peaks plus near ties, a few per blob);
+//   * a candidate's S is then computed exactly (25 loads from L2, raster-order __fadd_rn), compared
+//     with the threshold, and with the exact S of those neighbours whose S~ is within the tie band
+//     (normally none). The peak set, the scores and the raster order are therefore bit-identical to
+//     the exact kernel's; ties keep every tied pixel like `x == hmax` does;
+//   * maps holding a negative value (sign bit seen by a 2-LOP3-per-row check) void the bound: they
+//     are handed to the exact generic kernels through the overflow path, like maps with more than K
+//     peaks ("the first K in raster order").
 //
-// A CTA owns M whole maps (M x W/4 threads). Maps whose peak count exceeds the table capacity K
-// need "the first K in raster order": they are redone by the generic kernels (okp_peaks.cuh),
-// which skip every other map.
+// Data movement: heatmap rows arrive in shared memory by TMA (cp.async.bulk.tensor, one elected
+// thread); the tensor map's out-of-bounds zero fill IS conv2d's zero padding. TMA wants the
+// innermost start coordinate 16-byte aligned (tools/microbench/tma_probe.cu), so the box starts at
+// column -4 and strip s produces the pixels x = 4s-2 .. 4s+1 from the columns 4s-4 .. 4s+3 = two
+// aligned LDS.128. A thread owns one strip of one map and slides down it; per row step: 2 LDS.128,
+// 21 FADD, 1 STS.128 (S~ to a ring for the neighbourhood test), 3 FMNMX + 1 compare. Pixels above
+// the threshold that top their strip's own 5x4 block set a bit in a row-indexed bitmap ring; the
+// service warps test those bits against the ring, run the exact check and append peaks to the
+// map's list, which the epilogue ranks by raster key and writes, with centroids, to the tables.
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
@@ -35,21 +39,24 @@
 #include "okp_common.cuh"
 #include "okp_peaks.cuh"
 
-#define OKP_STRIP_RB 5            // rows per batch (= register window depth, so slots are static)
-#define OKP_STRIP_NS 2            // TMA stages
-#define OKP_STRIP_MAX_LAG 8        // swept[] barriers
+#define OKP_STRIP_RB 5            // rows per batch (= period of the register rings, so slots are static)
+#define OKP_STRIP_MAX_NS 8        // TMA stages (upper bound; the plan picks NS)
+#define OKP_STRIP_MAX_LAG 8       // swept[] barriers
+#define OKP_STRIP_TIE 1.00002f    // S~(q) > tie * S~(p) proves S(q) > S(p)   (see the header)
+#define OKP_STRIP_THRESHOLD_SLACK 1e-5f
 
 struct OkpStripPlan {
     int H, W, maps;
-    int SW;                       // pitch of the box-sum ring: W + 4, column index = x + 2
+    int SW;                       // pitch of the S~ ring: W + 4, column index = x + 2
     int strips;                   // W / 4 + 1 (strip s = pixels 4s-2 .. 4s+1)
     int half_strips;              // strips served by TMA box 0 (all of them when halves == 1)
     int halves;                   // 1 or 2 TMA boxes per row (box width <= 256 elements)
     int BW;                       // box width in floats
     int M;                        // maps per CTA
-    int service_warps;            // warps that issue TMA and run NMS (the rest slide windows)
-    int SR;                       // ring depth (rows, power of two) of the box-sum and bitmap rings
-    int lag;                      // compute batch b may start once the NMS of batch b - lag is done
+    int NS;                       // TMA stages
+    int service_warps;            // warps that issue TMA and test candidates (the rest slide windows)
+    int SR;                       // ring depth (rows, power of two) of the S~ and bitmap rings
+    int lag;                      // compute batch b may start once the candidates of batch b - lag are done
     int nb;                       // batches
     int K;                        // table capacity per map
     int wpr;                      // bitmap words per row (bit index = x + 2)
@@ -91,107 +98,119 @@ __device__ __forceinline__ void okp_mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+__device__ __forceinline__ void okp_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(okp_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void okp_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(okp_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(okp_smem_u32(bar)) : "memory");
 }
 
-// One row step of the sliding window. I = step inside the batch = register slot of the new row.
-// Column c of the strip is pixel x = xs + c - 2 (xs = 4 * strip); vmask has bit c set when that pixel
-// is inside the image. sw keeps the strip's last five rows of box sums (-inf outside the image), so
-// that the candidates of row y - 2 can be narrowed down to the strip's own 5 x 4 block maximum before
-// anything is written to the bitmap: one or two rows per blob instead of every row above threshold.
-template <int I>
-__device__ __forceinline__ void okp_strip_step(float (&w)[5][8], float (&sw)[5][4], const unsigned char* raw_row, int y,
-                                               int H, int SW, float threshold, float* score_map, uint32_t* bitmap_map,
-                                               int bitmap_pitch, int xs, uint32_t vmask, int ring_mask) {
-    const float4* rp = reinterpret_cast<const float4*>(raw_row);
-    const float4 lo = rp[0], hi = rp[1];
-    w[I][0] = lo.x; w[I][1] = lo.y; w[I][2] = lo.z; w[I][3] = lo.w;
-    w[I][4] = hi.x; w[I][5] = hi.y; w[I][6] = hi.z; w[I][7] = hi.w;
-    constexpr int R0 = (I + 1) % 5, R1 = (I + 2) % 5, R2 = (I + 3) % 5, R3 = (I + 4) % 5, R4 = I;
-    if (y >= 0 && y < H) {                                          // uniform over the CTA
-        float a[4];
-        // raster tap order: row y-2 first (0 + a00 is a00), then rows y-1 .. y+2, left to right
+// The reference's box sum at pixel (y, x): 25 additions in raster tap order starting from +0, zero
+// outside the image (perception/pipeline.py:70-71). The loads are independent (one L2 round trip).
+__device__ __forceinline__ float okp_exact_box_sum(const float* __restrict__ src, int H, int W, int y, int x) {
+    float q[25];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) a[c] = w[R0][c];
-#pragma unroll
-        for (int d = 1; d < 5; ++d)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[c] = __fadd_rn(a[c], w[R0][c + d]);
-#pragma unroll
-        for (int d = 0; d < 5; ++d)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[c] = __fadd_rn(a[c], w[R1][c + d]);
-#pragma unroll
-        for (int d = 0; d < 5; ++d)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[c] = __fadd_rn(a[c], w[R2][c + d]);
-#pragma unroll
-        for (int d = 0; d < 5; ++d)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[c] = __fadd_rn(a[c], w[R3][c + d]);
-#pragma unroll
-        for (int d = 0; d < 5; ++d)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[c] = __fadd_rn(a[c], w[R4][c + d]);
-        *reinterpret_cast<float4*>(score_map + (size_t)(y & ring_mask) * SW + xs) = make_float4(a[0], a[1], a[2], a[3]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sw[I][c] = a[c];
-    } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sw[I][c] = -INFINITY;           // max_pool2d pads with -inf
+    for (int k = 0; k < 25; ++k) {
+        const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+        const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+        q[k] = in ? __ldg(src + (size_t)i2 * W + j2) : 0.0f;
     }
-    // ---- candidates of row y - 2 (slot R2), whose five rows of box sums are now known ----
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) acc = __fadd_rn(acc, q[k]);
+    return acc;
+}
+
+// One row step of the sliding window. I = step inside the batch = slot of the register rings.
+// (lo, hi) are the columns 4s-4 .. 4s+3 of the new input row y + 2; the step produces S~ of row y for
+// the strip's pixels x = xs + c - 2 (c = 0..3, xs = 4 * strip). vmask has bit c set when that pixel is
+// inside the image. pr keeps the running pair sums h(t-1) + h(t) of the horizontal sums, sv the
+// strip's last five rows of S~, so that the candidates of row y - 2 can be
+// narrowed down to the strip's own 5 x 4 block before anything is written to the bitmap: one or two
+// rows per blob instead of every row above threshold.
+template <int I>
+__device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi, float (&pr)[5][4], float (&hp)[4],
+                                               float (&sv)[5][4], uint32_t& sign, int y, int H, int SW, float thr_lo,
+                                               float* score_map, uint32_t* bitmap_map, int bitmap_pitch, int xs,
+                                               uint32_t vmask, int ring_mask) {
+    // horizontal 5-sums of the four windows w[c .. c+4] (w = lo.xyzw, hi.xyzw): 9 adds
+    const float c34 = lo.w + hi.x;
+    const float t12 = lo.y + lo.z;
+    const float t56 = hi.y + hi.z;
+    const float tc = t12 + c34;
+    const float u = c34 + t56;
+    float h[4];
+    h[0] = lo.x + tc; h[1] = tc + hi.y; h[2] = lo.z + u; h[3] = u + hi.w;
+    // the strip's own pixels are w[2..5]: a set sign bit anywhere voids the bound (see the header)
+    sign |= __float_as_uint(lo.z) | __float_as_uint(lo.w);
+    sign |= __float_as_uint(hi.x) | __float_as_uint(hi.y);
+    // vertical: S~(t) = P(t-3) + P(t-1) + h(t), P(t) = h(t-1) + h(t): 12 adds
+    constexpr int R2 = (I + 3) % 5;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        v[c] = (pr[(I + 2) % 5][c] + pr[(I + 4) % 5][c]) + h[c];
+        pr[I][c] = hp[c] + h[c];
+        hp[c] = h[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sv[I][c] = v[c];
+    if (y >= 0 && y < H)                                            // uniform over the CTA
+        *reinterpret_cast<float4*>(score_map + (size_t)(y & ring_mask) * SW + xs) = make_float4(v[0], v[1], v[2], v[3]);
+    // ---- candidates of row y - 2 (slot R2), whose five rows of S~ are now known ----
     const int yc = y - 2;
     if (yc < 0 || yc >= H) return;                                  // uniform
-    const float (&b)[4] = sw[R2];
-    if (fmaxf(fmaxf(fmaxf(b[0], b[1]), b[2]), b[3]) > threshold) {  // rare; runs warp-wide, keep it short
+    const float (&b)[4] = sv[R2];
+    if (fmaxf(fmaxf(b[0], b[1]), fmaxf(b[2], b[3])) > thr_lo) {     // rare; runs warp-wide, keep it short
         const float ninf = -INFINITY;
+        // rows y-4, y-3 (slots I+1, I+2) and y-1, y (slots I+4, I) may lie outside the image: max_pool2d pads with -inf
+        const bool up2 = yc >= 2, up1 = yc >= 1, dn1 = yc + 1 < H, dn2 = yc + 2 < H;
         float cm[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float m = fmaxf(fmaxf(fmaxf(sw[0][c], sw[1][c]), fmaxf(sw[2][c], sw[3][c])), sw[4][c]);
+            float m = b[c];
+            m = fmaxf(m, up2 ? sv[(I + 1) % 5][c] : ninf);
+            m = fmaxf(m, up1 ? sv[(I + 2) % 5][c] : ninf);
+            m = fmaxf(m, dn1 ? sv[(I + 4) % 5][c] : ninf);
+            m = fmaxf(m, dn2 ? sv[I][c] : ninf);
             cm[c] = ((vmask >> c) & 1u) ? m : ninf;                  // columns outside the image never win
         }
         const float n012 = fmaxf(fmaxf(cm[0], cm[1]), cm[2]), n123 = fmaxf(fmaxf(cm[1], cm[2]), cm[3]);
         const float nall = fmaxf(n012, cm[3]);
-        uint32_t bits = (b[0] > threshold && b[0] == n012) ? 1u : 0u;
-        bits |= (b[1] > threshold && b[1] == nall) ? 2u : 0u;
-        bits |= (b[2] > threshold && b[2] == nall) ? 4u : 0u;
-        bits |= (b[3] > threshold && b[3] == n123) ? 8u : 0u;
+        const float tie = OKP_STRIP_TIE;
+        uint32_t bits = (b[0] > thr_lo && b[0] * tie >= n012) ? 1u : 0u;
+        bits |= (b[1] > thr_lo && b[1] * tie >= nall) ? 2u : 0u;
+        bits |= (b[2] > thr_lo && b[2] * tie >= nall) ? 4u : 0u;
+        bits |= (b[3] > thr_lo && b[3] * tie >= n123) ? 8u : 0u;
         bits &= vmask;
         if (bits) atomicOr(bitmap_map + (yc & ring_mask) * bitmap_pitch + (xs >> 5), bits << (xs & 31));
     }
 }
 
-__device__ __forceinline__ void okp_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(okp_smem_u32(bar)) : "memory");
-}
-
 // Roles. Warps [0, CW) are compute warps (thread = one strip of one map); they never meet a CTA-wide
 // barrier inside the row loop: they wait for TMA data (full[]), slide down RB rows, and arrive on
-// done[]. The last warps are service warps: they wait on done[b], re-arm the freed stage with the
-// TMA of batch b + NS, then run NMS on the rows batch b completed. The only back-pressure on the
-// compute warps is the ring guard swept[] (the service warps may lag at most one batch, because the
-// box-sum ring holds SR = 16 rows).
-__global__ void __launch_bounds__(768, 1)
+// done[]. The last warps are service warps: warp 0 of them keeps NS batches of rows in flight, the
+// others wait on ready[b] and test the candidates of the rows batch b completed. The only
+// back-pressure on the compute warps is the ring guard swept[] (the S~ ring holds SR = 16 rows).
+__global__ void __launch_bounds__(576, 1)
 okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ heat, OkpStripPlan p,
-                       float threshold, OkpDecodeTables t) {
+                       float threshold, float thr_lo, OkpDecodeTables t) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int RB = OKP_STRIP_RB;
     const int SR = p.SR;
-    constexpr int NS = OKP_STRIP_NS;
+    const int NS = p.NS;
     const int NSW = p.service_warps;
     float* score = reinterpret_cast<float*>(smem + p.off_score);             // [M][SR][SW], column x + 2
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem + p.off_bitmap);     // [SR][M][wpr], bit = x + 2
     OkpStripPeak* list = reinterpret_cast<OkpStripPeak*>(smem + p.off_list); // [M][K]
-    int* count = reinterpret_cast<int*>(smem + p.off_count);                 // [M]
+    int* count = reinterpret_cast<int*>(smem + p.off_count);                 // [M] peaks, [M] negative-input flags
+    int* negative = count + p.M;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_mbar);         // [NS] TMA landed
-    uint64_t* done = full + OKP_STRIP_NS;                                // [NS] compute warps finished the batch
-    uint64_t* ready = done + OKP_STRIP_NS;                               // [lag] same event, for the NMS warps (they may lag)
-    uint64_t* swept = ready + OKP_STRIP_MAX_LAG;                         // [lag] NMS warps finished the batch
+    uint64_t* done = full + OKP_STRIP_MAX_NS;                            // [NS] compute warps finished the batch
+    uint64_t* ready = done + OKP_STRIP_MAX_NS;                           // [lag] same event, for the candidate warps (they may lag)
+    uint64_t* swept = ready + OKP_STRIP_MAX_LAG;                         // [lag] candidate warps finished the batch
 
     const int tid = threadIdx.x;
     const int H = p.H, W = p.W, SW = p.SW;
@@ -200,7 +219,7 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
     const bool service = (tid >> 5) >= compute_warps;
 
     for (int i = tid; i < p.M * SR * p.wpr; i += blockDim.x) bitmap[i] = 0;
-    if (tid < p.M) count[tid] = 0;
+    if (tid < 2 * p.M) count[tid] = 0;
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { okp_mbar_init(full + i, 1); okp_mbar_init(done + i, compute_warps); }
         for (int i = 0; i < p.lag; ++i) { okp_mbar_init(ready + i, compute_warps); okp_mbar_init(swept + i, NSW - 1); }
@@ -212,102 +231,91 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
     if (service) {
         const int lane = tid & 31;
         const int sw = (tid >> 5) - compute_warps;        // service warp index
-        const CUtensorMap* tmap_ptr = &tmap;             // address of the __grid_constant__ parameter itself
-        auto issue = [=](int b) {                        // one thread: TMA the new rows of batch b
-            uint64_t* bar = full + (b % NS);
-            unsigned char* dst = smem + (size_t)(b % NS) * p.stage_bytes;
-            okp_mbar_expect_tx(bar, (uint32_t)(p.halves * p.half_bytes));
-            okp_tma_load_3d(dst, tmap_ptr, -4, b * RB - 2, first_map, bar);
-            if (p.halves == 2) okp_tma_load_3d(dst + p.half_stride, tmap_ptr, 4 * p.half_strips - 4, b * RB - 2, first_map, bar);
-        };
         if (sw == 0) {
-            // producer warp: keeps NS batches of rows in flight; nothing else, so that a burst of NMS work
-            // never delays the next TMA
+            // producer warp: keeps NS batches of rows in flight; nothing else, so that a burst of
+            // candidate work never delays the next TMA
             if (lane == 0) {
-                for (int b = 0; b < NS && b < p.nb; ++b) issue(b);
-                for (int b = 0; b + NS < p.nb; ++b) {
-                    okp_mbar_wait(done + (b % NS), (uint32_t)((b / NS) & 1));   // every compute warp has left stage b % NS
-                    issue(b + NS);
+                const CUtensorMap* tmap_ptr = &tmap;      // address of the __grid_constant__ parameter itself
+                int stage = 0;
+                uint32_t parity = 0;
+                for (int b = 0; b < p.nb; ++b) {
+                    if (b >= NS) okp_mbar_wait(done + stage, parity);        // every compute warp has left the stage
+                    uint64_t* bar = full + stage;
+                    unsigned char* dst = smem + (size_t)stage * p.stage_bytes;
+                    okp_mbar_expect_tx(bar, (uint32_t)(p.halves * p.half_bytes));
+                    okp_tma_load_3d(dst, tmap_ptr, -4, b * RB - 2, first_map, bar);
+                    if (p.halves == 2) okp_tma_load_3d(dst + p.half_stride, tmap_ptr, 4 * p.half_strips - 4, b * RB - 2, first_map, bar);
+                    if (++stage == NS) { stage = 0; if (b >= NS) parity ^= 1u; }
                 }
             }
         } else {
-        const int nw = NSW - 1, nwi = sw - 1;             // NMS warps
-        const int MW = p.M * p.wpr;                       // bitmap words per ring row
-        const int chunks_per_row = (MW + 31) >> 5;
-        const float ninf = -INFINITY;
-        int slot = 0;                                     // b % lag, ((b / lag) & 1) without dividing
-        uint32_t parity = 0;
-        for (int b = 0; b < p.nb; ++b) {
-            okp_mbar_wait(ready + slot, parity);          // batch b: box sums + candidate bits are visible
-            // ---- NMS of the rows whose 5x5 neighbourhood is now complete: [y0 - 2, y0 + 3) ----
-            // The row's bitmap is cut into chunks of 32 words, dealt round-robin to the service warps. A
-            // non-zero word (32 pixels of one row, a few candidates) is tested by the whole warp at once:
-            // lane i owns pixel x0 + i, takes the vertical maximum of its column over the 5 rows, lanes
-            // 0..3 do the same for the 4 halo columns, and the horizontal 5-window comes from shuffles.
-            const int y0 = b * RB - 4;
-            int rr = 0, cc = nwi;                         // chunk = rr * chunks_per_row + cc, without dividing
-            for (;; cc += nw) {
-                while (cc >= chunks_per_row) { cc -= chunks_per_row; ++rr; }
-                if (rr >= RB) break;
-                const int r = y0 - 2 + rr;
-                if (r < 0 || r >= H) continue;
-                const int j = (cc << 5) + lane;
-                uint32_t* row_words = bitmap + (size_t)(r & (SR - 1)) * MW;
-                uint32_t mine = 0;
-                if (j < MW) {
-                    mine = row_words[j];
-                    if (mine) row_words[j] = 0;
-                }
-                uint32_t nonzero = __ballot_sync(0xffffffffu, mine != 0);
-                while (nonzero) {
-                    const int src = __ffs(nonzero) - 1;
-                    nonzero &= nonzero - 1;
-                    const uint32_t bits = __shfl_sync(0xffffffffu, mine, src);
-                    const int jj = j - lane + src;
-                    const int m2 = jj / p.wpr, wi = jj - m2 * p.wpr;
-                    const float* sm = score + (size_t)m2 * SR * SW + 2;     // sm[ring row * SW + x]
-                    const int x0 = wi * 32 - 2;                              // pixel of bit 0
-                    const int x = x0 + lane;
-                    // halo columns x0-2, x0-1, x0+32, x0+33 on lanes 0..3
-                    const int xh = lane < 2 ? x0 - 2 + lane : x0 + 30 + lane;
-                    const bool x_in = x >= 0 && x < W;
-                    const bool xh_in = lane < 4 && xh >= 0 && xh < W;
-                    float vm = ninf, hv = ninf, v = ninf;
+            const int nw = NSW - 1, nwi = sw - 1;         // candidate warps
+            const int MW = p.M * p.wpr;                   // bitmap words per ring row
+            const int chunks_per_row = (MW + 31) >> 5;
+            const float tie = OKP_STRIP_TIE;
+            int slot = 0;                                 // b % lag, ((b / lag) & 1) without dividing
+            uint32_t parity = 0;
+            for (int b = 0; b < p.nb; ++b) {
+                okp_mbar_wait(ready + slot, parity);      // batch b: S~ rows + candidate bits are visible
+                // Rows whose 5x5 neighbourhood is now complete: [y0 - 2, y0 + 3). A row's bitmap is cut into
+                // chunks of 32 words, dealt round-robin to the candidate warps; a lane owns one word and
+                // walks its set bits (a few per blob): neighbourhood test on S~, then the exact check.
+                const int y0 = b * RB - 4;
+                int rr = 0, cc = nwi;                     // chunk = rr * chunks_per_row + cc, without dividing
+                for (;; cc += nw) {
+                    while (cc >= chunks_per_row) { cc -= chunks_per_row; ++rr; }
+                    if (rr >= RB) break;
+                    const int r = y0 - 2 + rr;
+                    if (r < 0 || r >= H) continue;
+                    const int j = (cc << 5) + lane;
+                    if (j >= MW) continue;
+                    uint32_t* word = bitmap + (size_t)(r & (SR - 1)) * MW + j;
+                    uint32_t mine = *word;
+                    if (!mine) continue;
+                    *word = 0;
+                    const int m2 = j / p.wpr, wi = j - m2 * p.wpr;
+                    const float* sm = score + (size_t)m2 * SR * SW + 2;      // sm[ring row * SW + x]
+                    const float* src = heat + (size_t)(first_map + m2) * H * W;
+                    do {
+                        const int bit = __ffs(mine) - 1;
+                        mine &= mine - 1;
+                        const int x = wi * 32 - 2 + bit;                      // inside the image (vmask)
+                        const float sp = sm[(r & (SR - 1)) * SW + x];
+                        const float lim = sp * tie;
+                        bool alive = true;
+                        uint32_t ties = 0;                                    // neighbours the bound cannot order
 #pragma unroll
-                    for (int d = -2; d <= 2; ++d) {
-                        const int ry = r + d;
-                        const bool row_in = ry >= 0 && ry < H;             // max_pool2d pads with -inf
-                        const float* row = sm + ((ry & (SR - 1)) * SW);
-                        const float u = (row_in && x_in) ? row[x] : ninf;
-                        const float uh = (row_in && xh_in) ? row[xh] : ninf;
-                        if (d == 0) v = u;
-                        vm = fmaxf(vm, u);
-                        hv = fmaxf(hv, uh);
-                    }
-                    float l1 = __shfl_up_sync(0xffffffffu, vm, 1), l2 = __shfl_up_sync(0xffffffffu, vm, 2);
-                    float r1 = __shfl_down_sync(0xffffffffu, vm, 1), r2 = __shfl_down_sync(0xffffffffu, vm, 2);
-                    const float h0 = __shfl_sync(0xffffffffu, hv, 0), h1 = __shfl_sync(0xffffffffu, hv, 1);
-                    const float h2 = __shfl_sync(0xffffffffu, hv, 2), h3 = __shfl_sync(0xffffffffu, hv, 3);
-                    if (lane == 0) { l1 = h1; l2 = h0; }
-                    if (lane == 1) l2 = h1;
-                    if (lane == 31) { r1 = h2; r2 = h3; }
-                    if (lane == 30) r2 = h2;
-                    const float hm = fmaxf(fmaxf(fmaxf(l1, l2), fmaxf(r1, r2)), vm);
-                    if (((bits >> lane) & 1u) && v == hm) {                // a peak: box sum equals the 5x5 maximum
-                        const int entry = atomicAdd(count + m2, 1);
+                        for (int k = 0; k < 25; ++k) {
+                            if (k == 12) continue;
+                            const int ry = r + k / 5 - 2, rx = x + k % 5 - 2;
+                            if (ry >= 0 && ry < H && rx >= 0 && rx < W) {    // max_pool2d pads with -inf
+                                const float v = sm[(ry & (SR - 1)) * SW + rx];
+                                if (v > lim) alive = false;
+                                else if (v * tie >= sp) ties |= 1u << k;
+                            }
+                        }
+                        if (!alive) continue;
+                        const float s = okp_exact_box_sum(src, H, W, r, x);
+                        if (!(s > threshold)) continue;
+                        while (ties) {
+                            const int k = __ffs(ties) - 1;
+                            ties &= ties - 1;
+                            if (okp_exact_box_sum(src, H, W, r + k / 5 - 2, x + k % 5 - 2) > s) { alive = false; break; }
+                        }
+                        if (!alive) continue;
+                        const int entry = atomicAdd(count + m2, 1);           // a peak: S equals the 5x5 maximum
                         if (entry < p.K) {                                    // overflow: redone by the overflow kernel
                             OkpStripPeak pk;
                             pk.key = r * W + x;
-                            pk.score = v;
+                            pk.score = s;
                             list[(size_t)m2 * p.K + entry] = pk;
                         }
-                    }
+                    } while (mine);
                 }
+                __syncwarp();
+                if (lane == 0) okp_mbar_arrive(swept + slot);
+                if (++slot == p.lag) { slot = 0; parity ^= 1u; }
             }
-            __syncwarp();
-            if (lane == 0) okp_mbar_arrive(swept + slot);
-            if (++slot == p.lag) { slot = 0; parity ^= 1u; }
-        }
         }
     } else {
         const bool active = tid < p.threads;              // the last compute warp may be partly idle
@@ -327,36 +335,47 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
         uint32_t* bitmap_map = bitmap + (size_t)mm * p.wpr;   // + ring row * M * wpr
         const int bitmap_pitch = p.M * p.wpr;
 
-        float w[5][8], sw[5][4];
+        float pr[5][4], hp[4], sv[5][4];
+        uint32_t sign = 0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[i][j] = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sw[i][j] = -INFINITY;
+            for (int j = 0; j < 4; ++j) { pr[i][j] = 0.0f; sv[i][j] = -INFINITY; }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hp[j] = 0.0f;
 
         const int lag = p.lag;
         int lag_slot = 0, ready_slot = 0;                 // b % lag and ((b - lag) / lag) & 1 without dividing
         uint32_t lag_parity = 0;
+        int stage = 0;
+        uint32_t full_parity = 0;
+#define OKP_STRIP_ARGS H, SW, thr_lo, score_map, bitmap_map, bitmap_pitch, xs, vmask, SR - 1
         for (int b = 0; b < p.nb; ++b) {
-            // ring guard: batch b overwrites ring rows the service warp reads until it has finished batch b - 2
-            if (b >= lag) {
-                okp_mbar_wait(swept + lag_slot, lag_parity);
-            }
-            okp_mbar_wait(full + (b % NS), (uint32_t)((b / NS) & 1));
-            const unsigned char* raw = smem + (size_t)(b % NS) * p.stage_bytes + thread_raw;
+            // ring guard: batch b overwrites ring rows the candidate warps read until they have finished batch b - lag
+            if (b >= lag) okp_mbar_wait(swept + lag_slot, lag_parity);
+            okp_mbar_wait(full + stage, full_parity);
+            const unsigned char* raw = smem + (size_t)stage * p.stage_bytes + thread_raw;
             const int y0 = b * RB - 4;                    // new row of step i is y0 + i + 2
-            okp_strip_step<0>(w, sw, raw + 0 * row_pitch, y0 + 0, H, SW, threshold, score_map, bitmap_map, bitmap_pitch, xs, vmask, SR - 1);
-            okp_strip_step<1>(w, sw, raw + 1 * row_pitch, y0 + 1, H, SW, threshold, score_map, bitmap_map, bitmap_pitch, xs, vmask, SR - 1);
-            okp_strip_step<2>(w, sw, raw + 2 * row_pitch, y0 + 2, H, SW, threshold, score_map, bitmap_map, bitmap_pitch, xs, vmask, SR - 1);
-            okp_strip_step<3>(w, sw, raw + 3 * row_pitch, y0 + 3, H, SW, threshold, score_map, bitmap_map, bitmap_pitch, xs, vmask, SR - 1);
-            okp_strip_step<4>(w, sw, raw + 4 * row_pitch, y0 + 4, H, SW, threshold, score_map, bitmap_map, bitmap_pitch, xs, vmask, SR - 1);
+            // rows are fetched one step ahead of their use (two register pairs, ping-pong)
+            float4 a0 = reinterpret_cast<const float4*>(raw)[0], a1 = reinterpret_cast<const float4*>(raw)[1];
+            float4 b0 = reinterpret_cast<const float4*>(raw + row_pitch)[0], b1 = reinterpret_cast<const float4*>(raw + row_pitch)[1];
+            okp_strip_step<0>(a0, a1, pr, hp, sv, sign, y0 + 0, OKP_STRIP_ARGS);
+            a0 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[1];
+            okp_strip_step<1>(b0, b1, pr, hp, sv, sign, y0 + 1, OKP_STRIP_ARGS);
+            b0 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[0]; b1 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[1];
+            okp_strip_step<2>(a0, a1, pr, hp, sv, sign, y0 + 2, OKP_STRIP_ARGS);
+            a0 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[1];
+            okp_strip_step<3>(b0, b1, pr, hp, sv, sign, y0 + 3, OKP_STRIP_ARGS);
+            okp_strip_step<4>(a0, a1, pr, hp, sv, sign, y0 + 4, OKP_STRIP_ARGS);
             __syncwarp();
-            if ((tid & 31) == 0) { okp_mbar_arrive(done + (b % NS)); okp_mbar_arrive(ready + ready_slot); }
+            if ((tid & 31) == 0) { okp_mbar_arrive(done + stage); okp_mbar_arrive(ready + ready_slot); }
+            if (++stage == NS) { stage = 0; full_parity ^= 1u; }
             if (++ready_slot == lag) ready_slot = 0;
             if (b >= lag && ++lag_slot == lag) { lag_slot = 0; lag_parity ^= 1u; }
         }
+#undef OKP_STRIP_ARGS
+        if (active && (sign >> 31)) negative[mm] = 1;     // benign race: every writer stores 1
     }
     __syncthreads();
 
@@ -366,7 +385,8 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
     const int s = tid - mm * p.strips;
     const int map = first_map + mm;
     if (map >= p.maps) return;
-    const int total = count[mm];
+    // a map with negative values is reported as overflowing, which hands it to the exact generic path
+    const int total = negative[mm] ? p.K + 1 : count[mm];
     if (s == 0) t.peak_count[map] = total;
     if (total > p.K) return;                             // tables of this map are written by the overflow path
     const OkpStripPeak* mine = list + (size_t)mm * p.K;
@@ -435,36 +455,38 @@ static inline bool okp_strip_plan(int maps, int H, int W, int K, OkpStripPlan* o
     p.BW = 4 * p.half_strips + 4;                         // columns 4s-4 .. 4s+3 of the box's strips
     p.wpr = (W + 4 + 31) / 32;
     p.nb = (H + 6 + OKP_STRIP_RB - 1) / OKP_STRIP_RB;
-    p.service_warps = 3;                                  // 1 TMA producer + 2 NMS warps
-    if (const char* e = getenv("OKP_STRIP_SERVICE_WARPS")) p.service_warps = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : 3;   // tuning aid
+    p.service_warps = 3;                                  // 1 TMA producer + 2 candidate warps
+    if (const char* e = getenv("OKP_STRIP_SERVICE_WARPS")) p.service_warps = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;   // tuning aid
     p.SR = 16;
     if (const char* e = getenv("OKP_STRIP_RING")) p.SR = atoi(e) == 32 ? 32 : 16;                                 // tuning aid
-    p.lag = (p.SR - 8) / OKP_STRIP_RB + 1;                // rows [5b'-8, ..) of a pending NMS must not alias rows <= 5b
-    const int per_map = OKP_STRIP_NS * OKP_STRIP_RB * p.BW * p.halves * 4 + p.SR * p.SW * 4 +
-                        p.SR * p.wpr * 4 + K * (int)sizeof(OkpStripPeak) + 4;
+    p.NS = 4;                                             // ~3 batches in flight per CTA cover the HBM latency
+    if (const char* e = getenv("OKP_STRIP_STAGES")) p.NS = atoi(e) >= 2 && atoi(e) <= OKP_STRIP_MAX_NS ? atoi(e) : 4;      // tuning aid
+    p.lag = (p.SR - 8) / OKP_STRIP_RB + 1;                // rows [5b'-8, ..) of a pending sweep must not alias rows <= 5b
+    const int per_map = p.NS * OKP_STRIP_RB * p.BW * p.halves * 4 + p.SR * p.SW * 4 +
+                        p.SR * p.wpr * 4 + K * (int)sizeof(OkpStripPeak) + 8;
     int budget = 110 * 1024;                              // two CTAs per SM
     if (const char* e = getenv("OKP_STRIP_SMEM_KB")) budget = atoi(e) * 1024;                                     // tuning aid
-    int M = budget / per_map;
-    if (M > 512 / p.strips) M = 512 / p.strips;
+    int M = (budget - 1024) / per_map;
+    if (M > 448 / p.strips) M = 448 / p.strips;           // 14 compute warps + service warps <= 576 threads
     if (M > maps) M = maps;
     if (M > 256) M = 256;
     if (M < 1) {
         M = 1;
-        if (per_map + 1024 > 220 * 1024 || p.strips > 512) return false;
+        if (per_map + 1024 > 220 * 1024 || p.strips > 448) return false;
     }
     p.M = M;
     p.threads = M * p.strips;
     p.half_bytes = M * OKP_STRIP_RB * p.BW * 4;
     p.half_stride = okp_round_up_int(p.half_bytes, 128);
     p.stage_bytes = p.halves * p.half_stride;
-    int off = OKP_STRIP_NS * p.stage_bytes;
+    int off = p.NS * p.stage_bytes;
     p.off_score = off; off += M * p.SR * p.SW * 4;
     p.off_bitmap = off; off += M * p.SR * p.wpr * 4;
     off = okp_round_up_int(off, 8);
     p.off_list = off; off += M * K * (int)sizeof(OkpStripPeak);
-    p.off_count = off; off += M * 4;
+    p.off_count = off; off += 2 * M * 4;
     off = okp_round_up_int(off, 8);
-    p.off_mbar = off; off += (2 * OKP_STRIP_NS + 2 * OKP_STRIP_MAX_LAG) * 8;
+    p.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 2 * OKP_STRIP_MAX_LAG) * 8;
     p.smem_bytes = off;
     p.grid = (maps + M - 1) / M;
     *out = p;
@@ -504,7 +526,8 @@ static inline int okp_strip_launch(const float* heat, const OkpStripPlan& p, flo
     if (r != CUDA_SUCCESS) return OKP_E_CUDA;
     OKP_CUDA_CHECK(cudaFuncSetAttribute(okp_peaks_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     const int block = (p.threads + 31) / 32 * 32 + 32 * p.service_warps;    // compute warps + service warps
-    okp_peaks_strip_kernel<<<p.grid, block, p.smem_bytes, stream>>>(tmap, heat, p, threshold, tables);
+    const float thr_lo = threshold - OKP_STRIP_THRESHOLD_SLACK * fabsf(threshold);
+    okp_peaks_strip_kernel<<<p.grid, block, p.smem_bytes, stream>>>(tmap, heat, p, threshold, thr_lo, tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

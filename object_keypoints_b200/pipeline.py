@@ -148,30 +148,52 @@ class KeypointDecoder:
 
     HOST_RESULT_TABLES = ('n_objects', 'flags', 'kp_count', 'kp_xy', 'kp_point')
 
+    def _host_alias(self, tensor):
+        """Device-side address of a pinned CPU tensor (okp_host_alias), or None if it has to be copied."""
+        if tensor.device.type != 'cpu' or tensor.dtype != torch.float32 or not tensor.is_contiguous() or not tensor.is_pinned():
+            return None
+        alias = ctypes.c_void_p()
+        if self._lib.okp_host_alias(ctypes.c_void_p(tensor.data_ptr()), ctypes.byref(alias)) != 0 or not alias.value:
+            return None
+        return alias.value
+
     def decode_host_batch(self, heat, depth, centers, chunk_frames=256):
-        """End-to-end form for HOST inputs: heat/depth/centers are CPU tensors (pinned memory makes
-        the copies asynchronous). The batch is cut into chunks; chunk i+1 is copied host->device on
-        a copy stream while chunk i is decoded, and the object tables of every chunk are copied back
-        into pinned host tensors. Returns a dict of CPU tensors (synchronised)."""
+        """End-to-end form for HOST inputs, the shape the reference's caller has (CPU tensors out of
+        InferenceComponent, pipeline.py:24-28). The batch is cut into chunks; the heatmaps of chunk
+        i+1 are copied host->device on a copy stream while chunk i is decoded. Depth and centre maps
+        are only gathered from (3 floats per spoke peak), so when they live in pinned host memory the
+        kernels read them in place over PCIe and 2/3 of the frame's bytes never cross the bus; pageable
+        tensors are copied like the heatmaps. The object tables of every chunk are copied back into
+        pinned host tensors. Returns a dict of CPU tensors (synchronised)."""
         N = int(heat.shape[0])
         chunk = max(1, min(chunk_frames, N))
-        key = ('host', N, chunk)
+        depth_alias = self._host_alias(depth)
+        centers_alias = self._host_alias(centers)
+        in_place = depth_alias is not None and centers_alias is not None
+        key = ('host', N, chunk, in_place)
         if key not in self._tables:
             staging = []
             for _ in range(2):
-                staging.append({
+                slot = {
                     'heat': torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device),
-                    'depth': torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device),
-                    'centers': torch.empty((chunk, self.C - 1, 2, self.H, self.W), dtype=torch.float32, device=self.device),
                     'tables': DecodeTables(chunk, self.C, self.cfg, self.params, self.device),
                     'ready': torch.cuda.Event(), 'done': torch.cuda.Event(),
-                })
+                }
+                if not in_place:
+                    slot['depth'] = torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device)
+                    slot['centers'] = torch.empty((chunk, self.C - 1, 2, self.H, self.W), dtype=torch.float32, device=self.device)
+                staging.append(slot)
             like = staging[0]['tables']
             result = {name: torch.empty((N,) + tuple(like[name].shape[1:]), dtype=like[name].dtype).pin_memory()
                       for name in self.HOST_RESULT_TABLES}
             self._tables[key] = (staging, result, torch.cuda.Stream(device=self.device))
         staging, result, copy_stream = self._tables[key]
         compute = torch.cuda.current_stream()
+        self._workspace_for(chunk)
+        depth_frame = self.C * self.H * self.W * 4
+        centers_frame = (self.C - 1) * 2 * self.H * self.W * 4
+        cam = ctypes.byref(self._camera) if self._camera is not None else None
+        self.host_bytes_copied = 0
         for index, f0 in enumerate(range(0, N, chunk)):
             f1 = min(f0 + chunk, N)
             n = f1 - f0
@@ -179,15 +201,23 @@ class KeypointDecoder:
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(slot['done'])          # the slot's previous decode + read-back finished
                 slot['heat'][:n].copy_(heat[f0:f1], non_blocking=True)
-                slot['depth'][:n].copy_(depth[f0:f1], non_blocking=True)
-                slot['centers'][:n].copy_(centers[f0:f1], non_blocking=True)
+                self.host_bytes_copied += n * depth_frame
+                if not in_place:
+                    slot['depth'][:n].copy_(depth[f0:f1], non_blocking=True)
+                    slot['centers'][:n].copy_(centers[f0:f1], non_blocking=True)
+                    self.host_bytes_copied += n * (depth_frame + centers_frame)
                 slot['ready'].record(copy_stream)
             compute.wait_event(slot['ready'])
-            if n == chunk:
-                tables = slot['tables']
-                self.decode_batch(slot['heat'], slot['depth'], slot['centers'], tables=tables)
+            tables = slot['tables'] if n == chunk else self.tables(n)
+            if in_place:
+                ws = self._workspace_for(n)
+                rc = self._lib.okp_decode_f32(slot['heat'].data_ptr(), depth_alias + f0 * depth_frame,
+                                              centers_alias + f0 * centers_frame, n, self.C, self.H, self.W,
+                                              self._cfg_array, cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                                              ws.data_ptr(), ws.numel(), _stream_handle(compute))
+                _lib.check(rc, 'okp_decode_f32')
             else:
-                tables = self.decode_batch(slot['heat'][:n], slot['depth'][:n], slot['centers'][:n])
+                self.decode_batch(slot['heat'][:n], slot['depth'][:n], slot['centers'][:n], tables=tables)
             for name in self.HOST_RESULT_TABLES:
                 result[name][f0:f1].copy_(tables[name][:n], non_blocking=True)
             slot['done'].record(compute)

@@ -259,3 +259,57 @@ def test_peak_extraction_shapes_noise_and_overflow(H, W, N, C, K):
     assert (got['peak_object'] == -1).all()
     if (H, W) == (33, 320):                                       # both the overflow path and the fast path
         assert (want['peak_count'] > K).any() and (want['peak_count'] <= K).any()
+
+
+def test_candidate_filter_adversarial_inputs_are_bitwise_the_oracle():
+    """Inputs chosen against the strip kernel's bounded filter (okp_peaks_strip.cuh): exact ties,
+    1-ulp tie breaks, a saturated plateau, random-init-network maps (every pixel above threshold),
+    denormal sums, border windows, and maps with negative values (bound void -> exact generic path)."""
+    from oracle import c_oracle
+    from object_keypoints_b200 import KeypointDecoder
+    from test_filter_bound import cases
+    rng = np.random.default_rng(7)
+    for name, p in sorted(cases().items()):
+        H, W = p.shape
+        if W % 4:
+            continue
+        threshold = 0.0 if name == 'tiny_values' else 0.5
+        negative = p.copy()
+        negative[H // 2, W // 2] = -0.25                              # one negative pixel in an otherwise equal map
+        mixed = rng.uniform(-0.1, 0.3, p.shape).astype(np.float32)
+        heat = np.stack([p, negative, mixed, p[::-1].copy()])[None]    # [1, 4, H, W]
+        heat = np.concatenate([heat, heat[:, ::-1]], axis=0)           # 2 frames, maps in a different CTA slot
+        cfg = [1, 1, 1]
+        K = 128
+        decoder = KeypointDecoder(cfg, (H, W), max_peaks=K, max_objects=16, threshold=threshold)
+        got = decoder.extract_peaks(heat).numpy()
+        want = c_oracle.decode(heat, np.zeros_like(heat), np.zeros((2, 3, 2, H, W), np.float32), cfg, None,
+                               max_peaks=K, max_objects=16, threshold=threshold)
+        np.testing.assert_array_equal(got['peak_count'], want['peak_count'], err_msg=name)
+        np.testing.assert_array_equal(got['peak_yx'], want['peak_yx'], err_msg=name)
+        for key in ['peak_score', 'peak_xy', 'peak_conf']:
+            np.testing.assert_array_equal(got[key].view(np.uint32), want[key].view(np.uint32), err_msg=f"{name} {key}")
+
+
+def test_host_batch_in_place_gather_equals_device_decode():
+    """decode_host_batch: pinned depth / centre maps are gathered in place over PCIe (okp_host_alias),
+    pageable ones are copied; both give the tables of the all-device decode, ragged last chunk included."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    cfg = [1, 3]
+    batch = synthetic.make_batch(37, cfg, (64, 64), seed=11, objects=(1, 3))
+    camera = synthetic.default_camera((64, 64))
+    decoder = KeypointDecoder(cfg, (64, 64), camera=camera)
+    want = decoder.decode_batch(batch.heat, batch.depth, batch.centers).numpy()
+    host = [torch.from_numpy(a) for a in (batch.heat, batch.depth, batch.centers)]
+    pinned = [t.pin_memory() for t in host]
+    assert decoder._host_alias(pinned[1]) is not None, "pinned host memory must be device-accessible on this box"
+    assert decoder._host_alias(host[1]) is None
+    for inputs, copied_maps in ((pinned, 1), (host, 3)):
+        got = decoder.decode_host_batch(*inputs, chunk_frames=16)
+        for name in KeypointDecoder.HOST_RESULT_TABLES:
+            np.testing.assert_array_equal(got[name].numpy().view(np.uint8), want[name].view(np.uint8), err_msg=name)
+        if copied_maps == 1:
+            assert decoder.host_bytes_copied == batch.heat.nbytes
+        else:
+            assert decoder.host_bytes_copied == batch.heat.nbytes + batch.depth.nbytes + batch.centers.nbytes
