@@ -30,8 +30,10 @@
 // aligned LDS.128. A thread owns one strip of one map and slides down it; per row step: 2 LDS.128,
 // 21 FADD, 1 STS.128 (S~ to a ring for the neighbourhood test), 3 FMNMX + 1 compare. Pixels above
 // the threshold that top their strip's own 5x4 block set a bit in a row-indexed bitmap ring; the
-// service warps test those bits against the ring, run the exact check and append peaks to the
-// map's list, which the epilogue ranks by raster key and writes, with centroids, to the tables.
+// service warps test those bits against the ring and queue the survivors. The epilogue runs the
+// exact check for all of them at once (one thread each, so the CTA pays one L2 round trip; doing it
+// in the service warps serialised the round trips and stalled the stream on the ring guard), ranks
+// the confirmed peaks by raster key and writes them, with centroids, to the tables.
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
@@ -59,17 +61,19 @@ struct OkpStripPlan {
     int lag;                      // compute batch b may start once the candidates of batch b - lag are done
     int nb;                       // batches
     int K;                        // table capacity per map
+    int PK;                       // candidate slots per map (2 K)
     int wpr;                      // bitmap words per row (bit index = x + 2)
     int threads;
     int half_bytes;               // bytes of one TMA box: M * RB * BW * 4
     int half_stride;              // half_bytes rounded up to 128 (TMA destinations are 128-byte aligned)
     int stage_bytes;              // halves * half_stride
-    int off_score, off_bitmap, off_list, off_count, off_mbar;
+    int off_score, off_bitmap, off_list, off_pending, off_count, off_mbar;
     int smem_bytes;
     int grid;
 };
 
-struct OkpStripPeak { int32_t key; float score; };
+struct OkpStripPeak { int32_t key; float score, cx, cy, conf; };   // a confirmed peak, ready for the tables
+struct OkpStripCandidate { int32_t key; uint32_t ties; };          // survived the S~ test; ties = neighbours in the tie band
 
 __device__ __forceinline__ uint32_t okp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -205,8 +209,10 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
     float* score = reinterpret_cast<float*>(smem + p.off_score);             // [M][SR][SW], column x + 2
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem + p.off_bitmap);     // [SR][M][wpr], bit = x + 2
     OkpStripPeak* list = reinterpret_cast<OkpStripPeak*>(smem + p.off_list); // [M][K]
-    int* count = reinterpret_cast<int*>(smem + p.off_count);                 // [M] peaks, [M] negative-input flags
+    OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + p.off_pending);   // [M][PK]
+    int* count = reinterpret_cast<int*>(smem + p.off_count);                 // [M] peaks, [M] negative-input flags, [M] candidates
     int* negative = count + p.M;
+    int* n_pending = count + 2 * p.M;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_mbar);         // [NS] TMA landed
     uint64_t* done = full + OKP_STRIP_MAX_NS;                            // [NS] compute warps finished the batch
     uint64_t* ready = done + OKP_STRIP_MAX_NS;                           // [lag] same event, for the candidate warps (they may lag)
@@ -219,7 +225,7 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
     const bool service = (tid >> 5) >= compute_warps;
 
     for (int i = tid; i < p.M * SR * p.wpr; i += blockDim.x) bitmap[i] = 0;
-    if (tid < 2 * p.M) count[tid] = 0;
+    for (int i = tid; i < 3 * p.M; i += blockDim.x) count[i] = 0;
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { okp_mbar_init(full + i, 1); okp_mbar_init(done + i, compute_warps); }
         for (int i = 0; i < p.lag; ++i) { okp_mbar_init(ready + i, compute_warps); okp_mbar_init(swept + i, NSW - 1); }
@@ -259,7 +265,7 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
                 okp_mbar_wait(ready + slot, parity);      // batch b: S~ rows + candidate bits are visible
                 // Rows whose 5x5 neighbourhood is now complete: [y0 - 2, y0 + 3). A row's bitmap is cut into
                 // chunks of 32 words, dealt round-robin to the candidate warps; a lane owns one word and
-                // walks its set bits (a few per blob): neighbourhood test on S~, then the exact check.
+                // walks its set bits (a few per blob): neighbourhood test on S~; survivors are queued for the epilogue.
                 const int y0 = b * RB - 4;
                 int rr = 0, cc = nwi;                     // chunk = rr * chunks_per_row + cc, without dividing
                 for (;; cc += nw) {
@@ -275,7 +281,6 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
                     *word = 0;
                     const int m2 = j / p.wpr, wi = j - m2 * p.wpr;
                     const float* sm = score + (size_t)m2 * SR * SW + 2;      // sm[ring row * SW + x]
-                    const float* src = heat + (size_t)(first_map + m2) * H * W;
                     do {
                         const int bit = __ffs(mine) - 1;
                         mine &= mine - 1;
@@ -295,20 +300,14 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
                             }
                         }
                         if (!alive) continue;
-                        const float s = okp_exact_box_sum(src, H, W, r, x);
-                        if (!(s > threshold)) continue;
-                        while (ties) {
-                            const int k = __ffs(ties) - 1;
-                            ties &= ties - 1;
-                            if (okp_exact_box_sum(src, H, W, r + k / 5 - 2, x + k % 5 - 2) > s) { alive = false; break; }
-                        }
-                        if (!alive) continue;
-                        const int entry = atomicAdd(count + m2, 1);           // a peak: S equals the 5x5 maximum
-                        if (entry < p.K) {                                    // overflow: redone by the overflow kernel
-                            OkpStripPeak pk;
-                            pk.key = r * W + x;
-                            pk.score = s;
-                            list[(size_t)m2 * p.K + entry] = pk;
+                        // survivor: the exact check needs global loads, which must not hold up the ring; it
+                        // runs in the epilogue for all survivors of the CTA at once
+                        const int entry = atomicAdd(n_pending + m2, 1);
+                        if (entry < p.PK) {
+                            OkpStripCandidate cd;
+                            cd.key = r * W + x;
+                            cd.ties = ties;
+                            pending[(size_t)m2 * p.PK + entry] = cd;
                         }
                     } while (mine);
                 }
@@ -379,14 +378,66 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
     }
     __syncthreads();
 
-    // ---- epilogue: raster order (rank by key), centroids, final tables, unused slots cleared ----
+    // ---- epilogue A: exact check of every surviving candidate, one thread each (all loads of the CTA in
+    // flight together: one L2 round trip). The 25 window values give the reference's box sum (raster-order
+    // adds) and, for a confirmed peak, its centroid (pipeline.py:46-62) without loading anything twice. ----
+    for (int i = tid; i < p.M * p.PK; i += blockDim.x) {
+        const int mm = i / p.PK, j = i - mm * p.PK;
+        if (first_map + mm >= p.maps || j >= n_pending[mm]) continue;
+        const OkpStripCandidate cd = pending[i];
+        const int y = cd.key / W, x = cd.key - y * W;
+        const float* src = heat + (size_t)(first_map + mm) * H * W;
+        float q[25];
+#pragma unroll
+        for (int k = 0; k < 25; ++k) {
+            const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+            const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+            q[k] = in ? __ldg(src + (size_t)i2 * W + j2) : 0.0f;       // +0 outside: conv2d's zero padding
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 25; ++k) sum = __fadd_rn(sum, q[k]);
+        if (!(sum > threshold)) continue;
+        bool alive = true;
+        uint32_t ties = cd.ties;
+        while (ties) {                                           // neighbours the bound could not order (rare)
+            const int k = __ffs(ties) - 1;
+            ties &= ties - 1;
+            if (okp_exact_box_sum(src, H, W, y + k / 5 - 2, x + k % 5 - 2) > sum) { alive = false; break; }
+        }
+        if (!alive) continue;
+        const int entry = atomicAdd(count + mm, 1);               // a peak: S equals the 5x5 maximum
+        if (entry >= p.K) continue;                               // overflow: redone by the overflow kernel
+        float sy = 0.0f, sx = 0.0f, sp = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 25; ++k) {
+            const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+            const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+            if (in) {                                             // border-clipped window, raster order
+                sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
+                sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
+                sp = __fadd_rn(sp, q[k]);
+            }
+        }
+        OkpStripPeak pk;
+        pk.key = cd.key;
+        pk.score = sum;
+        pk.cx = __fdiv_rn(sx, sp);
+        pk.cy = __fdiv_rn(sy, sp);
+        pk.conf = sp;
+        list[(size_t)mm * p.K + entry] = pk;
+    }
+    __syncthreads();
+
+    // ---- epilogue B: raster order (rank by key), final tables, unused slots cleared ----
     if (tid >= p.threads) return;
     const int mm = tid / p.strips;
     const int s = tid - mm * p.strips;
     const int map = first_map + mm;
     if (map >= p.maps) return;
-    // a map with negative values is reported as overflowing, which hands it to the exact generic path
-    const int total = negative[mm] ? p.K + 1 : count[mm];
+    // a map with negative values, or with more candidates than slots, is reported as overflowing, which
+    // hands it to the exact generic path
+    const int total = (negative[mm] || n_pending[mm] > p.PK) ? p.K + 1 : count[mm];
     if (s == 0) t.peak_count[map] = total;
     if (total > p.K) return;                             // tables of this map are written by the overflow path
     const OkpStripPeak* mine = list + (size_t)mm * p.K;
@@ -404,33 +455,11 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
             int rank = 0;
             for (int j = 0; j < total; ++j) rank += (mine[j].key < pk.key);
             const size_t dst = (size_t)map * p.K + rank;
-            const int y = pk.key / W, x = pk.key - y * W;
-            // centroid over the border-clipped window, raster order (pipeline.py:46-62). The 25 loads are
-            // independent (clamped address, zero weight outside the image: adding +0 changes nothing), so
-            // the whole map's peaks cost one L2 round trip here instead of one per tap inside the row loop.
-            const float* src = heat + (size_t)map * H * W;
-            float q[25];
-#pragma unroll
-            for (int k = 0; k < 25; ++k) {
-                const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                q[k] = in ? __ldg(src + (size_t)i2 * W + j2) : 0.0f;
-            }
-            float sy = 0.0f, sx = 0.0f, sp = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 25; ++k) {
-                const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                if (in) {
-                    sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
-                    sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
-                    sp = __fadd_rn(sp, q[k]);
-                }
-            }
-            t.peak_yx[2 * dst] = y; t.peak_yx[2 * dst + 1] = x;
+            const int y = pk.key / W;
+            t.peak_yx[2 * dst] = y; t.peak_yx[2 * dst + 1] = pk.key - y * W;
             t.peak_score[dst] = pk.score;
-            t.peak_xy[2 * dst] = __fdiv_rn(sx, sp); t.peak_xy[2 * dst + 1] = __fdiv_rn(sy, sp);
-            t.peak_conf[dst] = sp;
+            t.peak_xy[2 * dst] = pk.cx; t.peak_xy[2 * dst + 1] = pk.cy;
+            t.peak_conf[dst] = pk.conf;
         }
     }
 }
@@ -463,7 +492,7 @@ static inline bool okp_strip_plan(int maps, int H, int W, int K, OkpStripPlan* o
     if (const char* e = getenv("OKP_STRIP_STAGES")) p.NS = atoi(e) >= 2 && atoi(e) <= OKP_STRIP_MAX_NS ? atoi(e) : 4;      // tuning aid
     p.lag = (p.SR - 8) / OKP_STRIP_RB + 1;                // rows [5b'-8, ..) of a pending sweep must not alias rows <= 5b
     const int per_map = p.NS * OKP_STRIP_RB * p.BW * p.halves * 4 + p.SR * p.SW * 4 +
-                        p.SR * p.wpr * 4 + K * (int)sizeof(OkpStripPeak) + 8;
+                        p.SR * p.wpr * 4 + K * (int)sizeof(OkpStripPeak) + 2 * K * (int)sizeof(OkpStripCandidate) + 12;
     int budget = 110 * 1024;                              // two CTAs per SM
     if (const char* e = getenv("OKP_STRIP_SMEM_KB")) budget = atoi(e) * 1024;                                     // tuning aid
     int M = (budget - 1024) / per_map;
@@ -483,8 +512,11 @@ static inline bool okp_strip_plan(int maps, int H, int W, int K, OkpStripPlan* o
     p.off_score = off; off += M * p.SR * p.SW * 4;
     p.off_bitmap = off; off += M * p.SR * p.wpr * 4;
     off = okp_round_up_int(off, 8);
+    p.PK = 2 * K;
     p.off_list = off; off += M * K * (int)sizeof(OkpStripPeak);
-    p.off_count = off; off += 2 * M * 4;
+    off = okp_round_up_int(off, 8);
+    p.off_pending = off; off += M * p.PK * (int)sizeof(OkpStripCandidate);
+    p.off_count = off; off += 3 * M * 4;
     off = okp_round_up_int(off, 8);
     p.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 2 * OKP_STRIP_MAX_LAG) * 8;
     p.smem_bytes = off;
