@@ -167,7 +167,10 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     const int yc = y - 2;
     if (yc < 0 || yc >= H) return;                                  // uniform
     const float (&b)[4] = sv[R2];
-    if (fmaxf(fmaxf(b[0], b[1]), fmaxf(b[2], b[3])) > thr_lo) {     // rare; runs warp-wide, keep it short
+    // warp-uniform branch (taken by about a quarter of the warp rows of a busy map): the column maxima of
+    // the neighbouring strips come from the neighbouring lanes, so that a bit is only set for a pixel that
+    // tops (within the tie band) its whole 5 x 5 neighbourhood as far as this warp can see it
+    if (__any_sync(0xffffffffu, fmaxf(fmaxf(b[0], b[1]), fmaxf(b[2], b[3])) > thr_lo)) {
         const float ninf = -INFINITY;
         // rows y-4, y-3 (slots I+1, I+2) and y-1, y (slots I+4, I) may lie outside the image: max_pool2d pads with -inf
         const bool up2 = yc >= 2, up1 = yc >= 1, dn1 = yc + 1 < H, dn2 = yc + 2 < H;
@@ -181,13 +184,23 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
             m = fmaxf(m, dn2 ? sv[I][c] : ninf);
             cm[c] = ((vmask >> c) & 1u) ? m : ninf;                  // columns outside the image never win
         }
-        const float n012 = fmaxf(fmaxf(cm[0], cm[1]), cm[2]), n123 = fmaxf(fmaxf(cm[1], cm[2]), cm[3]);
-        const float nall = fmaxf(n012, cm[3]);
+        // columns -2, -1 from the strip to the left, 4, 5 from the strip to the right. vmask bits 4 / 5 say that
+        // lane - 1 / lane + 1 holds that strip; where it does not (warp edge: unknown, image edge: nothing
+        // there) -inf keeps the test conservative, the candidate warps see the whole neighbourhood anyway
+        float l2 = __shfl_up_sync(0xffffffffu, cm[2], 1), l3 = __shfl_up_sync(0xffffffffu, cm[3], 1);
+        float r0 = __shfl_down_sync(0xffffffffu, cm[0], 1), r1 = __shfl_down_sync(0xffffffffu, cm[1], 1);
+        if (!(vmask & 16u)) { l2 = ninf; l3 = ninf; }
+        if (!(vmask & 32u)) { r0 = ninf; r1 = ninf; }
+        const float m12 = fmaxf(cm[1], cm[2]);
+        const float n0 = fmaxf(fmaxf(l2, l3), fmaxf(cm[0], m12));
+        const float n1 = fmaxf(fmaxf(l3, cm[0]), fmaxf(m12, cm[3]));
+        const float n2 = fmaxf(fmaxf(cm[0], m12), fmaxf(cm[3], r0));
+        const float n3 = fmaxf(fmaxf(m12, cm[3]), fmaxf(r0, r1));
         const float tie = OKP_STRIP_TIE;
-        uint32_t bits = (b[0] > thr_lo && b[0] * tie >= n012) ? 1u : 0u;
-        bits |= (b[1] > thr_lo && b[1] * tie >= nall) ? 2u : 0u;
-        bits |= (b[2] > thr_lo && b[2] * tie >= nall) ? 4u : 0u;
-        bits |= (b[3] > thr_lo && b[3] * tie >= n123) ? 8u : 0u;
+        uint32_t bits = (b[0] > thr_lo && b[0] * tie >= n0) ? 1u : 0u;
+        bits |= (b[1] > thr_lo && b[1] * tie >= n1) ? 2u : 0u;
+        bits |= (b[2] > thr_lo && b[2] * tie >= n2) ? 4u : 0u;
+        bits |= (b[3] > thr_lo && b[3] * tie >= n3) ? 8u : 0u;
         bits &= vmask;
         if (bits) atomicOr(bitmap_map + (yc & ring_mask) * bitmap_pitch + (xs >> 5), bits << (xs & 31));
     }
@@ -327,6 +340,8 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
 #pragma unroll
         for (int c = 0; c < 4; ++c) vmask |= (xs + c - 2 >= 0 && xs + c - 2 < W) ? (1u << c) : 0u;
         if (!active) vmask = 0;
+        if (active && (tid & 31) > 0 && s > 0) vmask |= 16u;                   // lane - 1 holds strip s - 1 of this map
+        if (active && (tid & 31) < 31 && s + 1 < p.strips && tid + 1 < p.threads) vmask |= 32u;   // lane + 1 holds strip s + 1
         // this thread's window row inside a stage: box [M][RB][BW], first column 4 * (s - half * half_strips)
         const int thread_raw = half * p.half_stride + (mm * RB * p.BW + 4 * (s - half * p.half_strips)) * 4;
         const int row_pitch = p.BW * 4;
@@ -484,8 +499,8 @@ static inline bool okp_strip_plan(int maps, int H, int W, int K, OkpStripPlan* o
     p.BW = 4 * p.half_strips + 4;                         // columns 4s-4 .. 4s+3 of the box's strips
     p.wpr = (W + 4 + 31) / 32;
     p.nb = (H + 6 + OKP_STRIP_RB - 1) / OKP_STRIP_RB;
-    p.service_warps = 3;                                  // 1 TMA producer + 2 candidate warps
-    if (const char* e = getenv("OKP_STRIP_SERVICE_WARPS")) p.service_warps = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;   // tuning aid
+    p.service_warps = 4;                                  // 1 TMA producer + 3 candidate warps
+    if (const char* e = getenv("OKP_STRIP_SERVICE_WARPS")) p.service_warps = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 4;   // tuning aid
     p.SR = 16;
     if (const char* e = getenv("OKP_STRIP_RING")) p.SR = atoi(e) == 32 ? 32 : 16;                                 // tuning aid
     p.NS = 4;                                             // ~3 batches in flight per CTA cover the HBM latency
