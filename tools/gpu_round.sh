@@ -10,7 +10,7 @@ tail -3 $out/pytest_gpu.log
 timeout 300 python tools/bench_k1.py 180x320 2048 10 > $out/bench_k1.log 2>&1
 timeout 300 python tools/bench_k1.py 64x64 32768 10 >> $out/bench_k1.log 2>&1
 cat $out/bench_k1.log
-if grep -q 'pytest exit 0' $out/pytest_gpu.log; then timeout 600 python tools/sweep_k1.py 180x320 2048 5 > $out/sweep_k1.log 2>&1; timeout 300 python tools/sweep_k1.py 64x64 32768 5 >> $out/sweep_k1.log 2>&1; grep -v '^$' $out/sweep_k1.log | tail -60; fi
+if grep -q 'pytest exit 0' $out/pytest_gpu.log; then timeout 240 python tools/sweep_k1.py 180x320 2048 3 > $out/sweep_k1.log 2>&1; timeout 120 python tools/sweep_k1.py 64x64 32768 3 >> $out/sweep_k1.log 2>&1; grep -v '^$' $out/sweep_k1.log | tail -60; fi
 timeout 900 python bench.py --steps 10 --warmup 3 > $out/bench.json 2> $out/bench.err; tail -2 $out/bench.err; cat $out/bench.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_reference.json 2>> $out/bench.err; cat $out/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/launches.csv \

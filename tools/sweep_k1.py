@@ -16,10 +16,10 @@ tables = dec.tables(frames)
 gb = frames * 3 * H * W * 4 / 1e9
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 rows = []
-for stages, smem, service in itertools.product([2, 3, 4, 6], [72, 110, 220], [3, 4]):
+for stages, smem, service in itertools.product([2, 3, 4, 6], [56, 72, 110, 220], [160, 288, 608]):
     os.environ['OKP_STRIP_STAGES'] = str(stages)
     os.environ['OKP_STRIP_SMEM_KB'] = str(smem)
-    os.environ['OKP_STRIP_SERVICE_WARPS'] = str(service)
+    os.environ['OKP_STRIP_THREADS'] = str(service)
     try:
         for _ in range(2):
             dec.extract_peaks(heat, tables)
@@ -31,9 +31,9 @@ for stages, smem, service in itertools.product([2, 3, 4, 6], [72, 110, 220], [3,
             total += ev[0].elapsed_time(ev[1])
         ms = total / reps
         rows.append((gb / (ms / 1e3), stages, smem, service, ms))
-        print(f"{shape} stages={stages} smem_kb={smem} service={service}: {ms * 1e3:.1f} us = {gb / (ms / 1e3):.0f} GB/s", flush=True)
+        print(f"{shape} stages={stages} smem_kb={smem} threads={service}: {ms * 1e3:.1f} us = {gb / (ms / 1e3):.0f} GB/s", flush=True)
     except Exception as e:
-        print(f"{shape} stages={stages} smem_kb={smem} service={service}: FAILED {e}", flush=True)
+        print(f"{shape} stages={stages} smem_kb={smem} threads={service}: FAILED {e}", flush=True)
         break
 rows.sort(reverse=True)
 print("best:", rows[:3])
