@@ -142,8 +142,9 @@ struct OkpStripLane {
 // (lo, hi) are the columns 4s-4 .. 4s+3 of the new input row y + 2; the step produces S~ of row y for
 // the strip's pixels x = xs + c - 2 (c = 0..3). pr keeps the running pair sums h(t-1) + h(t) of the
 // horizontal sums, sv the strip's last five rows of S~, so that the pixels of row y - 2 can be tested
-// against their 5x5 neighbourhood as soon as S~ of row y is known.
-template <int I>
+// against their 5x5 neighbourhood as soon as S~ of row y is known. EDGE = false: the batch lies in the
+// interior of the map (every row of every neighbourhood exists), which saves the -inf padding selects.
+template <int I, bool EDGE>
 __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi, float (&pr)[5][4], float (&hp)[4],
                                                float (&sv)[5][4], uint32_t& sign, int y, const OkpStripLane& L) {
     // horizontal 5-sums of the four windows w[c .. c+4] (w = lo.xyzw, hi.xyzw): 9 adds
@@ -166,7 +167,7 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     }
     // ---- row yc = y - 2 (slot R2), whose five rows of S~ are now known ----
     const int yc = y - 2;
-    if (yc < 0 || yc >= L.H) return;                                // uniform over the CTA
+    if (EDGE && (yc < 0 || yc >= L.H)) return;                      // uniform over the CTA
     constexpr int R2 = (I + 3) % 5;
     const float (&b)[4] = sv[R2];
     // warp-uniform branch (taken by about a quarter of the warp rows of a busy map)
@@ -174,16 +175,14 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     const float ninf = -INFINITY;
     const uint32_t vmask = L.vmask;
     // rows yc-2, yc-1 (slots I+1, I+2) and yc+1, yc+2 (slots I+4, I) may lie outside the image: max_pool2d pads with -inf
-    const bool up2 = yc >= 2, up1 = yc >= 1, dn1 = yc + 1 < L.H, dn2 = yc + 2 < L.H;
-    float cm[4];
+    const bool up2 = !EDGE || yc >= 2, up1 = !EDGE || yc >= 1, dn1 = !EDGE || yc + 1 < L.H, dn2 = !EDGE || yc + 2 < L.H;
+    float own[4], cm[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        float m = b[c];
-        m = fmaxf(m, up2 ? sv[(I + 1) % 5][c] : ninf);
-        m = fmaxf(m, up1 ? sv[(I + 2) % 5][c] : ninf);
-        m = fmaxf(m, dn1 ? sv[(I + 4) % 5][c] : ninf);
-        m = fmaxf(m, dn2 ? sv[I][c] : ninf);
-        cm[c] = ((vmask >> c) & 1u) ? m : ninf;                      // columns outside the image never win
+        float m = fmaxf(up2 ? sv[(I + 1) % 5][c] : ninf, up1 ? sv[(I + 2) % 5][c] : ninf);
+        m = fmaxf(m, fmaxf(dn1 ? sv[(I + 4) % 5][c] : ninf, dn2 ? sv[I][c] : ninf));
+        own[c] = m;                                                  // column c without the centre row
+        cm[c] = ((vmask >> c) & 1u) ? fmaxf(m, b[c]) : ninf;         // columns outside the image never win
     }
     // columns -2, -1 from the strip to the left, 4, 5 from the strip to the right. Where the neighbouring
     // lane does not hold that strip (warp edge: unknown; image edge: nothing there) -inf keeps the test
@@ -192,51 +191,45 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     float r0 = __shfl_down_sync(0xffffffffu, cm[0], 1), r1 = __shfl_down_sync(0xffffffffu, cm[1], 1);
     if (!(vmask & 16u)) { l2 = ninf; l3 = ninf; }
     if (!(vmask & 32u)) { r0 = ninf; r1 = ninf; }
-    const float m12 = fmaxf(cm[1], cm[2]);
-    const float n0 = fmaxf(fmaxf(l2, l3), fmaxf(cm[0], m12));
-    const float n1 = fmaxf(fmaxf(l3, cm[0]), fmaxf(m12, cm[3]));
-    const float n2 = fmaxf(fmaxf(cm[0], m12), fmaxf(cm[3], r0));
-    const float n3 = fmaxf(fmaxf(m12, cm[3]), fmaxf(r0, r1));
+    // maximum over the pixel's neighbours (5 columns x 5 rows without the pixel itself)
+    const float q0 = fmaxf(fmaxf(l2, l3), fmaxf(cm[1], cm[2])), q3 = fmaxf(fmaxf(cm[1], cm[2]), fmaxf(r0, r1));
+    const float others[4] = {fmaxf(own[0], q0), fmaxf(fmaxf(l3, cm[0]), fmaxf(own[1], fmaxf(cm[2], cm[3]))),
+                             fmaxf(fmaxf(cm[0], cm[1]), fmaxf(own[2], fmaxf(cm[3], r0))), fmaxf(own[3], q3)};
     const float tie = OKP_STRIP_TIE;
-    uint32_t bits = (b[0] > L.thr_lo && b[0] * tie >= n0) ? 1u : 0u;
-    bits |= (b[1] > L.thr_lo && b[1] * tie >= n1) ? 2u : 0u;
-    bits |= (b[2] > L.thr_lo && b[2] * tie >= n2) ? 4u : 0u;
-    bits |= (b[3] > L.thr_lo && b[3] * tie >= n3) ? 8u : 0u;
-    bits &= vmask;
-    if (!bits) return;
-    // ---- candidates (a few per blob): no visible neighbour is provably larger. Collect the neighbours
-    // that are not provably smaller (own strip: pixel by pixel; neighbouring lanes: by column maximum;
-    // other warps: unknown) for the exact check in the epilogue ----
-    const uint32_t rowmask = (up2 ? 0x1Fu : 0u) | (up1 ? 0x3E0u : 0u) | 0x6C00u | (dn1 ? 0xF8000u : 0u) | (dn2 ? 0x1F00000u : 0u);
-    const float side[4] = {l2, l3, r0, r1};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        if (!((bits >> c) & 1u)) continue;
-        const float sp = b[c];
-        const int x = L.xs + c - 2;
-        uint32_t ties = 0;
-#pragma unroll
-        for (int dc = -2; dc <= 2; ++dc) {
-            const int col = c + dc;
-            if (x + dc < 0 || x + dc >= L.W) continue;
-            if (col >= 0 && col <= 3) {
-#pragma unroll
-                for (int dr = -2; dr <= 2; ++dr)
-                    if (sv[(I + 8 + dr) % 5][col] * tie >= sp) ties |= 1u << (5 * (dr + 2) + dc + 2);
-            } else {
-                const bool known = col < 0 ? (vmask & 16u) != 0 : (vmask & 32u) != 0;
-                if (!known || side[col < 0 ? col + 2 : col - 2] * tie >= sp) ties |= 0x108421u << (dc + 2);
-            }
-        }
-        ties &= rowmask;
+        // a candidate: above the threshold, inside the image, and no visible neighbour is provably larger
+        if (!(b[c] > L.thr_lo && b[c] * tie >= others[c] && ((vmask >> c) & 1u))) continue;
+        // neighbours that are not provably smaller go into the exact-check mask: all of them when any is inside the
+        // tie band (rare), and the columns another warp holds; the epilogue drops the ones outside the image
+        uint32_t ties = others[c] * tie >= b[c] ? 0x1FFEFFFu : 0u;
+        if (c < 2 && !(vmask & 16u)) ties |= c == 0 ? 0x318C63u : 0x108421u;
+        if (c > 1 && !(vmask & 32u)) ties |= c == 3 ? 0x18C6318u : 0x1084210u;
         const int entry = atomicAdd(L.n_pending, 1);
         if (entry < L.PK) {
             OkpStripCandidate cd;
-            cd.key = yc * L.W + x;
+            cd.key = yc * L.W + L.xs + c - 2;
             cd.ties = ties;
             L.pending[entry] = cd;
         }
     }
+}
+
+// One batch of RB rows: the five unrolled steps, rows fetched one step ahead of their use (two register
+// pairs, ping-pong). raw: this thread's window in the stage; y0: the batch's first output row.
+template <bool EDGE>
+__device__ __forceinline__ void okp_strip_batch(const unsigned char* raw, int row_pitch, float (&pr)[5][4], float (&hp)[4],
+                                                float (&sv)[5][4], uint32_t& sign, int y0, const OkpStripLane& L) {
+    float4 a0 = reinterpret_cast<const float4*>(raw)[0], a1 = reinterpret_cast<const float4*>(raw)[1];
+    float4 b0 = reinterpret_cast<const float4*>(raw + row_pitch)[0], b1 = reinterpret_cast<const float4*>(raw + row_pitch)[1];
+    okp_strip_step<0, EDGE>(a0, a1, pr, hp, sv, sign, y0 + 0, L);
+    a0 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[1];
+    okp_strip_step<1, EDGE>(b0, b1, pr, hp, sv, sign, y0 + 1, L);
+    b0 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[0]; b1 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[1];
+    okp_strip_step<2, EDGE>(a0, a1, pr, hp, sv, sign, y0 + 2, L);
+    a0 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[1];
+    okp_strip_step<3, EDGE>(b0, b1, pr, hp, sv, sign, y0 + 3, L);
+    okp_strip_step<4, EDGE>(a0, a1, pr, hp, sv, sign, y0 + 4, L);
 }
 
 // Roles. Warps [0, CW) are compute warps (thread = one strip of one map, packed densely); the only thing
@@ -324,18 +317,11 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
         for (int b = 0; b < p.nb; ++b) {
             okp_mbar_wait(full + stage, full_parity);
             const unsigned char* raw = smem + (size_t)stage * p.stage_bytes + thread_raw;
-            const int y0 = b * RB - 4;                    // new row of step i is y0 + i + 2
-            // rows are fetched one step ahead of their use (two register pairs, ping-pong)
-            float4 a0 = reinterpret_cast<const float4*>(raw)[0], a1 = reinterpret_cast<const float4*>(raw)[1];
-            float4 b0 = reinterpret_cast<const float4*>(raw + row_pitch)[0], b1 = reinterpret_cast<const float4*>(raw + row_pitch)[1];
-            okp_strip_step<0>(a0, a1, pr, hp, sv, sign, y0 + 0, L);
-            a0 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[1];
-            okp_strip_step<1>(b0, b1, pr, hp, sv, sign, y0 + 1, L);
-            b0 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[0]; b1 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[1];
-            okp_strip_step<2>(a0, a1, pr, hp, sv, sign, y0 + 2, L);
-            a0 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[1];
-            okp_strip_step<3>(b0, b1, pr, hp, sv, sign, y0 + 3, L);
-            okp_strip_step<4>(a0, a1, pr, hp, sv, sign, y0 + 4, L);
+            const int y0 = b * RB - 4;                    // new row of step i is y0 + i + 2, tested row y0 + i - 2
+            if (b >= 2 && y0 + 4 < H)                     // rows y0 - 4 .. y0 + 4 all exist
+                okp_strip_batch<false>(raw, row_pitch, pr, hp, sv, sign, y0, L);
+            else
+                okp_strip_batch<true>(raw, row_pitch, pr, hp, sv, sign, y0, L);
             __syncwarp();
             if ((tid & 31) == 0) okp_mbar_arrive(done + stage);
             if (++stage == NS) { stage = 0; full_parity ^= 1u; }
@@ -383,7 +369,9 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
                 pk.cx = __fdiv_rn(sx, sp);
                 pk.cy = __fdiv_rn(sy, sp);
                 pk.conf = sp;
-                uint32_t ties = cd.ties;
+                uint32_t ties = cd.ties;                          // keep the neighbours that exist
+                ties &= (y >= 2 ? 0x1Fu : 0u) | (y >= 1 ? 0x3E0u : 0u) | 0x6C00u | (y + 1 < H ? 0xF8000u : 0u) | (y + 2 < H ? 0x1F00000u : 0u);
+                ties &= (x >= 2 ? 0x108421u : 0u) | (x >= 1 ? 0x210842u : 0u) | 0x421084u | (x + 1 < W ? 0x842108u : 0u) | (x + 2 < W ? 0x1084210u : 0u);
                 if (ties) {
                     const int at = atomicAdd(n_items, __popc(ties));
                     if (at + __popc(ties) > p.IC) {
@@ -487,13 +475,13 @@ static inline bool okp_strip_plan(int maps, int H, int W, int K, OkpStripPlan* o
     }
     p.BW = 4 * p.half_strips + 4;                         // columns 4s-4 .. 4s+3 of the box's strips
     p.nb = (H + 6 + OKP_STRIP_RB - 1) / OKP_STRIP_RB;
-    p.NS = okp_env_int("OKP_STRIP_STAGES", 2, OKP_STRIP_MAX_NS, 3);
+    p.NS = okp_env_int("OKP_STRIP_STAGES", 2, OKP_STRIP_MAX_NS, 4);
     p.PK = 2 * K;
     const int items_per_map = 64;
     const int per_map = p.NS * OKP_STRIP_RB * p.BW * p.halves * 4 +
                         p.PK * (int)(sizeof(OkpStripCandidate) + sizeof(OkpStripPeak)) + items_per_map * 4 + 12;
-    const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 220) * 1024;   // default: one CTA per SM
-    const int max_threads = okp_env_int("OKP_STRIP_THREADS", 32, OKP_STRIP_MAX_THREADS - 32, 608);
+    const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;   // default: two CTAs per SM
+    const int max_threads = okp_env_int("OKP_STRIP_THREADS", 32, OKP_STRIP_MAX_THREADS - 32, 288);
     int M = (budget - 1024) / per_map;
     if (M > max_threads / p.strips) M = max_threads / p.strips;
     if (M > maps) M = maps;

@@ -16,7 +16,7 @@ tables = dec.tables(frames)
 gb = frames * 3 * H * W * 4 / 1e9
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 rows = []
-for stages, smem, service in itertools.product([2, 3, 4, 6], [56, 72, 110, 220], [160, 288, 608]):
+for stages, smem, service in itertools.product([2, 3, 4], [110, 220], [288, 448, 608]):
     os.environ['OKP_STRIP_STAGES'] = str(stages)
     os.environ['OKP_STRIP_SMEM_KB'] = str(smem)
     os.environ['OKP_STRIP_THREADS'] = str(service)
