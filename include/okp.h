@@ -187,6 +187,27 @@ int okp_triangulate_robust_f64(const double* obs_dev, uint8_t* valid_dev, const 
                                const OkpCamera* camera, int P, int V, double max_error_px, int max_rounds,
                                double* out_dev, double* err_dev, int32_t* dropped_dev, void* stream);
 
+/* Replaces the cv2.correctMatches call of StereoCamera.triangulate (camera_utils.py:100-101): the
+ * Hartley-Sturm optimal correction. F: 9 doubles row-major on the HOST with x_right^T F x_left = 0
+ * (camera_utils.py:184-189). left_dev/right_dev: [n,2] float64 UNDISTORTED pixels; the outputs are the
+ * closest pair (in summed squared pixel distance) that satisfies the epipolar constraint exactly.
+ * round_to_f32 != 0 rounds the outputs to float32 like OpenCV does for the float32 input the
+ * reference passes (camera_utils.py:93-94). Where the minimum is at t = infinity OpenCV returns NaN;
+ * this entry returns the limit point. */
+int okp_correct_matches_f64(const double* F, const double* left_dev, const double* right_dev, int n,
+                            int round_to_f32, double* left_out_dev, double* right_out_dev, void* stream);
+
+/* Stereo association (the AssociationComponent test/test_pipeline.py:208-261 expects; its
+ * implementation is absent from the reference). For each of B frame pairs: left_dev [B,max_left,2] and
+ * right_dev [B,max_right,2] float64 UNDISTORTED pixels with n_left_dev / n_right_dev [B] valid counts
+ * (max_left, max_right <= 64). cost = mean of the two point-to-epipolar-line distances; matches are
+ * taken greedily by globally smallest cost, one-to-one, while cost <= max_distance_px.
+ * match_dev [B,max_left]: index into the frame's right points or -1; cost_dev [B,max_left]. */
+int okp_stereo_associate_f64(const double* F, const double* left_dev, const int32_t* n_left_dev,
+                             const double* right_dev, const int32_t* n_right_dev, int B, int max_left,
+                             int max_right, double max_distance_px, int32_t* match_dev, double* cost_dev,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ from .pipeline import (DecodeTables, KeypointDecoder, InferenceComponent, Keypoi
                        ObjectExtraction, DetectionToPoint, ObjectKeypointPipeline,
                        LearnedKeypointTrackingPipeline, tables_to_objects, tables_to_keypoints)
 from .triangulation import (TriangulationComponent, triangulate, triangulate_multiview, triangulate_stereo,   # noqa: F401
-                            undistort_points, project_points, reprojection_filter)
+                            undistort_points, project_points, reprojection_filter, correct_matches, associate,
+                            AssociationComponent)
 
 __version__ = "0.1.0"

@@ -16,7 +16,7 @@ EXPORTS = [
     'okp_version', 'okp_strerror', 'okp_decode_workspace_bytes', 'okp_extract_peaks_f32',
     'okp_group_objects_f32', 'okp_decode_f32', 'okp_fisheye_undistort_f64', 'okp_fisheye_project_f64',
     'okp_detection_to_point_f32', 'okp_triangulate_f64', 'okp_reprojection_filter_f64',
-    'okp_triangulate_robust_f64', 'okp_host_alias',
+    'okp_triangulate_robust_f64', 'okp_host_alias', 'okp_correct_matches_f64', 'okp_stereo_associate_f64',
 ]
 
 
@@ -89,6 +89,10 @@ def lib():
     L.okp_reprojection_filter_f64.argtypes = [vp, vp, vp, vp, P(_abi.OkpCamera), i32, i32, dbl, vp, vp]
     L.okp_triangulate_robust_f64.restype = i32
     L.okp_triangulate_robust_f64.argtypes = [vp, vp, vp, P(_abi.OkpCamera), i32, i32, dbl, i32, vp, vp, vp, vp]
+    L.okp_correct_matches_f64.restype = i32
+    L.okp_correct_matches_f64.argtypes = [P(dbl), vp, vp, i32, i32, vp, vp, vp]
+    L.okp_stereo_associate_f64.restype = i32
+    L.okp_stereo_associate_f64.argtypes = [P(dbl), vp, vp, vp, vp, i32, i32, i32, dbl, vp, vp, vp]
     _LIB = L
     return L
 

@@ -186,7 +186,7 @@ class StereoCamera:
         P2 = self.right_camera.K @ self.T_RL[:3]
         return P1, P2
 
-    def triangulate(self, left_keypoints, right_keypoints, optimal_correction=False):
+    def triangulate(self, left_keypoints, right_keypoints, optimal_correction=True):
         """N x 2 distorted pixel pairs -> N x 3 points in the left camera frame, on the GPU.
 
         Follows camera_utils.py:92-110: cast to float32, undistort both views, Hartley-Sturm

@@ -10,6 +10,7 @@
 #include "okp_geometry.cuh"
 #include "okp_group.cuh"
 #include "okp_dlt.cuh"
+#include "okp_stereo.cuh"
 
 namespace {
 
@@ -259,6 +260,34 @@ int okp_triangulate_robust_f64(const double* obs_dev, uint8_t* valid_dev, const 
     const size_t smem = sizeof(double) * 24 * (size_t)V;
     okp_triangulate_robust_kernel<<<(P + 127) / 128, 128, smem, (cudaStream_t)stream>>>(
         obs_dev, valid_dev, poses_dev, *camera, P, V, max_error_px, max_rounds, out_dev, err_dev, dropped_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_correct_matches_f64(const double* F, const double* left_dev, const double* right_dev, int n, int round_to_f32,
+                            double* left_out_dev, double* right_out_dev, void* stream) {
+    if (n < 0) return OKP_E_SHAPE;
+    if (n == 0) return OKP_OK;
+    if (!F || !left_dev || !right_dev || !left_out_dev || !right_out_dev) return OKP_E_NULL;
+    OkpMat3 Fm;
+    for (int i = 0; i < 9; ++i) Fm.m[i] = F[i];
+    okp_correct_matches_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(Fm, left_dev, right_dev, n, round_to_f32,
+                                                                              left_out_dev, right_out_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_stereo_associate_f64(const double* F, const double* left_dev, const int32_t* n_left_dev, const double* right_dev,
+                             const int32_t* n_right_dev, int B, int max_left, int max_right, double max_distance_px,
+                             int32_t* match_dev, double* cost_dev, void* stream) {
+    if (B < 0 || max_left < 1 || max_right < 1 || max_left > OKP_ASSOC_MAX || max_right > OKP_ASSOC_MAX) return OKP_E_SHAPE;
+    if (B == 0) return OKP_OK;
+    if (!F || !left_dev || !n_left_dev || !right_dev || !n_right_dev || !match_dev || !cost_dev) return OKP_E_NULL;
+    OkpMat3 Fm;
+    for (int i = 0; i < 9; ++i) Fm.m[i] = F[i];
+    const size_t smem = sizeof(double) * (size_t)max_left * max_right;
+    okp_associate_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(Fm, left_dev, n_left_dev, right_dev, n_right_dev,
+                                                               max_left, max_right, max_distance_px, match_dev, cost_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

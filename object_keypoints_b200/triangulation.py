@@ -7,7 +7,10 @@
   (scripts/label.py:296-305);
 * ``TriangulationComponent`` -- the ``reset(stereo)`` / ``__call__(left, right)`` component the
   reference's test-suite expects (test/test_pipeline.py:171-177), pairs matched by index;
-* ``triangulate_multiview`` -- undistort, DLT over V views, reprojection-error gate, re-solve.
+* ``triangulate_multiview`` -- undistort, DLT over V views, reprojection-error gate, re-solve;
+* ``correct_matches`` -- cv2.correctMatches (Hartley-Sturm) as camera_utils.py:100-101 uses it;
+* ``AssociationComponent`` / ``associate`` -- stereo association by epipolar distance
+  (test/test_pipeline.py:208-261).
 """
 import ctypes
 
@@ -121,16 +124,92 @@ def triangulate_multiview(observations, valid, poses, camera, max_error_px=2.0, 
     return X, valid, err
 
 
-def triangulate_stereo(stereo, left_keypoints, right_keypoints, optimal_correction=False):
+def correct_matches(F, left, right, round_to_f32=False, device=None):
+    """cv2.correctMatches (camera_utils.py:100-101) on the GPU: [n,2] UNDISTORTED pixel pairs ->
+    the closest pairs that satisfy x_right^T F x_left = 0 (Hartley-Sturm). Returns two [n,2] float64
+    CUDA tensors."""
+    device = _device(device)
+    left = _as_f64(left, device)
+    right = _as_f64(right, device)
+    if left.shape != right.shape or left.dim() != 2 or left.shape[1] != 2:
+        raise ValueError(f"correct_matches wants two [n,2] arrays, got {tuple(left.shape)} and {tuple(right.shape)}")
+    out_left = torch.empty_like(left)
+    out_right = torch.empty_like(right)
+    Fm = np.ascontiguousarray(np.asarray(F, dtype=np.float64).reshape(9))
+    rc = _lib.lib().okp_correct_matches_f64(Fm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), left.data_ptr(),
+                                            right.data_ptr(), int(left.shape[0]), int(round_to_f32),
+                                            out_left.data_ptr(), out_right.data_ptr(), _stream_handle())
+    _lib.check(rc, 'okp_correct_matches_f64')
+    return out_left, out_right
+
+
+def associate(F, left, right, n_left=None, n_right=None, max_distance_px=2.5, device=None):
+    """Batched stereo association: left [B,ML,2], right [B,MR,2] UNDISTORTED pixels (+ optional valid
+    counts [B]) -> (match [B,ML] int32: index into right or -1, cost [B,ML] float64 pixels)."""
+    device = _device(device)
+    left = _as_f64(left, device)
+    right = _as_f64(right, device)
+    B, ML, MR = int(left.shape[0]), int(left.shape[1]), int(right.shape[1])
+
+    def counts(n, full):
+        if n is None:
+            return torch.full((B,), full, dtype=torch.int32, device=device)
+        if isinstance(n, np.ndarray):
+            n = torch.from_numpy(np.ascontiguousarray(n))
+        return torch.as_tensor(n).to(device=device, dtype=torch.int32).contiguous()
+    n_left = counts(n_left, ML)
+    n_right = counts(n_right, MR)
+    match = torch.empty((B, max(ML, 1)), dtype=torch.int32, device=device)
+    cost = torch.empty((B, max(ML, 1)), dtype=torch.float64, device=device)
+    if ML == 0 or MR == 0:
+        return match[:, :ML].fill_(-1), cost[:, :ML].zero_()
+    Fm = np.ascontiguousarray(np.asarray(F, dtype=np.float64).reshape(9))
+    rc = _lib.lib().okp_stereo_associate_f64(Fm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), left.data_ptr(),
+                                             n_left.data_ptr(), right.data_ptr(), n_right.data_ptr(), B, ML, MR,
+                                             float(max_distance_px), match.data_ptr(), cost.data_ptr(),
+                                             _stream_handle())
+    _lib.check(rc, 'okp_stereo_associate_f64')
+    return match, cost
+
+
+class AssociationComponent:
+    """The component test/test_pipeline.py:208-261 expects (its implementation is gone from the
+    reference): ``reset(stereo_camera)`` then ``__call__(left[nL,2], right[nR,2])`` distorted pixels ->
+    int array [nL], the index of the matching right point or -1. Points are undistorted, then matched
+    one-to-one by epipolar distance under ``stereo_camera.F`` (okp_stereo_associate_f64)."""
+    name = "association"
+
+    def __init__(self, max_distance_px=2.5):
+        self.max_distance_px = max_distance_px
+        self.stereo_camera = None
+
+    def reset(self, stereo_camera):
+        self.stereo_camera = stereo_camera
+
+    def __call__(self, left_keypoints, right_keypoints):
+        left = np.asarray(left_keypoints, dtype=np.float64).reshape(-1, 2)
+        right = np.asarray(right_keypoints, dtype=np.float64).reshape(-1, 2)
+        if left.shape[0] == 0 or right.shape[0] == 0:
+            return np.full((left.shape[0],), -1, dtype=np.int64)
+        uL = undistort_points(left, self.stereo_camera.left_camera)
+        uR = undistort_points(right, self.stereo_camera.right_camera)
+        match, _ = associate(self.stereo_camera.F, uL[None], uR[None], max_distance_px=self.max_distance_px)
+        return match[0].cpu().numpy().astype(np.int64)
+
+
+def triangulate_stereo(stereo, left_keypoints, right_keypoints, optimal_correction=True):
     """StereoCamera.triangulate (camera_utils.py:92-110) on the GPU: float32 cast, undistort both
-    views, [optional Hartley-Sturm correction], two-view DLT. Returns [N,3] float64 NumPy in the
-    left camera frame."""
+    views, Hartley-Sturm correction (cv2.correctMatches; ``optimal_correction=False`` gives the plain
+    DLT of scripts/label.py:296-305), two-view DLT. Returns [N,3] float64 NumPy in the left camera
+    frame."""
     left = np.asarray(left_keypoints).astype(np.float32).astype(np.float64)      # camera_utils.py:93-94
     right = np.asarray(right_keypoints).astype(np.float32).astype(np.float64)
+    if left.shape[0] == 0:
+        return np.zeros((0, 3))
     uL = undistort_points(left, stereo.left_camera, round_to_f32=True)
     uR = undistort_points(right, stereo.right_camera, round_to_f32=True)
     if optimal_correction:
-        raise NotImplementedError("Hartley-Sturm correction (cv2.correctMatches) is not on the GPU path yet")
+        uL, uR = correct_matches(stereo.F, uL, uR, round_to_f32=True)            # camera_utils.py:100-101
     P1, P2 = stereo.projection_matrices()
     points = torch.stack([uL, uR], dim=1)
     X = triangulate(points, np.stack([P1, P2]))
@@ -142,7 +221,7 @@ class TriangulationComponent:
     ``__call__(left[N,2], right[N,2])`` -> [N,3] points in the left camera frame."""
     name = "triangulation"
 
-    def __init__(self, optimal_correction=False):
+    def __init__(self, optimal_correction=True):
         self.optimal_correction = optimal_correction
         self.stereo_camera = None
 

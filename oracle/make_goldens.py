@@ -342,12 +342,55 @@ def geometry_case(camera_utils):
     out['D_left'] = left.D
     out['K_right'] = right.K
     out['D_right'] = right.D
+    # Hartley-Sturm stress set (cv2.correctMatches): epipoles at infinity (the rig), inside the image
+    # (forward motion) and a general pose, 0.5 - 1 px noise; own generator so the arrays above keep
+    # their values.
+    rng2 = np.random.default_rng(70)
+    Kl = left.K
+    Fs, ls, rs, cls_, crs = [], [], [], [], []
+    poses = [stereo.T_RL]
+    T = np.eye(4)
+    T[:3, 3] = [0.01, -0.005, -0.25]                      # forward motion: epipole near the image centre
+    poses.append(T)
+    T = np.eye(4)
+    T[:3, :3] = cv2.Rodrigues(np.array([0.2, -0.3, 0.1]))[0]
+    T[:3, 3] = [0.2, 0.1, 0.05]
+    poses.append(T)
+    for T_21, sigma in zip(poses, (0.5, 1.0, 0.7)):
+        Fm = camera_utils.fundamental_matrix(T_21, Kl, Kl)
+        Xs = np.stack([rng2.uniform(-0.4, 0.4, 96), rng2.uniform(-0.25, 0.25, 96), rng2.uniform(0.6, 2.0, 96)], axis=1)
+        x1 = (Kl @ Xs.T).T
+        x1 = x1[:, :2] / x1[:, 2:]
+        X2 = Xs @ T_21[:3, :3].T + T_21[:3, 3]
+        x2 = (Kl @ X2.T).T
+        x2 = x2[:, :2] / x2[:, 2:]
+        x1 = x1 + rng2.normal(0, sigma, x1.shape)
+        x2 = x2 + rng2.normal(0, sigma, x2.shape)
+        c1, c2 = cv2.correctMatches(Fm, x1[None], x2[None])
+        Fs.append(Fm); ls.append(x1); rs.append(x2); cls_.append(c1[0]); crs.append(c2[0])
+    out['hs_F'] = np.stack(Fs)
+    out['hs_left'] = np.stack(ls)
+    out['hs_right'] = np.stack(rs)
+    out['hs_corrected_left'] = np.stack(cls_)
+    out['hs_corrected_right'] = np.stack(crs)
+    # StereoCamera.triangulate at the reference test's small scale with 0.5 px noise (SURVEY 8a A13:
+    # plain DLT is 1.8e-3 relative away from it there)
+    small = camera_utils.StereoCamera(left.scale(180 / 720), right.scale(180 / 720), stereo.T_RL)
+    Xs = np.stack([rng2.uniform(-0.3, 0.3, 64), rng2.uniform(-0.15, 0.15, 64), rng2.uniform(0.5, 1.5, 64)], axis=1)
+    sl = small.left_camera.project(Xs, np.eye(4)) + rng2.normal(0, 0.5, (64, 2))
+    sr = small.right_camera.project(Xs, stereo.T_RL) + rng2.normal(0, 0.5, (64, 2))
+    out['small_pairs_left'] = sl
+    out['small_pairs_right'] = sr
+    out['small_pairs_stereo_triangulate'] = small.triangulate(sl, sr)
     return out
 
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref, camera_utils, video = ref_import.load()
+    if '--only-geometry' in sys.argv:
+        save('geometry.npz', **geometry_case(camera_utils))
+        return
 
     # 1-2: model-resolution clean sets (bit-exact parity)
     valve = synthetic.make_batch(48, [1, 3], (64, 64), seed=1001, objects=(1, 2))

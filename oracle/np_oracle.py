@@ -391,3 +391,115 @@ def triangulate_robust(obs, valid, poses, cam, K, max_error_px=2.0, max_rounds=N
             mask[p, worst] = False
             dropped[p] += 1
     return X, mask.astype(np.uint8), err, dropped
+
+
+# ------------------------------------------------------------------------------------------
+# A13: cv2.correctMatches as camera_utils.py:100-101 calls it -- Hartley-Sturm optimal
+# correction (Hartley & Zisserman Alg. 12.1; OpenCV 4.13 modules/calib3d/src/triangulate.cpp,
+# a dependency absent from /root/reference, restated from its published algorithm). Pinned
+# against cv2 itself by tests/golden/geometry.npz (pairs_corrected_*, pairs_stereo_triangulate).
+# ------------------------------------------------------------------------------------------
+def correct_matches(F, left, right):
+    """left/right [n,2] float64 undistorted pixels with right^T F left = 0 -> corrected pairs."""
+    F = np.asarray(F, dtype=np.float64)
+    left = np.asarray(left, dtype=np.float64)
+    right = np.asarray(right, dtype=np.float64)
+    out_l = np.zeros_like(left)
+    out_r = np.zeros_like(right)
+    for p in range(left.shape[0]):
+        x1, y1 = left[p]
+        x2, y2 = right[p]
+        T1 = np.array([[1, 0, x1], [0, 1, y1], [0, 0, 1.0]])
+        T2 = np.array([[1, 0, x2], [0, 1, y2], [0, 0, 1.0]])
+        Ft = T2.T @ F @ T1
+        U, _, Vt = np.linalg.svd(Ft)
+        e1 = Vt[2] / np.hypot(Vt[2, 0], Vt[2, 1])
+        e2 = U[:, 2] / np.hypot(U[0, 2], U[1, 2])
+        R1 = np.array([[e1[0], e1[1], 0], [-e1[1], e1[0], 0], [0, 0, 1.0]])
+        R2 = np.array([[e2[0], e2[1], 0], [-e2[1], e2[0], 0], [0, 0, 1.0]])
+        Fp = R2 @ Ft @ R1.T
+        f1, f2, a, b, c, d = e1[2], e2[2], Fp[1, 1], Fp[1, 2], Fp[2, 1], Fp[2, 2]
+        # g(t) = t((at+b)^2 + f2^2 (ct+d)^2)^2 - (ad-bc)(1+f1^2 t^2)^2 (at+b)(ct+d)
+        t = np.polynomial.Polynomial([0.0, 1.0])
+        q = (a * t + b) ** 2 + f2 ** 2 * (c * t + d) ** 2
+        g = t * q * q - (a * d - b * c) * (1 + f1 ** 2 * t ** 2) ** 2 * (a * t + b) * (c * t + d)
+        roots = g.roots()
+
+        def cost(tv):
+            return tv * tv / (1 + f1 * f1 * tv * tv) + (c * tv + d) ** 2 / ((a * tv + b) ** 2 + f2 * f2 * (c * tv + d) ** 2)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            best_s = 1.0 / (f1 * f1) + c * c / (a * a + f2 * f2 * c * c)     # t = infinity
+        best_t = None
+        for r in roots:
+            s = cost(float(np.real(r)))
+            if s < best_s:
+                best_s, best_t = s, float(np.real(r))
+        if best_t is None:
+            l1 = np.array([f1, 0.0, f1 * f1])
+            l2 = np.array([f2 * c * c, -a * c, f2 * f2 * c * c + a * a])
+        else:
+            tv = best_t
+            l1 = np.array([tv * tv * f1, tv, tv * tv * f1 * f1 + 1])
+            l2 = np.array([f2 * (c * tv + d) ** 2, -(a * tv + b) * (c * tv + d),
+                           f2 * f2 * (c * tv + d) ** 2 + (a * tv + b) ** 2])
+        n1 = T1 @ R1.T @ (l1 / l1[2])
+        n2 = T2 @ R2.T @ (l2 / l2[2])
+        out_l[p] = n1[:2] / n1[2]
+        out_r[p] = n2[:2] / n2[2]
+    return out_l, out_r
+
+
+def triangulate_stereo(left_px, right_px, cam_left, cam_right, K_left, K_right, T_RL, F, optimal_correction=True):
+    """StereoCamera.triangulate (camera_utils.py:92-110): float32 cast, undistort (float32 results),
+    correctMatches (float32 results), cv2.triangulatePoints, dehomogenise."""
+    l32 = np.asarray(left_px).astype(np.float32).astype(np.float64)
+    r32 = np.asarray(right_px).astype(np.float32).astype(np.float64)
+    uL = np.array([undistort_point(u, v, cam_left) for u, v in l32]).astype(np.float32).astype(np.float64)
+    uR = np.array([undistort_point(u, v, cam_right) for u, v in r32]).astype(np.float32).astype(np.float64)
+    if optimal_correction:
+        uL, uR = correct_matches(F, uL, uR)
+        uL = uL.astype(np.float32).astype(np.float64)
+        uR = uR.astype(np.float32).astype(np.float64)
+    P1 = np.asarray(K_left) @ np.eye(3, 4)
+    P2 = np.asarray(K_right) @ np.asarray(T_RL)[:3]
+    pts = np.stack([uL, uR], axis=1)
+    return triangulate_dlt(pts, np.ones(pts.shape[:2], bool), np.stack([P1, P2]))
+
+
+# ------------------------------------------------------------------------------------------
+# Stereo association -- PARITY UNPINNED: the implementation was removed from the reference, only
+# its expectations survive (test/test_pipeline.py:208-261: index of the matching right point, -1 for
+# unmatched, one-to-one). Statement of record for okp_stereo_associate_f64.
+# ------------------------------------------------------------------------------------------
+def associate(F, left, right, max_distance_px=2.5):
+    """left [nL,2], right [nR,2] UNDISTORTED pixels -> (match [nL] int32, cost [nL])."""
+    F = np.asarray(F, dtype=np.float64)
+    left = np.asarray(left, dtype=np.float64).reshape(-1, 2)
+    right = np.asarray(right, dtype=np.float64).reshape(-1, 2)
+    nl, nr = left.shape[0], right.shape[0]
+    cost = np.zeros((nl, nr))
+    for i in range(nl):
+        x, y = left[i]
+        l0 = F[0, 0] * x + F[0, 1] * y + F[0, 2]
+        l1 = F[1, 0] * x + F[1, 1] * y + F[1, 2]
+        l2 = F[2, 0] * x + F[2, 1] * y + F[2, 2]
+        for j in range(nr):
+            xp, yp = right[j]
+            m0 = F[0, 0] * xp + F[1, 0] * yp + F[2, 0]
+            m1 = F[0, 1] * xp + F[1, 1] * yp + F[2, 1]
+            r = abs(xp * l0 + yp * l1 + l2)
+            cost[i, j] = 0.5 * (r / np.sqrt(l0 * l0 + l1 * l1) + r / np.sqrt(m0 * m0 + m1 * m1))
+    match = np.full(nl, -1, np.int32)
+    match_cost = np.zeros(nl)
+    free = np.ones((nl, nr), bool)
+    for _ in range(min(nl, nr)):
+        masked = np.where(free, cost, np.inf)
+        e = int(np.argmin(masked))                 # first minimum in (left, right) raster order
+        i, j = divmod(e, nr)
+        if not (masked[i, j] <= max_distance_px):
+            break
+        match[i] = j
+        match_cost[i] = masked[i, j]
+        free[i, :] = False
+        free[:, j] = False
+    return match, match_cost

@@ -126,3 +126,98 @@ def test_stereo_pipeline_end_to_end_like_reference_test():
         assert X.shape == (count, 3)
     X0 = triangulation(np.stack(keypoints[0][0]), np.stack(keypoints[1][0]))
     assert np.linalg.norm(X0[0] - g['keypoints_3d'][0]) < 5e-2
+
+
+def test_correct_matches_is_cv2_and_the_oracle():
+    """A13: okp_correct_matches_f64 against cv2.correctMatches goldens (rig, forward motion, general
+    pose) and the NumPy restatement."""
+    from object_keypoints_b200 import correct_matches
+    from oracle import np_oracle
+    g = load_golden('geometry.npz')
+    cases = [(g['F'], g['pairs_undistorted_left'], g['pairs_undistorted_right'],
+              g['pairs_corrected_left'], g['pairs_corrected_right'])]
+    cases += [(g['hs_F'][i], g['hs_left'][i], g['hs_right'][i], g['hs_corrected_left'][i], g['hs_corrected_right'][i])
+              for i in range(g['hs_F'].shape[0])]
+    for F, l, r, want_l, want_r in cases:
+        got_l, got_r = correct_matches(F, l, r)
+        got_l, got_r = got_l.cpu().numpy(), got_r.cpu().numpy()
+        assert np.abs(got_l - want_l).max() < 1e-7 and np.abs(got_r - want_r).max() < 1e-7
+        ol, orr = np_oracle.correct_matches(F, l, r)
+        assert np.abs(got_l - ol).max() < 1e-7 and np.abs(got_r - orr).max() < 1e-7
+    # degenerate inputs: pairs already on their epipolar lines stay where they are
+    got_l, got_r = correct_matches(g['F'], g['pairs_corrected_left'], g['pairs_corrected_right'])
+    assert np.abs(got_l.cpu().numpy() - g['pairs_corrected_left']).max() < 1e-6
+    empty_l, empty_r = correct_matches(g['F'], np.zeros((0, 2)), np.zeros((0, 2)))
+    assert empty_l.shape == (0, 2) and empty_r.shape == (0, 2)
+
+
+def test_stereo_triangulate_with_correction_matches_the_reference():
+    """StereoCamera.triangulate (camera_utils.py:92-110) of the unmodified reference on noisy pairs,
+    <= 1e-4 relative (north_star), at full and at test scale."""
+    from object_keypoints_b200 import camera_utils
+    g = load_golden('geometry.npz')
+    left, right = cameras(g)
+    for scale, lp, rp, want in ((1.0, g['pairs_left'], g['pairs_right'], g['pairs_stereo_triangulate']),
+                                (180 / 720, g['small_pairs_left'], g['small_pairs_right'],
+                                 g['small_pairs_stereo_triangulate'])):
+        stereo = camera_utils.StereoCamera(left.scale(scale), right.scale(scale), g['T_RL']) if scale != 1.0 else \
+            camera_utils.StereoCamera(left, right, g['T_RL'])
+        got = stereo.triangulate(lp, rp)
+        rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert rel.max() <= TOL_METRES_REL
+        plain = stereo.triangulate(lp, rp, optimal_correction=False)
+        assert (np.linalg.norm(plain - want, axis=1) / np.linalg.norm(want, axis=1)).max() > rel.max()
+
+
+def test_association_component_meets_reference_test_expectations():
+    """test/test_pipeline.py:208-261 (AssociationComponent) and the oracle, batched and single."""
+    from object_keypoints_b200 import AssociationComponent, associate, camera_utils, undistort_points
+    from oracle import np_oracle
+    g = load_golden('geometry.npz')
+    left, right = cameras(g)
+    stereo = camera_utils.StereoCamera(left.scale(0.25), right.scale(0.25), g['T_RL'])
+    keypoints_X = np.array([[0.0, 0.0, 1.0], [0.0, 0.25, 1.0], [0.0, -0.25, 1.0]])
+    points_left = stereo.left_camera.project(keypoints_X, np.eye(4))
+    points_right = stereo.right_camera.project(keypoints_X, stereo.T_RL)
+    association = AssociationComponent()
+    association.reset(stereo)
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        shuffled = points_right[rng.permutation(3)]
+        associations = association(points_left, shuffled)
+        assert (associations != -1).all()
+        np.testing.assert_equal(points_right, shuffled[associations])
+    two_left = np.array([[160.251929, 92.04110211], [160.251929, 135.25386897], [160.251929, 48.82833525]])
+    two_right = np.array([[149.9327, 139.14128], [149.93279695, 133.14128143], [149.88808034, 47.08818382]])
+    np.testing.assert_array_equal(association(two_left, two_right), [-1, 1, 2])
+    # the 64x64 cameras of test_association_tricky: every left point gets its own right point
+    K = np.array([[62.31692844, 0., 31.92640056], [0., 62.38274914, 32.92623658], [0., 0., 1.]])
+    Kp = np.array([[62.07155716, 0., 31.79527486], [0., 62.14031698, 32.54056898], [0., 0., 1.]])
+    D = np.array([-1.73678913e-01, 2.69084607e-02, -2.66312740e-04, -1.11094300e-04])
+    Dp = np.array([-0.17596905, 0.02856535, -0.00036341, -0.00021308])
+    tiny = camera_utils.StereoCamera(camera_utils.FisheyeCamera(K, D, [64, 64]), camera_utils.FisheyeCamera(Kp, Dp, [64, 64]),
+                                     g['T_RL'])
+    association.reset(tiny)
+    tricky = association(np.array([[35.5, 25.5], [26.5, 39.5], [38.5, 39.5]]),
+                         np.array([[29.5, 25.5], [20.5, 38.5], [33.5, 39.5]]))
+    assert tricky.shape[0] == 3 and np.unique(tricky).size == 3 and (tricky >= 0).all()
+    assert association(np.zeros((0, 2)), two_right).shape == (0,)
+    np.testing.assert_array_equal(association(two_left, np.zeros((0, 2))), [-1, -1, -1])
+    # batched, ragged, random: bit-equal to the oracle
+    B, ML, MR = 37, 9, 7
+    L = np.zeros((B, ML, 2))
+    R = np.zeros((B, MR, 2))
+    nl = rng.integers(0, ML + 1, B).astype(np.int32)
+    nr = rng.integers(0, MR + 1, B).astype(np.int32)
+    for b in range(B):
+        X = np.stack([rng.uniform(-0.3, 0.3, ML), rng.uniform(-0.2, 0.2, ML), rng.uniform(0.5, 1.5, ML)], axis=1)
+        L[b] = stereo.left_camera.undistort(stereo.left_camera.project(X, np.eye(4)) + rng.normal(0, 0.3, (ML, 2)))
+        Rp = stereo.right_camera.undistort(stereo.right_camera.project(X, stereo.T_RL) + rng.normal(0, 0.3, (ML, 2)))
+        R[b] = Rp[rng.permutation(ML)[:MR]]
+    match, cost = associate(stereo.F, L, R, nl, nr, max_distance_px=1.0)
+    match, cost = match.cpu().numpy(), cost.cpu().numpy()
+    for b in range(B):
+        want_m, want_c = np_oracle.associate(stereo.F, L[b, :nl[b]], R[b, :nr[b]], max_distance_px=1.0)
+        np.testing.assert_array_equal(match[b, :nl[b]], want_m)
+        assert (match[b, nl[b]:] == -1).all()
+        np.testing.assert_allclose(cost[b, :nl[b]], want_c, rtol=0, atol=1e-9)

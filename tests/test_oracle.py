@@ -163,3 +163,69 @@ def test_robust_multiview_oracles_agree_and_recover_points():
     proj = np.stack([camera.K @ poses[v][:3] for v in range(V)])
     plain = c_oracle.triangulate(und, inside, proj)
     assert (np.linalg.norm(Xq - plain, axis=1) <= 1e-9 * np.linalg.norm(plain, axis=1) + 1e-12).all()
+
+
+def _stereo_from_golden(g, scale=None):
+    from object_keypoints_b200 import camera_utils
+    left = camera_utils.FisheyeCamera(g['K_left'], g['D_left'], [720, 1280])
+    right = camera_utils.FisheyeCamera(g['K_right'], g['D_right'], [720, 1280])
+    if scale is not None:
+        left, right = left.scale(scale), right.scale(scale)
+    return camera_utils.StereoCamera(left, right, g['T_RL'])
+
+
+def test_hartley_sturm_restatement_is_cv2_correct_matches():
+    """A13 pinned: np_oracle.correct_matches against cv2.correctMatches outputs (rig F, forward
+    motion, general pose) stored by oracle/make_goldens.py."""
+    g = load_golden('geometry.npz')
+    l, r = np_oracle.correct_matches(g['F'], g['pairs_undistorted_left'], g['pairs_undistorted_right'])
+    assert np.abs(l - g['pairs_corrected_left']).max() < 1e-9
+    assert np.abs(r - g['pairs_corrected_right']).max() < 1e-9
+    for i in range(g['hs_F'].shape[0]):
+        l, r = np_oracle.correct_matches(g['hs_F'][i], g['hs_left'][i], g['hs_right'][i])
+        assert np.abs(l - g['hs_corrected_left'][i]).max() < 1e-9
+        assert np.abs(r - g['hs_corrected_right'][i]).max() < 1e-9
+        # the corrected pairs satisfy the epipolar constraint
+        h = lambda x: np.concatenate([x, np.ones((len(x), 1))], axis=1)
+        resid = np.einsum('ni,ij,nj->n', h(r), g['hs_F'][i], h(l)) / np.abs(g['hs_F'][i]).max()
+        assert np.abs(resid).max() < 1e-6
+
+
+def test_stereo_triangulate_restatement_is_the_reference():
+    """StereoCamera.triangulate of the unmodified reference (float32 casts, correctMatches, DLT) on
+    noisy pairs at full and at test scale; the plain DLT is measurably different."""
+    g = load_golden('geometry.npz')
+    for scale, left_px, right_px, want in ((None, g['pairs_left'], g['pairs_right'], g['pairs_stereo_triangulate']),
+                                           (180 / 720, g['small_pairs_left'], g['small_pairs_right'],
+                                            g['small_pairs_stereo_triangulate'])):
+        stereo = _stereo_from_golden(g, scale)
+        args = (left_px, right_px, np_oracle.camera_dict(stereo.left_camera), np_oracle.camera_dict(stereo.right_camera),
+                stereo.left_camera.K, stereo.right_camera.K, stereo.T_RL, stereo.F)
+        got = np_oracle.triangulate_stereo(*args)
+        rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert np.median(rel) < 1e-6 and rel.max() < 1e-4       # float32 roundings of undistort/correct outputs
+        plain = np_oracle.triangulate_stereo(*args, optimal_correction=False)
+        rel_plain = np.linalg.norm(plain - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert rel_plain.max() > 10 * rel.max()
+
+
+def test_association_oracle_meets_reference_test_expectations():
+    """test/test_pipeline.py:208-261 restated with consistent camera scales."""
+    g = load_golden('geometry.npz')
+    stereo = _stereo_from_golden(g, 0.25)
+    keypoints_X = np.array([[0.0, 0.0, 1.0], [0.0, 0.25, 1.0], [0.0, -0.25, 1.0]])
+    pl = stereo.left_camera.project(keypoints_X, np.eye(4))
+    pr = stereo.right_camera.project(keypoints_X, stereo.T_RL)
+    uL, uR = stereo.left_camera.undistort(pl), stereo.right_camera.undistort(pr)
+    rng = np.random.default_rng(3)
+    for _ in range(5):                                    # test_association_simple
+        perm = rng.permutation(3)
+        match, _ = np_oracle.associate(stereo.F, uL, uR[perm])
+        assert (match != -1).all()
+        np.testing.assert_array_equal(uR, uR[perm][match])
+    # test_association_two_same: left 0 has no partner, the other two share one image column
+    points_left = np.array([[160.251929, 92.04110211], [160.251929, 135.25386897], [160.251929, 48.82833525]])
+    points_right = np.array([[149.9327, 139.14128], [149.93279695, 133.14128143], [149.88808034, 47.08818382]])
+    match, _ = np_oracle.associate(stereo.F, stereo.left_camera.undistort(points_left),
+                                   stereo.right_camera.undistort(points_right))
+    np.testing.assert_array_equal(match, [-1, 1, 2])
