@@ -105,7 +105,7 @@ typedef struct OkpDecodeTables {
 int okp_version(void);
 const char* okp_strerror(int code);
 
-/* Scratch bytes okp_decode_f32 / okp_extract_peaks_f32 need for this problem size. */
+/* Scratch bytes okp_decode_* / okp_extract_peaks_* need for this problem size (either element type). */
 size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodeParams* params);
 
 /* Replaces KeypointExtractionComponent.__call__ (perception/pipeline.py:64-91) including
@@ -140,6 +140,24 @@ int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* c
                    const OkpCamera* camera, const OkpDecodeParams* params,
                    const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
                    void* stream);
+
+/* bfloat16 forms of the three decode entries, for network heads that write bf16 (BASELINE config 5:
+ * the reference's InferenceComponent, pipeline.py:13-28, hands over whatever dtype the TorchScript
+ * model produces; package_model.py:28 applies the sigmoid inside the model). All three maps are bf16
+ * [same shapes as the _f32 forms]; bf16 -> float32 is exact and every sum, comparison and centroid is
+ * computed in float32 exactly as in the _f32 forms, so the tables equal those of the _f32 entry run on
+ * the up-cast maps bit for bit. The TMA path needs W % 8 == 0; other widths take the generic kernels. */
+int okp_extract_peaks_bf16(const void* heat_dev, int N, int C, int H, int W,
+                           const OkpDecodeParams* params, const OkpDecodeTables* tables,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+int okp_group_objects_bf16(const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
+                           const int32_t* keypoint_config, const OkpCamera* camera,
+                           const OkpDecodeParams* params, const OkpDecodeTables* tables, void* stream);
+int okp_decode_bf16(const void* heat_dev, const void* depth_dev, const void* centers_dev,
+                    int N, int C, int H, int W, const int32_t* keypoint_config,
+                    const OkpCamera* camera, const OkpDecodeParams* params,
+                    const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
+                    void* stream);
 
 /* Replaces FisheyeCamera.undistort (camera_utils.py:75-81, cv2.fisheye.undistortPoints with
  * P = K). xy_dev/out_dev: [n,2] float64. round_to_f32 != 0 reproduces OpenCV's float32 output

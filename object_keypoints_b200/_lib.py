@@ -17,6 +17,7 @@ EXPORTS = [
     'okp_group_objects_f32', 'okp_decode_f32', 'okp_fisheye_undistort_f64', 'okp_fisheye_project_f64',
     'okp_detection_to_point_f32', 'okp_triangulate_f64', 'okp_reprojection_filter_f64',
     'okp_triangulate_robust_f64', 'okp_host_alias', 'okp_correct_matches_f64', 'okp_stereo_associate_f64',
+    'okp_extract_peaks_bf16', 'okp_group_objects_bf16', 'okp_decode_bf16',
 ]
 
 
@@ -75,6 +76,12 @@ def lib():
     L.okp_decode_f32.restype = i32
     L.okp_decode_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, P(ctypes.c_int32), P(_abi.OkpCamera),
                                  P(_abi.OkpDecodeParams), P(_abi.OkpDecodeTables), vp, sz, vp]
+    for suffix in ('f32', 'bf16'):
+        extract, group, decode = (getattr(L, f'okp_{stem}_{suffix}') for stem in ('extract_peaks', 'group_objects', 'decode'))
+        extract.restype = group.restype = decode.restype = i32
+        extract.argtypes = L.okp_extract_peaks_f32.argtypes
+        group.argtypes = L.okp_group_objects_f32.argtypes
+        decode.argtypes = L.okp_decode_f32.argtypes
     L.okp_host_alias.restype = i32
     L.okp_host_alias.argtypes = [vp, P(vp)]
     L.okp_fisheye_undistort_f64.restype = i32

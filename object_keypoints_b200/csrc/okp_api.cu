@@ -27,10 +27,10 @@ struct PeakPlan {
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-PeakPlan plan_peaks(int maps, int H, int W, int K) {
+PeakPlan plan_peaks(int maps, int H, int W, int K, int esize) {
     PeakPlan p;
     memset(&p, 0, sizeof(p));
-    p.strip = okp_strip_plan(maps, H, W, K, &p.sp);
+    p.strip = okp_strip_plan(maps, H, W, K, esize, &p.sp);
     p.geo.H = H; p.geo.W = W; p.geo.maps = maps;
     p.geo.TW = W <= 64 ? round_up(W, 8) : 64;
     p.geo.TH = H <= 64 ? H : 32;
@@ -93,12 +93,23 @@ const char* okp_strerror(int code) {
 size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodeParams* params) {
     if (check_params(params) != OKP_OK || check_shape(N, C, H, W) != OKP_OK) return 0;
     if (N == 0) return 256;
-    const PeakPlan p = plan_peaks(N * C, H, W, params->max_peaks);
-    return workspace_for(p, N * C, params->max_peaks, p.strip);
+    // enough for either element type (their launch plans can differ: bf16 rows need W % 8 == 0 for TMA)
+    size_t need = 0;
+    for (int esize = 2; esize <= 4; esize += 2) {
+        const PeakPlan p = plan_peaks(N * C, H, W, params->max_peaks, esize);
+        const size_t bytes = workspace_for(p, N * C, params->max_peaks, p.strip);
+        if (bytes > need) need = bytes;
+    }
+    return need;
 }
 
-int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
-                          const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
+                  const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
     int rc = check_params(params);
     if (rc != OKP_OK) return rc;
     rc = check_shape(N, C, H, W);
@@ -111,7 +122,7 @@ int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, con
     cudaStream_t s = (cudaStream_t)stream;
     const int K = params->max_peaks;
     const int maps = N * C;
-    const PeakPlan p = plan_peaks(maps, H, W, K);
+    const PeakPlan p = plan_peaks(maps, H, W, K, (int)sizeof(T));
     const bool strip = p.strip && ((uintptr_t)heat_dev & 15u) == 0;      // TMA needs a 16-byte aligned base
     if (workspace_bytes < workspace_for(p, maps, K, strip)) return OKP_E_WORKSPACE;
     const size_t tiles = strip ? (size_t)overflow_grid(maps) * p.tiles_per_map : (size_t)maps * p.tiles_per_map;
@@ -120,17 +131,17 @@ int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, con
     OkpPeakRecord* tile_peaks = (OkpPeakRecord*)(base + align_up(tiles * sizeof(int32_t), 256));
 
     if (strip) {
-        rc = okp_strip_launch(heat_dev, p.sp, params->threshold, *tables, s);
+        rc = okp_strip_launch<T>(heat_dev, p.sp, params->threshold, *tables, s);
         if (rc != OKP_OK) return rc;
         // maps with more than K peaks ("first K in raster order") are redone here; a no-op otherwise
-        auto kernel = okp_peaks_overflow_kernel<256>;
+        auto kernel = okp_peaks_overflow_kernel<256, T>;
         OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
         kernel<<<overflow_grid(maps), 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks, *tables);
         OKP_CUDA_CHECK(cudaGetLastError());
         return OKP_OK;
     }
     {
-        auto kernel = okp_peaks_generic_kernel<256>;
+        auto kernel = okp_peaks_generic_kernel<256, T>;
         OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
         kernel<<<p.grid, 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks);
         OKP_CUDA_CHECK(cudaGetLastError());
@@ -142,9 +153,10 @@ int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, con
     return OKP_OK;
 }
 
-int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
-                          const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
-                          const OkpDecodeTables* tables, void* stream) {
+template <typename T>
+int group_objects(const T* depth_dev, const T* centers_dev, int N, int C, int H, int W,
+                  const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                  const OkpDecodeTables* tables, void* stream) {
     int rc = check_params(params);
     if (rc != OKP_OK) return rc;
     rc = check_shape(N, C, H, W);
@@ -167,10 +179,38 @@ int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int 
     OkpCamera cam;
     memset(&cam, 0, sizeof(cam));
     if (camera) cam = *camera;
-    okp_group_kernel<128><<<N, 128, 0, (cudaStream_t)stream>>>(depth_dev, centers_dev, N, C, H, W, config, cam,
-                                                               camera != nullptr, *params, S, *tables);
+    okp_group_kernel<128, T><<<N, 128, 0, (cudaStream_t)stream>>>(depth_dev, centers_dev, N, C, H, W, config, cam,
+                                                                  camera != nullptr, *params, S, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
+                          const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return extract_peaks<float>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
+}
+
+int okp_extract_peaks_bf16(const void* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
+                           const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return extract_peaks<__nv_bfloat16>((const __nv_bfloat16*)heat_dev, N, C, H, W, params, tables, workspace_dev,
+                                        workspace_bytes, stream);
+}
+
+int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
+                          const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                          const OkpDecodeTables* tables, void* stream) {
+    return group_objects<float>(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, stream);
+}
+
+int okp_group_objects_bf16(const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
+                           const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                           const OkpDecodeTables* tables, void* stream) {
+    return group_objects<__nv_bfloat16>((const __nv_bfloat16*)depth_dev, (const __nv_bfloat16*)centers_dev, N, C, H, W,
+                                        keypoint_config, camera, params, tables, stream);
 }
 
 int okp_host_alias(const void* host_ptr, void** dev_ptr_out) {
@@ -191,6 +231,14 @@ int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* c
     int rc = okp_extract_peaks_f32(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
     if (rc != OKP_OK) return rc;
     return okp_group_objects_f32(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, stream);
+}
+
+int okp_decode_bf16(const void* heat_dev, const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
+                    const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                    const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    int rc = okp_extract_peaks_bf16(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
+    if (rc != OKP_OK) return rc;
+    return okp_group_objects_bf16(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, stream);
 }
 
 int okp_fisheye_undistort_f64(const double* xy_dev, int n, const OkpCamera* camera, int round_to_f32,

@@ -54,7 +54,8 @@ __device__ __forceinline__ void okp_project_point(const double* X, const double*
     *ov = cam.fy * (b * s) + cam.cy;
 }
 
-__device__ __forceinline__ void okp_detection_to_point(float x, float y, const float* __restrict__ depth_map,
+template <typename T>
+__device__ __forceinline__ void okp_detection_to_point(float x, float y, const T* __restrict__ depth_map,
                                                        int H, int W, const OkpCamera& cam, int compat_clip_bug,
                                                        double* out) {
     double du, dv;
@@ -67,7 +68,7 @@ __device__ __forceinline__ void okp_detection_to_point(float x, float y, const f
     }
     xi = okp_clamp(xi, 0, W - 1);                     // the reference would raise IndexError here
     yi = okp_clamp(yi, 0, H - 1);
-    const double z = (double)__ldg(depth_map + (size_t)yi * W + xi);
+    const double z = (double)okp_ld<T>(depth_map + (size_t)yi * W + xi);
     const double hx = (double)ux, hy = (double)uy;
 #pragma unroll
     for (int r = 0; r < 3; ++r) out[r] = (cam.kinv[3 * r] * hx + cam.kinv[3 * r + 1] * hy + cam.kinv[3 * r + 2]) * z;

@@ -78,9 +78,9 @@ __device__ __noinline__ void okp_cluster_detections(const float* __restrict__ xy
 #undef OKP_PT
 }
 
-template <int THREADS>
+template <int THREADS, typename E>
 __global__ void __launch_bounds__(THREADS)
-okp_group_kernel(const float* __restrict__ depth, const float* __restrict__ centers, int N, int C, int H, int W,
+okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int N, int C, int H, int W,
                  OkpConfig config, OkpCamera cam, int have_camera, OkpDecodeParams prm, int S, OkpDecodeTables t) {
     const int n = blockIdx.x;
     if (n >= N) return;
@@ -135,9 +135,9 @@ okp_group_kernel(const float* __restrict__ depth, const float* __restrict__ cent
         const float px = t.peak_xy[2 * s], py = t.peak_xy[2 * s + 1];
         const int xi = okp_clamp(__float2int_rn(px), 0, W - 1);      // np.round = half to even
         const int yi = okp_clamp(__float2int_rn(py), 0, H - 1);
-        const float* cmap = centers + ((size_t)n * T + (c - 1)) * 2 * HW;
-        const double vx = ((double)xi + 0.5) + (double)__ldg(cmap + (size_t)yi * W + xi);
-        const double vy = ((double)yi + 0.5) + (double)__ldg(cmap + HW + (size_t)yi * W + xi);
+        const E* cmap = centers + ((size_t)n * T + (c - 1)) * 2 * HW;
+        const double vx = ((double)xi + 0.5) + (double)okp_ld<E>(cmap + (size_t)yi * W + xi);
+        const double vy = ((double)yi + 0.5) + (double)okp_ld<E>(cmap + HW + (size_t)yi * W + xi);
         t.peak_vote[2 * s] = vx;
         t.peak_vote[2 * s + 1] = vy;
         int arg = 0;

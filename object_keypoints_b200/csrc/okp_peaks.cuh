@@ -44,8 +44,8 @@ __device__ __forceinline__ void okp_centroid_from_smem(const float* raw, int pit
 }
 
 // Processes one (map, tile) work item with the whole CTA; shared memory as laid out by the kernels below.
-template <int THREADS>
-__device__ __forceinline__ void okp_generic_tile(const float* __restrict__ heat, const OkpTileGeometry& g, float threshold,
+template <int THREADS, typename T>
+__device__ __forceinline__ void okp_generic_tile(const T* __restrict__ heat, const OkpTileGeometry& g, float threshold,
                                                  int K, long long work, long long out_index,
                                                  int32_t* __restrict__ tile_count,
                                                  OkpPeakRecord* __restrict__ tile_peaks, unsigned char* smem_raw,
@@ -63,14 +63,14 @@ __device__ __forceinline__ void okp_generic_tile(const float* __restrict__ heat,
         const int tile = (int)(work - (long long)map * tiles_per_map);
         const int ty0 = (tile / g.tiles_x) * g.TH;
         const int tx0 = (tile % g.tiles_x) * g.TW;
-        const float* src = heat + (size_t)map * g.H * g.W;
+        const T* src = heat + (size_t)map * g.H * g.W;
         if (threadIdx.x == 0) s_count = 0;
         // ---- stage the tile + 4 px halo, zero outside the image (conv2d zero padding) ----
         for (int i = threadIdx.x; i < (g.TH + 8) * RP; i += THREADS) {
             const int ry = i / RP, rx = i - ry * RP;
             const int gy = ty0 - 4 + ry, gx = tx0 - 4 + rx;
             float v = 0.0f;
-            if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) v = __ldg(src + (size_t)gy * g.W + gx);
+            if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) v = okp_ld<T>(src + (size_t)gy * g.W + gx);
             raw[i] = v;
         }
         __syncthreads();
@@ -166,15 +166,15 @@ __device__ __forceinline__ void okp_generic_tile(const float* __restrict__ heat,
     }
 }
 
-template <int THREADS>
+template <int THREADS, typename T>
 __global__ void __launch_bounds__(THREADS)
-okp_peaks_generic_kernel(const float* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
+okp_peaks_generic_kernel(const T* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
                          int32_t* __restrict__ tile_count, OkpPeakRecord* __restrict__ tile_peaks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_count;
     const long long work_items = (long long)g.maps * g.tiles_y * g.tiles_x;
     for (long long work = blockIdx.x; work < work_items; work += gridDim.x)
-        okp_generic_tile<THREADS>(heat, g, threshold, K, work, work, tile_count, tile_peaks, smem_raw, &s_count);
+        okp_generic_tile<THREADS, T>(heat, g, threshold, K, work, work, tile_count, tile_peaks, smem_raw, &s_count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,9 +249,9 @@ okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakReco
 // the workspace) and merged by warp 0. With no
 // overflow the kernel is one coalesced read of peak_count.
 // ---------------------------------------------------------------------------------------------
-template <int THREADS>
+template <int THREADS, typename T>
 __global__ void __launch_bounds__(THREADS)
-okp_peaks_overflow_kernel(const float* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
+okp_peaks_overflow_kernel(const T* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
                           int32_t* __restrict__ tile_count, OkpPeakRecord* __restrict__ tile_peaks, OkpDecodeTables t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_count;
@@ -266,7 +266,7 @@ okp_peaks_overflow_kernel(const float* __restrict__ heat, OkpTileGeometry g, flo
             if (!s_over[i]) continue;                     // uniform: shared flag
             const int m = base + i;
             for (int tile = 0; tile < tiles_per_map; ++tile)
-                okp_generic_tile<THREADS>(heat, g, threshold, K, (long long)m * tiles_per_map + tile,
+                okp_generic_tile<THREADS, T>(heat, g, threshold, K, (long long)m * tiles_per_map + tile,
                                           (long long)blockIdx.x * tiles_per_map + tile, tile_count, tile_peaks, smem_raw,
                                           &s_count);
             __threadfence_block();

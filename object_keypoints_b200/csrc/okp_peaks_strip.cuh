@@ -55,7 +55,10 @@ struct OkpStripPlan {
     int strips;                   // W / 4 + 1 (strip s = pixels 4s-2 .. 4s+1)
     int half_strips;              // strips served by TMA box 0 (all of them when halves == 1)
     int halves;                   // 1 or 2 TMA boxes per row (box width <= 256 elements)
-    int BW;                       // box width in floats
+    int BW;                       // box width in elements
+    int esize;                    // bytes per map element: 4 (float32) or 2 (bfloat16)
+    int lead[2];                  // elements between a box's first column and its first strip's column 4s-4
+                                  // (the box start must be 16-byte aligned: 0 for float32, 0 or 4 for bfloat16)
     int M;                        // maps per CTA
     int NS;                       // TMA stages
     int nb;                       // batches
@@ -63,7 +66,7 @@ struct OkpStripPlan {
     int PK;                       // candidate slots per map (2 K)
     int IC;                       // exact-check items per CTA (neighbours the stream could not order)
     int threads;                  // compute threads: M * strips (dense: a warp may hold strips of two maps)
-    int half_bytes;               // bytes of one TMA box: M * RB * BW * 4
+    int half_bytes;               // bytes of one TMA box: M * RB * BW * esize
     int half_stride;              // half_bytes rounded up to 128 (TMA destinations are 128-byte aligned)
     int stage_bytes;              // halves * half_stride
     int off_pending, off_peaks, off_items, off_count, off_mbar;
@@ -113,13 +116,14 @@ __device__ __forceinline__ void okp_tma_load_3d(void* dst, const CUtensorMap* ma
 
 // The reference's box sum at pixel (y, x): 25 additions in raster tap order starting from +0, zero
 // outside the image (perception/pipeline.py:70-71). The loads are independent (one L2 round trip).
-__device__ __forceinline__ float okp_exact_box_sum(const float* __restrict__ src, int H, int W, int y, int x) {
+template <typename T>
+__device__ __forceinline__ float okp_exact_box_sum(const T* __restrict__ src, int H, int W, int y, int x) {
     float q[25];
 #pragma unroll
     for (int k = 0; k < 25; ++k) {
         const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
         const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-        q[k] = in ? __ldg(src + (size_t)i2 * W + j2) : 0.0f;
+        q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;
     }
     float acc = 0.0f;
 #pragma unroll
@@ -215,19 +219,36 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     }
 }
 
+// The eight columns 4s-4 .. 4s+3 of one staged row as float32. float32 maps: two aligned LDS.128.
+// bfloat16 maps: the window is 16 bytes at an 8-byte aligned address (two LDS.64); a bf16 is the upper
+// half of the float32 with the same value, so the conversion is a shift / a mask per element (exact).
+template <typename T> __device__ __forceinline__ void okp_strip_window(const unsigned char* row, float4& lo, float4& hi);
+template <> __device__ __forceinline__ void okp_strip_window<float>(const unsigned char* row, float4& lo, float4& hi) {
+    lo = reinterpret_cast<const float4*>(row)[0];
+    hi = reinterpret_cast<const float4*>(row)[1];
+}
+template <> __device__ __forceinline__ void okp_strip_window<__nv_bfloat16>(const unsigned char* row, float4& lo, float4& hi) {
+    const uint2 a = reinterpret_cast<const uint2*>(row)[0], b = reinterpret_cast<const uint2*>(row)[1];
+    lo.x = __uint_as_float(a.x << 16); lo.y = __uint_as_float(a.x & 0xFFFF0000u);
+    lo.z = __uint_as_float(a.y << 16); lo.w = __uint_as_float(a.y & 0xFFFF0000u);
+    hi.x = __uint_as_float(b.x << 16); hi.y = __uint_as_float(b.x & 0xFFFF0000u);
+    hi.z = __uint_as_float(b.y << 16); hi.w = __uint_as_float(b.y & 0xFFFF0000u);
+}
+
 // One batch of RB rows: the five unrolled steps, rows fetched one step ahead of their use (two register
 // pairs, ping-pong). raw: this thread's window in the stage; y0: the batch's first output row.
-template <bool EDGE>
+template <bool EDGE, typename T>
 __device__ __forceinline__ void okp_strip_batch(const unsigned char* raw, int row_pitch, float (&pr)[5][4], float (&hp)[4],
                                                 float (&sv)[5][4], uint32_t& sign, int y0, const OkpStripLane& L) {
-    float4 a0 = reinterpret_cast<const float4*>(raw)[0], a1 = reinterpret_cast<const float4*>(raw)[1];
-    float4 b0 = reinterpret_cast<const float4*>(raw + row_pitch)[0], b1 = reinterpret_cast<const float4*>(raw + row_pitch)[1];
+    float4 a0, a1, b0, b1;
+    okp_strip_window<T>(raw, a0, a1);
+    okp_strip_window<T>(raw + row_pitch, b0, b1);
     okp_strip_step<0, EDGE>(a0, a1, pr, hp, sv, sign, y0 + 0, L);
-    a0 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 2 * row_pitch)[1];
+    okp_strip_window<T>(raw + 2 * row_pitch, a0, a1);
     okp_strip_step<1, EDGE>(b0, b1, pr, hp, sv, sign, y0 + 1, L);
-    b0 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[0]; b1 = reinterpret_cast<const float4*>(raw + 3 * row_pitch)[1];
+    okp_strip_window<T>(raw + 3 * row_pitch, b0, b1);
     okp_strip_step<2, EDGE>(a0, a1, pr, hp, sv, sign, y0 + 2, L);
-    a0 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[0]; a1 = reinterpret_cast<const float4*>(raw + 4 * row_pitch)[1];
+    okp_strip_window<T>(raw + 4 * row_pitch, a0, a1);
     okp_strip_step<3, EDGE>(b0, b1, pr, hp, sv, sign, y0 + 3, L);
     okp_strip_step<4, EDGE>(a0, a1, pr, hp, sv, sign, y0 + 4, L);
 }
@@ -235,8 +256,9 @@ __device__ __forceinline__ void okp_strip_batch(const unsigned char* raw, int ro
 // Roles. Warps [0, CW) are compute warps (thread = one strip of one map, packed densely); the only thing
 // they ever wait for is TMA data (full[]); after RB rows they arrive on done[]. The last warp is the
 // producer: one lane keeps NS batches of rows in flight.
+template <typename T>
 __global__ void __launch_bounds__(OKP_STRIP_MAX_THREADS, 1)
-okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ heat, OkpStripPlan p,
+okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ heat, OkpStripPlan p,
                        float threshold, float thr_lo, OkpDecodeTables t) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int RB = OKP_STRIP_RB;
@@ -276,8 +298,9 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
                 uint64_t* bar = full + stage;
                 unsigned char* dst = smem + (size_t)stage * p.stage_bytes;
                 okp_mbar_expect_tx(bar, (uint32_t)(p.halves * p.half_bytes));
-                okp_tma_load_3d(dst, tmap_ptr, -4, b * RB - 2, first_map, bar);
-                if (p.halves == 2) okp_tma_load_3d(dst + p.half_stride, tmap_ptr, 4 * p.half_strips - 4, b * RB - 2, first_map, bar);
+                okp_tma_load_3d(dst, tmap_ptr, -4 - p.lead[0], b * RB - 2, first_map, bar);
+                if (p.halves == 2)
+                    okp_tma_load_3d(dst + p.half_stride, tmap_ptr, 4 * p.half_strips - 4 - p.lead[1], b * RB - 2, first_map, bar);
                 if (++stage == NS) { stage = 0; if (b >= NS) parity ^= 1u; }
             }
         }
@@ -298,9 +321,10 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
         if (active && (tid & 31) < 31 && s + 1 < p.strips && tid + 1 < p.threads) L.vmask |= 32u;   // lane + 1 holds strip s + 1
         L.pending = pending + (size_t)mm * p.PK;
         L.n_pending = n_pending + mm;
-        // this thread's window row inside a stage: box [M][RB][BW], first column 4 * (s - half * half_strips)
-        const int thread_raw = half * p.half_stride + (mm * RB * p.BW + 4 * (s - half * p.half_strips)) * 4;
-        const int row_pitch = p.BW * 4;
+        // this thread's window row inside a stage: box [M][RB][BW], first column lead + 4 * (s - half * half_strips)
+        const int thread_raw = half * p.half_stride +
+                               (mm * RB * p.BW + p.lead[half] + 4 * (s - half * p.half_strips)) * (int)sizeof(T);
+        const int row_pitch = p.BW * (int)sizeof(T);
 
         float pr[5][4], hp[4], sv[5][4];
         uint32_t sign = 0;
@@ -319,9 +343,9 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
             const unsigned char* raw = smem + (size_t)stage * p.stage_bytes + thread_raw;
             const int y0 = b * RB - 4;                    // new row of step i is y0 + i + 2, tested row y0 + i - 2
             if (b >= 2 && y0 + 4 < H)                     // rows y0 - 4 .. y0 + 4 all exist
-                okp_strip_batch<false>(raw, row_pitch, pr, hp, sv, sign, y0, L);
+                okp_strip_batch<false, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
             else
-                okp_strip_batch<true>(raw, row_pitch, pr, hp, sv, sign, y0, L);
+                okp_strip_batch<true, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
             __syncwarp();
             if ((tid & 31) == 0) okp_mbar_arrive(done + stage);
             if (++stage == NS) { stage = 0; full_parity ^= 1u; }
@@ -341,13 +365,13 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
         if (first_map + mm < p.maps && j < n_pending[mm]) {
             const OkpStripCandidate cd = pending[i];
             const int y = cd.key / W, x = cd.key - y * W;
-            const float* src = heat + (size_t)(first_map + mm) * H * W;
+            const T* src = heat + (size_t)(first_map + mm) * H * W;
             float q[25];
 #pragma unroll
             for (int k = 0; k < 25; ++k) {
                 const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
                 const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                q[k] = in ? __ldg(src + (size_t)i2 * W + j2) : 0.0f;   // +0 outside: conv2d's zero padding
+                q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;   // +0 outside: conv2d's zero padding
             }
             float sum = 0.0f;
 #pragma unroll
@@ -403,8 +427,8 @@ okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
             const int mm = i / p.PK;
             const int key = pending[i].key;
             const int y = key / W, x = key - y * W;
-            const float* src = heat + (size_t)(first_map + mm) * H * W;
-            if (okp_exact_box_sum(src, H, W, y + k / 5 - 2, x + k % 5 - 2) > peaks[i].score) peaks[i].key = -1;
+            const T* src = heat + (size_t)(first_map + mm) * H * W;
+            if (okp_exact_box_sum<T>(src, H, W, y + k / 5 - 2, x + k % 5 - 2) > peaks[i].score) peaks[i].key = -1;
         }
     }
     __syncthreads();
@@ -462,23 +486,28 @@ static inline int okp_env_int(const char* name, int lo, int hi, int fallback) { 
     return v >= lo && v <= hi ? v : fallback;
 }
 
-static inline bool okp_strip_plan(int maps, int H, int W, int K, OkpStripPlan* out) {
-    if (maps < 1 || H < 1 || W < 4 || (W % 4) != 0 || W > 500) return false;
+static inline bool okp_strip_plan(int maps, int H, int W, int K, int esize, OkpStripPlan* out) {
+    const int align = 16 / esize;                         // elements per 16 bytes: TMA box starts and row pitches
+    if (maps < 1 || H < 1 || W < 4 || (W % 4) != 0 || (W % align) != 0 || W > 500) return false;
     OkpStripPlan p;
     memset(&p, 0, sizeof(p));
-    p.H = H; p.W = W; p.maps = maps; p.K = K;
+    p.H = H; p.W = W; p.maps = maps; p.K = K; p.esize = esize;
     p.strips = W / 4 + 1;
-    if (4 * p.strips + 4 <= 256) {
+    p.lead[0] = align - 4;                                // box 0 starts at column -4 - lead[0] = -align
+    if (4 * p.strips + 4 + p.lead[0] <= 256) {
         p.halves = 1; p.half_strips = p.strips;
     } else {
         p.halves = 2; p.half_strips = (p.strips + 1) / 2;
+        p.lead[1] = (4 * p.half_strips - 4) % align;      // box 1 starts at the aligned column below 4 * half_strips - 4
     }
-    p.BW = 4 * p.half_strips + 4;                         // columns 4s-4 .. 4s+3 of the box's strips
+    // columns 4s-4 .. 4s+3 of the box's strips behind the lead, rounded up to whole 16-byte units
+    p.BW = okp_round_up_int(4 * p.half_strips + 4 + (p.lead[0] > p.lead[1] ? p.lead[0] : p.lead[1]), align);
+    if (p.BW > 256) return false;                         // a TMA box holds at most 256 elements per dimension
     p.nb = (H + 6 + OKP_STRIP_RB - 1) / OKP_STRIP_RB;
     p.NS = okp_env_int("OKP_STRIP_STAGES", 2, OKP_STRIP_MAX_NS, 4);
     p.PK = 2 * K;
     const int items_per_map = 64;
-    const int per_map = p.NS * OKP_STRIP_RB * p.BW * p.halves * 4 +
+    const int per_map = p.NS * OKP_STRIP_RB * p.BW * p.halves * esize +
                         p.PK * (int)(sizeof(OkpStripCandidate) + sizeof(OkpStripPeak)) + items_per_map * 4 + 12;
     const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;   // default: two CTAs per SM
     const int max_threads = okp_env_int("OKP_STRIP_THREADS", 32, OKP_STRIP_MAX_THREADS - 32, 288);
@@ -493,7 +522,7 @@ static inline bool okp_strip_plan(int maps, int H, int W, int K, OkpStripPlan* o
     p.M = M;
     p.threads = M * p.strips;
     p.IC = M * items_per_map;
-    p.half_bytes = M * OKP_STRIP_RB * p.BW * 4;
+    p.half_bytes = M * OKP_STRIP_RB * p.BW * esize;
     p.half_stride = okp_round_up_int(p.half_bytes, 128);
     p.stage_bytes = p.halves * p.half_stride;
     int off = p.NS * p.stage_bytes;
@@ -526,24 +555,26 @@ static inline OkpEncodeTiledFn okp_encode_tiled_fn() {
     return fn;
 }
 
-static inline int okp_strip_launch(const float* heat, const OkpStripPlan& p, float threshold,
+template <typename T>
+static inline int okp_strip_launch(const T* heat, const OkpStripPlan& p, float threshold,
                                    const OkpDecodeTables& tables, cudaStream_t stream) {
     OkpEncodeTiledFn encode = okp_encode_tiled_fn();
     if (!encode) return OKP_E_CUDA;
     if (((uintptr_t)heat & 15u) != 0) return OKP_E_UNSUPPORTED;
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.maps};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(T), (cuuint64_t)p.W * p.H * sizeof(T)};
     const cuuint32_t box[3] = {(cuuint32_t)p.BW, (cuuint32_t)OKP_STRIP_RB, (cuuint32_t)p.M};
     const cuuint32_t elem[3] = {1, 1, 1};
-    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)heat, dims, strides, box, elem,
+    const CUtensorMapDataType dtype = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUresult r = encode(&tmap, dtype, 3, (void*)heat, dims, strides, box, elem,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return OKP_E_CUDA;
-    OKP_CUDA_CHECK(cudaFuncSetAttribute(okp_peaks_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    OKP_CUDA_CHECK(cudaFuncSetAttribute(okp_peaks_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     const int block = (p.threads + 31) / 32 * 32 + 32;     // compute warps + the producer warp
     const float thr_lo = threshold - OKP_STRIP_THRESHOLD_SLACK * fabsf(threshold);
-    okp_peaks_strip_kernel<<<p.grid, block, p.smem_bytes, stream>>>(tmap, heat, p, threshold, thr_lo, tables);
+    okp_peaks_strip_kernel<T><<<p.grid, block, p.smem_bytes, stream>>>(tmap, heat, p, threshold, thr_lo, tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

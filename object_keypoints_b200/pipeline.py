@@ -47,6 +47,16 @@ def _as_device_f32(x, device):
     return x.contiguous()
 
 
+def _as_device_map(x, device):
+    """Like _as_device_f32, but a bfloat16 tensor (a bf16 network head's output) stays bfloat16:
+    the okp_*_bf16 entries read it in place. -> (tensor, 'f32' | 'bf16')."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.bfloat16:
+        if x.device != device:
+            x = x.to(device, non_blocking=True)
+        return x.contiguous(), 'bf16'
+    return _as_device_f32(x, device), 'f32'
+
+
 class DecodeTables:
     """The OkpDecodeTables record as torch tensors on one device (layout: include/okp.h)."""
 
@@ -114,24 +124,26 @@ class KeypointDecoder:
 
     def extract_peaks(self, heat, tables=None, stream=None):
         """K1 only: fills the peak_* tables. Asynchronous on the current (or given) stream."""
-        heat = _as_device_f32(heat, self.device)
+        heat, kind = _as_device_map(heat, self.device)
         self._check(heat)
         N = heat.shape[0]
         tables = self.tables(N) if tables is None else tables
         ws = self._workspace_for(N)
-        rc = self._lib.okp_extract_peaks_f32(heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params),
-                                             ctypes.byref(tables.struct), ws.data_ptr(), ws.numel(),
-                                             _stream_handle(stream))
-        _lib.check(rc, 'okp_extract_peaks_f32')
+        entry = getattr(self._lib, f'okp_extract_peaks_{kind}')
+        rc = entry(heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params),
+                   ctypes.byref(tables.struct), ws.data_ptr(), ws.numel(), _stream_handle(stream))
+        _lib.check(rc, f'okp_extract_peaks_{kind}')
         return tables
 
     def decode_batch(self, heat, depth, centers, tables=None, stream=None):
-        """heat [N,C,H,W], depth [N,C,H,W], centers [N,C-1,2,H,W] (float32; CUDA tensors are used in
-        place, host arrays are copied) -> DecodeTables on the device. No synchronisation."""
-        heat = _as_device_f32(heat, self.device)
+        """heat [N,C,H,W], depth [N,C,H,W], centers [N,C-1,2,H,W] (float32 or bfloat16; CUDA tensors
+        are used in place, host arrays are copied) -> DecodeTables on the device. No synchronisation."""
+        heat, heat_kind = _as_device_map(heat, self.device)
         self._check(heat)
-        depth = _as_device_f32(depth, self.device)
-        centers = _as_device_f32(centers, self.device)
+        depth, depth_kind = _as_device_map(depth, self.device)
+        centers, centers_kind = _as_device_map(centers, self.device)
+        if depth_kind != centers_kind:                       # the grouping entry takes one element type
+            depth, centers, depth_kind = depth.float(), centers.float(), 'f32'
         N = heat.shape[0]
         if tuple(depth.shape) != tuple(heat.shape):
             raise ValueError("depth must have the heatmap's shape")
@@ -140,10 +152,20 @@ class KeypointDecoder:
         tables = self.tables(N) if tables is None else tables
         ws = self._workspace_for(N)
         cam = ctypes.byref(self._camera) if self._camera is not None else None
-        rc = self._lib.okp_decode_f32(heat.data_ptr(), depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W,
-                                      self._cfg_array, cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
-                                      ws.data_ptr(), ws.numel(), _stream_handle(stream))
-        _lib.check(rc, 'okp_decode_f32')
+        if heat_kind == depth_kind:
+            rc = getattr(self._lib, f'okp_decode_{heat_kind}')(
+                heat.data_ptr(), depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array, cam,
+                ctypes.byref(self.params), ctypes.byref(tables.struct), ws.data_ptr(), ws.numel(), _stream_handle(stream))
+            _lib.check(rc, f'okp_decode_{heat_kind}')
+        else:                                                # e.g. bf16 heatmaps with float32 depth / centre maps
+            rc = getattr(self._lib, f'okp_extract_peaks_{heat_kind}')(
+                heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                ws.data_ptr(), ws.numel(), _stream_handle(stream))
+            _lib.check(rc, f'okp_extract_peaks_{heat_kind}')
+            rc = getattr(self._lib, f'okp_group_objects_{depth_kind}')(
+                depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array, cam,
+                ctypes.byref(self.params), ctypes.byref(tables.struct), _stream_handle(stream))
+            _lib.check(rc, f'okp_group_objects_{depth_kind}')
         return tables
 
     HOST_RESULT_TABLES = ('n_objects', 'flags', 'kp_count', 'kp_xy', 'kp_point')
@@ -227,17 +249,19 @@ class KeypointDecoder:
     def group_objects(self, depth, centers, tables, stream=None):
         """K3 + K4 on peak tables that are already filled (ObjectExtraction + DetectionToPoint)."""
         N = tables.N
-        centers = _as_device_f32(centers, self.device)
+        centers, kind = _as_device_map(centers, self.device)
         depth_ptr = None
         cam = None
         if depth is not None and self._camera is not None:
-            depth = _as_device_f32(depth, self.device)
+            depth, depth_kind = _as_device_map(depth, self.device)
+            if depth_kind != kind:
+                depth, centers, kind = depth.float(), centers.float(), 'f32'
             depth_ptr = depth.data_ptr()
             cam = ctypes.byref(self._camera)
-        rc = self._lib.okp_group_objects_f32(depth_ptr, centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array,
-                                             cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
-                                             _stream_handle(stream))
-        _lib.check(rc, 'okp_group_objects_f32')
+        rc = getattr(self._lib, f'okp_group_objects_{kind}')(
+            depth_ptr, centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array, cam, ctypes.byref(self.params),
+            ctypes.byref(tables.struct), _stream_handle(stream))
+        _lib.check(rc, f'okp_group_objects_{kind}')
         return tables
 
 

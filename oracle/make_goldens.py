@@ -385,11 +385,44 @@ def geometry_case(camera_utils):
     return out
 
 
+def producer_frames(seed, frames=1):
+    """Seeded network input the producer fixture and its test both rebuild (not stored: 3 MB per frame)."""
+    return np.random.default_rng(seed).normal(0.0, 1.0, (frames, 3, 511, 511)).astype(np.float32)
+
+
+def producer_case(heatmaps_out=3, seed=21):
+    """The UNMODIFIED reference KeypointNet (perception/models.py:60-91; its hourglass comes from
+    CornerNet_Squeeze.model().hg) with name-derived weights (producer.deterministic_state_dict), float32 on
+    the CPU, deployed forward of scripts/package_model.py:28. KeypointNet opens config files by relative
+    path (models.py:71), hence the chdir."""
+    from object_keypoints_b200 import producer
+    cwd = os.getcwd()
+    os.chdir(ref_import.REFERENCE_ROOT)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            from perception.models import KeypointNet
+            net = KeypointNet((64, 64), heatmaps_out=heatmaps_out).eval()
+    finally:
+        os.chdir(cwd)
+    weights = producer.deterministic_state_dict(net, seed=seed)
+    net.load_state_dict(weights, strict=True)
+    frames = torch.from_numpy(producer_frames(seed))
+    with torch.no_grad():
+        heat, depth, centers = net(frames)
+    names = sorted(weights)
+    return dict(seed=np.int64(seed), heatmaps_out=np.int64(heatmaps_out),
+                heat=torch.sigmoid(heat[-1]).numpy(), depth=depth[-1].numpy(), centers=centers[-1].numpy(),
+                parameter_names=np.array(names), parameter_sizes=np.array([weights[n].numel() for n in names], np.int64))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref, camera_utils, video = ref_import.load()
     if '--only-geometry' in sys.argv:
         save('geometry.npz', **geometry_case(camera_utils))
+        return
+    if '--only-producer' in sys.argv:
+        save('producer_valve.npz', **producer_case())
         return
 
     # 1-2: model-resolution clean sets (bit-exact parity)
@@ -428,6 +461,9 @@ def main():
 
     # 7: camera geometry and triangulation
     save('geometry.npz', **geometry_case(camera_utils))
+
+    # 8: the keypoint network (input producer of BASELINE config 5)
+    save('producer_valve.npz', **producer_case())
 
 
 if __name__ == '__main__':

@@ -313,3 +313,74 @@ def test_host_batch_in_place_gather_equals_device_decode():
             assert decoder.host_bytes_copied == batch.heat.nbytes
         else:
             assert decoder.host_bytes_copied == batch.heat.nbytes + batch.depth.nbytes + batch.centers.nbytes
+
+
+def _bf16_round(a):
+    """float32 array -> (torch bf16 CUDA tensor, the same values as float32 NumPy) -- what a bf16 head emits."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda().to(torch.bfloat16)
+    return t, t.float().cpu().numpy()
+
+
+@pytest.mark.parametrize('cfg,size,frames,objects', [
+    ([1, 3], (64, 64), 96, (1, 2)),          # config 5 shape: the network's output resolution
+    ([1, 1, 1], (64, 64), 64, (1, 4)),
+    ([1, 3], (180, 320), 12, (1, 6)),        # two TMA boxes per row, second box with a 4-element lead
+    ([2], (40, 56), 8, (1, 1)),              # W % 8 == 0, single box
+    ([1, 3], (36, 92), 6, (1, 1)),           # W % 8 != 0: no bf16 tensor map -> generic kernels
+])
+def test_bf16_maps_decode_like_the_upcast_float32_maps(cfg, size, frames, objects):
+    """okp_decode_bf16 (BASELINE config 5: bf16 head outputs stay on the device): bf16 -> f32 is exact,
+    so the tables must be bitwise those of the C oracle run on the up-cast maps."""
+    from oracle import c_oracle
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    layout = {}
+    if size[0] < 64:
+        layout = dict(center_separation=18.0, spoke_radius=(4.0, 6.0), peak_separation=5.0, border=3.0)
+    batch = synthetic.make_batch(frames, cfg, size, seed=3000 + size[1], objects=objects, **layout)
+    camera = synthetic.default_camera(size) if size in ((64, 64), (180, 320)) else \
+        __import__('object_keypoints_b200').camera_utils.FisheyeCamera(
+            np.array([[50.0, 0, size[1] / 2], [0, 50.0, size[0] / 2], [0, 0, 1]]), np.array([0.1, 0.01, -0.02, 0.003]), size)
+    (heat, heat32), (depth, depth32), (centers, centers32) = (_bf16_round(a) for a in (batch.heat, batch.depth, batch.centers))
+    decoder = KeypointDecoder(cfg, size, camera=camera)
+    got = decoder.decode_batch(heat, depth, centers).numpy()
+    assert_matches_oracle(got, c_oracle.decode(heat32, depth32, centers32, cfg, camera))
+    assert got['n_objects'].sum() > 0
+    # mixed: bf16 heatmaps with float32 depth / centre maps (extract and group entries of different types)
+    import torch
+    got = decoder.decode_batch(heat, torch.from_numpy(batch.depth).cuda(), torch.from_numpy(batch.centers).cuda()).numpy()
+    assert_matches_oracle(got, c_oracle.decode(heat32, batch.depth, batch.centers, cfg, camera))
+
+
+@pytest.mark.parametrize('H,W,N,C,K', [
+    (64, 64, 37, 3, 32),
+    (3, 8, 5, 2, 8),
+    (7, 240, 3, 2, 64),        # widest single bf16 box (4 * 61 + 4 + 4 = 252 -> 256 columns)
+    (9, 248, 2, 3, 64),        # narrowest two-box bf16 row
+    (33, 320, 2, 3, 16),       # K small: most maps overflow -> overflow path (bf16 generic tiles)
+    (12, 488, 2, 2, 256),      # widest bf16 row the strip kernel takes (two boxes of 256 columns)
+    (11, 496, 1, 2, 64),       # wider: generic kernel
+    (30, 68, 2, 2, 32),        # W % 8 != 0 -> generic kernel
+])
+def test_bf16_peak_extraction_shapes_noise_and_overflow(H, W, N, C, K):
+    """Dense random bf16 maps (bf16 quantisation makes exact ties common): strip kernel, overflow path and
+    generic kernel give bitwise the oracle's peak tables on the up-cast maps; also maps with a negative
+    value (-0.0 included), which void the bounded filter and take the exact path."""
+    from oracle import c_oracle
+    from object_keypoints_b200 import KeypointDecoder
+    rng = np.random.default_rng(H * 1000 + W + 1)
+    heat = rng.uniform(0, 0.2, (N, C, H, W)).astype(np.float32)
+    heat[0, 0, H // 2, W // 2] = -0.0
+    if N > 1:
+        heat[1, C - 1] = 0.001
+        heat[1, 0, 0, 0] = -0.125
+    heat_dev, heat32 = _bf16_round(heat)
+    cfg = [1] * (C - 1)
+    decoder = KeypointDecoder(cfg, (H, W), max_peaks=K, max_objects=16)
+    got = decoder.extract_peaks(heat_dev).numpy()
+    want = c_oracle.decode(heat32, np.zeros_like(heat32), np.zeros((N, C - 1, 2, H, W), np.float32), cfg, None,
+                           max_peaks=K, max_objects=16)
+    np.testing.assert_array_equal(got['peak_count'], want['peak_count'])
+    np.testing.assert_array_equal(got['peak_yx'], want['peak_yx'])
+    for key in ['peak_score', 'peak_xy', 'peak_conf']:
+        np.testing.assert_array_equal(got[key].view(np.uint32), want[key].view(np.uint32), err_msg=key)

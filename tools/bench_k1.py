@@ -1,5 +1,5 @@
-"""Times okp_extract_peaks_f32 (K1) and okp_group_objects_f32 alone on synthetic batches.
-usage: python tools/bench_k1.py [180x320|64x64] [frames] [reps]"""
+"""Times okp_extract_peaks_* (K1) and okp_group_objects_* alone on synthetic batches.
+usage: python tools/bench_k1.py [180x320|64x64] [frames] [reps] [f32|bf16]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,9 +8,12 @@ from object_keypoints_b200 import KeypointDecoder, synthetic
 shape = sys.argv[1] if len(sys.argv) > 1 else '180x320'
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+dtype = sys.argv[4] if len(sys.argv) > 4 else 'f32'
 H, W = [int(v) for v in shape.split('x')]
 grid = (4, 2) if W >= 128 else (2, 1)
 heat, depth, centers, _ = synthetic.torch_grid_batch(frames, [1, 3], (H, W), seed=7, grid=grid, device='cuda')
+if dtype == 'bf16':
+    heat, depth, centers = heat.bfloat16(), depth.bfloat16(), centers.bfloat16()
 camera = synthetic.default_camera((H, W))
 dec = KeypointDecoder([1, 3], (H, W), camera=camera)
 tables = dec.tables(frames)
@@ -24,7 +27,7 @@ for _ in range(reps):
     torch.cuda.synchronize()
     k1 += ev[0].elapsed_time(ev[1]); k3 += ev[1].elapsed_time(ev[2])
 k1 /= reps; k3 /= reps
-gb = frames * 3 * H * W * 4 / 1e9
-print(f"{shape} frames={frames} env={ {k: v for k, v in os.environ.items() if k.startswith('OKP_')} } "
+gb = frames * 3 * H * W * heat.element_size() / 1e9
+print(f"{shape} {dtype} frames={frames} env={ {k: v for k, v in os.environ.items() if k.startswith('OKP_')} } "
       f"K1 {k1 * 1e3:.1f} us = {gb / (k1 / 1e3):.0f} GB/s ({gb / (k1 / 1e3) / 6548.2:.3f} of measured HBM peak); group {k3 * 1e3:.1f} us; "
       f"objects/frame {float(tables['n_objects'].float().mean()):.2f}")
