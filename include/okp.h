@@ -226,6 +226,32 @@ int okp_stereo_associate_f64(const double* F, const double* left_dev, const int3
                              int max_right, double max_distance_px, int32_t* match_dev, double* cost_dev,
                              void* stream);
 
+/* Evaluation bookkeeping. Replaces Results.add of the reference's
+ * scripts/eval_model.py:141-187 for a batch of N frames, reading the decode tables in place:
+ * kp_point_dev [N,O,C,S,3], kp_count_dev [N,O,C], n_objects_dev [N] (OkpDecodeTables fields), T_WC_dev
+ * [N,4,4] camera->world per frame, scene_points_dev [G,Kp,3] world points, row 0 of each object its centre
+ * (perception/datasets/video.py:121-129). Every predicted object is matched to the ground-truth object with
+ * the nearest centre in camera-frame XY (:153-155) and dropped when that centre does not project into the
+ * frame (:158-163); a point with all coordinates < max_coordinate (2.0) is matched to the nearest of the
+ * object's ground-truth points (:171-173) and dropped when that point is not in view (:174-178), any other
+ * point counts as missing (:183-185). frame_limit_x / frame_limit_y are camera.image_size[0] / [1] AS THE
+ * REFERENCE HOLDS THEM, i.e. (H, W) compared with (x, y) (camera_utils.py:36-43).
+ * Outputs: status_dev [N,O,C,S] (-1 empty slot, 0 matched, 1 missing, 2 point not in view, 3 object not in
+ * view), gt_point_dev [N,O,C,S,3] camera-frame ground truth, err_dev / err_xy_dev [N,O,C,S] metres,
+ * gt_object_dev [N,O], frame_stats_dev [N,8] per-frame (matched, missing, errors < small_error, mean, M2,
+ * sum of xy errors, 0, 0) for okp_eval_summary_f64. */
+int okp_eval_match_f64(const double* kp_point_dev, const int32_t* kp_count_dev, const int32_t* n_objects_dev,
+                       const double* T_WC_dev, const double* scene_points_dev, int N, int O, int C, int S,
+                       int G, int Kp, const OkpCamera* camera, double frame_limit_x, double frame_limit_y,
+                       double max_coordinate, double small_error, int32_t* status_dev, double* gt_point_dev,
+                       double* err_dev, double* err_xy_dev, int32_t* gt_object_dev, double* frame_stats_dev,
+                       void* stream);
+
+/* Replaces the accumulation loop of Results.print_results (scripts/eval_model.py:192-214): merges
+ * frame_stats_dev [N,8] into totals_dev [8] = (matched, missing, small, mean error, M2 = sum of squared
+ * deviations, sum of xy errors, 0, 0), metres, deterministically (fixed merge order). */
+int okp_eval_summary_f64(const double* frame_stats_dev, int N, double* totals_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ EXPORTS = [
     'okp_detection_to_point_f32', 'okp_triangulate_f64', 'okp_reprojection_filter_f64',
     'okp_triangulate_robust_f64', 'okp_host_alias', 'okp_correct_matches_f64', 'okp_stereo_associate_f64',
     'okp_extract_peaks_bf16', 'okp_group_objects_bf16', 'okp_decode_bf16',
+    'okp_eval_match_f64', 'okp_eval_summary_f64',
 ]
 
 
@@ -100,6 +101,11 @@ def lib():
     L.okp_correct_matches_f64.argtypes = [P(dbl), vp, vp, i32, i32, vp, vp, vp]
     L.okp_stereo_associate_f64.restype = i32
     L.okp_stereo_associate_f64.argtypes = [P(dbl), vp, vp, vp, vp, i32, i32, i32, dbl, vp, vp, vp]
+    L.okp_eval_match_f64.restype = i32
+    L.okp_eval_match_f64.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, P(_abi.OkpCamera), dbl, dbl, dbl, dbl,
+                                     vp, vp, vp, vp, vp, vp, vp]
+    L.okp_eval_summary_f64.restype = i32
+    L.okp_eval_summary_f64.argtypes = [vp, i32, vp, vp]
     _LIB = L
     return L
 

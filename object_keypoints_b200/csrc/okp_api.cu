@@ -11,6 +11,7 @@
 #include "okp_group.cuh"
 #include "okp_dlt.cuh"
 #include "okp_stereo.cuh"
+#include "okp_eval.cuh"
 
 namespace {
 
@@ -336,6 +337,39 @@ int okp_stereo_associate_f64(const double* F, const double* left_dev, const int3
     const size_t smem = sizeof(double) * (size_t)max_left * max_right;
     okp_associate_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(Fm, left_dev, n_left_dev, right_dev, n_right_dev,
                                                                max_left, max_right, max_distance_px, match_dev, cost_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_eval_match_f64(const double* kp_point_dev, const int32_t* kp_count_dev, const int32_t* n_objects_dev,
+                       const double* T_WC_dev, const double* scene_points_dev, int N, int O, int C, int S, int G, int Kp,
+                       const OkpCamera* camera, double frame_limit_x, double frame_limit_y, double max_coordinate,
+                       double small_error, int32_t* status_dev, double* gt_point_dev, double* err_dev,
+                       double* err_xy_dev, int32_t* gt_object_dev, double* frame_stats_dev, void* stream) {
+    if (N < 0 || O < 1 || O > OKP_MAX_OBJECTS || C < 1 || C > OKP_MAX_MAPS || S < 1 || S > OKP_MAX_SLOTS || G < 1 || Kp < 1)
+        return OKP_E_SHAPE;
+    const size_t smem = sizeof(double) * 3 * (size_t)G * Kp + sizeof(int) * 2 * (size_t)O;
+    if (smem > 200 * 1024) return OKP_E_SHAPE;
+    if (N == 0) return OKP_OK;
+    if (!kp_point_dev || !kp_count_dev || !n_objects_dev || !T_WC_dev || !scene_points_dev || !camera || !status_dev ||
+        !gt_point_dev || !err_dev || !err_xy_dev || !gt_object_dev || !frame_stats_dev)
+        return OKP_E_NULL;
+    OkpEvalDims d;
+    d.N = N; d.O = O; d.C = C; d.S = S; d.G = G; d.Kp = Kp;
+    auto kernel = okp_eval_match_kernel<128>;
+    if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<N, 128, smem, (cudaStream_t)stream>>>(kp_point_dev, kp_count_dev, n_objects_dev, T_WC_dev, scene_points_dev, d,
+                                                    *camera, frame_limit_x, frame_limit_y, max_coordinate, small_error,
+                                                    status_dev, gt_point_dev, err_dev, err_xy_dev, gt_object_dev,
+                                                    frame_stats_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_eval_summary_f64(const double* frame_stats_dev, int N, double* totals_dev, void* stream) {
+    if (N < 0) return OKP_E_SHAPE;
+    if (!totals_dev || (N > 0 && !frame_stats_dev)) return OKP_E_NULL;
+    okp_eval_summary_kernel<256><<<1, 256, 0, (cudaStream_t)stream>>>(frame_stats_dev, N, totals_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

@@ -415,6 +415,117 @@ def producer_case(heatmaps_out=3, seed=21):
                 parameter_names=np.array(names), parameter_sizes=np.array([weights[n].numel() for n in names], np.int64))
 
 
+def import_reference_eval_model():
+    """scripts/eval_model.py of the UNMODIFIED reference, with stand-ins for the GUI / plotting packages it
+    imports at module level (hud, matplotlib); its Results class (:137-232) only needs NumPy."""
+    import types
+    ref_import.load()
+    hud = sys.modules['hud']
+    hud.Rect = lambda *a, **k: None
+    for name in ['matplotlib', 'matplotlib.cm', 'matplotlib.pyplot']:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['matplotlib'].cm = sys.modules['matplotlib.cm']
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['matplotlib.cm'].get_cmap = lambda name: None
+    scripts = os.path.join(ref_import.REFERENCE_ROOT, 'scripts')
+    if scripts not in sys.path:
+        sys.path.insert(0, scripts)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import eval_model
+    return eval_model
+
+
+def evaluation_case(camera_utils, seed=31, frames=40, cfg=(1, 3)):
+    """Results.add / print_results of the unmodified reference (scripts/eval_model.py:137-232) on a synthetic
+    scene: G objects in the world, a camera pose per frame, predictions = ground truth + 1 cm noise with
+    dropped / reordered / decoy objects, absent keypoints, points beyond 2 m ("missing") and objects or points
+    outside the frame. The non-square 180x320 camera pins in_frame's (x, y) vs (H, W) comparison."""
+    eval_model = import_reference_eval_model()
+    rng = np.random.default_rng(seed)
+    camera = reference_camera(camera_utils, (180, 320))
+    C, S, O = 1 + len(cfg), max(cfg), O_OBJECTS
+    slots = [1] + list(cfg)
+    G, Kp = 5, sum(slots)
+    scene = np.zeros((G, Kp, 3))
+    for g in range(G):
+        centre = np.array([rng.uniform(-0.7, 0.15), rng.uniform(-0.4, 0.4), rng.uniform(-0.1, 0.1)])
+        scene[g, 1:] = centre + rng.normal(0, 0.08, (Kp - 1, 3))
+        scene[g, 0] = scene[g, 1:].mean(axis=0)
+    kp_point = np.zeros((frames, O, C, S, 3))
+    kp_count = np.zeros((frames, O, C), np.int32)
+    n_objects = np.zeros(frames, np.int32)
+    T_WC = np.zeros((frames, 4, 4))
+    rows = []
+
+    class Row:                                   # stands in for rich.table.Table: keeps what print_results adds
+        def __init__(self, *a, **k): pass
+        def add_column(self, *a, **k): pass
+        def add_row(self, *cells): rows.append(cells)
+    eval_model.Table = Row
+    results = eval_model.Results()
+    results.screen = types_namespace(update=lambda table: None)
+    results.set_calibration(camera)
+    for n in range(frames):
+        from scipy.spatial.transform import Rotation
+        R = Rotation.from_euler('xyz', rng.normal(0, [0.15, 0.15, 0.3])).as_matrix()
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), -rng.uniform(0.7, 1.9)])
+        T_WC[n] = T
+        T_CW = np.linalg.inv(T)
+        scene_C = scene @ T_CW[:3, :3].T + T_CW[:3, 3]
+        order = [g for g in rng.permutation(G) if rng.uniform() > 0.2]
+        objects = []
+        for g in order:
+            points = scene_C[g] + rng.normal(0, 0.01, (Kp, 3))
+            p_C, at = [], 0
+            for c, count in enumerate(slots):
+                keep = count if c == 0 else int(rng.integers(0, count + 1))
+                block = points[at:at + keep].copy()
+                at += count
+                for row in block:
+                    if c > 0 and rng.uniform() < 0.1:
+                        row[2] += 2.0                      # beyond the 2 m cut -> "missing"
+                p_C.append(block if keep else None)
+            objects.append({'p_C': p_C})
+        if rng.uniform() < 0.3:                            # a decoy far from every ground-truth object
+            objects.append({'p_C': [np.array([[1.5, 1.2, 1.0]])] + [None] * (C - 1)})
+        n_objects[n] = len(objects)
+        for o, obj in enumerate(objects):
+            for c, block in enumerate(obj['p_C']):
+                if block is not None:
+                    kp_count[n, o, c] = len(block)
+                    kp_point[n, o, c, :len(block)] = block
+        with contextlib.redirect_stdout(io.StringIO()):
+            results.add(T, objects, scene)
+    L = Kp
+    seq_kind = np.full((frames, O, L), -1, np.int32)
+    seq_pred = np.zeros((frames, O, L, 3))
+    seq_gt = np.zeros((frames, O, L, 3))
+    kept_objects = np.zeros(frames, np.int32)
+    for n, (gt_frame, pred_frame) in enumerate(zip(results.gt_keypoints, results.predicted_keypoints)):
+        kept_objects[n] = len(gt_frame)
+        for o, (gt_points, pred_points) in enumerate(zip(gt_frame, pred_frame)):
+            for i, (g, p) in enumerate(zip(gt_points, pred_points)):
+                seq_kind[n, o, i] = 1 if p is None else 0
+                if p is not None:
+                    seq_pred[n, o, i], seq_gt[n, o, i] = p, g
+    results.print_results()
+    cells = rows[-1]
+    summary = np.array([float(c.rstrip('%')) for c in cells], np.float64)
+    assert (seq_kind == 1).any() and kept_objects.sum() < n_objects.sum(), "fixture must cover missing points and dropped objects"
+    return dict(kp_point=kp_point, kp_count=kp_count, n_objects=n_objects, T_WC=T_WC, scene_points=scene,
+                keypoint_config=np.array(cfg, np.int32), ref_seq_kind=seq_kind, ref_seq_pred=seq_pred, ref_seq_gt=seq_gt,
+                ref_kept_objects=kept_objects, ref_summary=summary,
+                ref_summary_columns=np.array(['mean', 'mean_xy', 'std', 'small', 'percentile25', 'percentile75',
+                                              'missing_percentage', 'points']), **camera_arrays(camera))
+
+
+def types_namespace(**kw):
+    import types
+    return types.SimpleNamespace(**kw)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref, camera_utils, video = ref_import.load()
@@ -423,6 +534,9 @@ def main():
         return
     if '--only-producer' in sys.argv:
         save('producer_valve.npz', **producer_case())
+        return
+    if '--only-evaluation' in sys.argv:
+        save('evaluation.npz', **evaluation_case(camera_utils))
         return
 
     # 1-2: model-resolution clean sets (bit-exact parity)
@@ -461,6 +575,9 @@ def main():
 
     # 7: camera geometry and triangulation
     save('geometry.npz', **geometry_case(camera_utils))
+
+    # 9: evaluation bookkeeping (scripts/eval_model.py Results)
+    save('evaluation.npz', **evaluation_case(camera_utils))
 
     # 8: the keypoint network (input producer of BASELINE config 5)
     save('producer_valve.npz', **producer_case())

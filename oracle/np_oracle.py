@@ -503,3 +503,86 @@ def associate(F, left, right, max_distance_px=2.5):
         free[i, :] = False
         free[:, j] = False
     return match, match_cost
+
+
+# ------------------------------------------------------------------------------------------
+# evaluation bookkeeping, scripts/eval_model.py:137-232 (Results.add /
+# Results.print_results), restated on the record tables of include/okp.h
+# ------------------------------------------------------------------------------------------
+EVAL_EMPTY, EVAL_MATCHED, EVAL_MISSING, EVAL_POINT_NOT_IN_VIEW, EVAL_OBJECT_NOT_IN_VIEW = -1, 0, 1, 2, 3
+
+
+def _in_frame(px, image_size):
+    """PinholeCamera.in_frame (camera_utils.py:36-43): (x, y) against image_size = (H, W) AS GIVEN --
+    x is compared with the height, like the clip in pipeline.py:169."""
+    return not ((px <= 0.0).any() or (px >= np.asarray(image_size, dtype=np.float64)).any())
+
+
+def evaluation_match(kp_point, kp_count, n_objects, T_WC, scene_points, cam, image_size, max_coordinate=2.0):
+    """Results.add (eval_model.py:141-187) for every frame of a batch.
+
+    kp_point [N,O,C,S,3] camera-frame predictions 'p_C', kp_count [N,O,C], n_objects [N] (the decode
+    tables); T_WC [N,4,4] camera->world per frame; scene_points [G,Kp,3] world, row 0 of every object its
+    centre (video.py:121-129). Per predicted point: status, matched ground-truth point (camera frame),
+    3D error and xy error in metres; per object the ground-truth object it was matched to.
+      - object -> ground-truth object: nearest centre in camera-frame XY (:154-155), depth ignored;
+      - the object is dropped if that ground-truth centre does not project into the frame (:159-163);
+      - a point with every coordinate < max_coordinate (2.0, :171) is matched to the nearest of the
+        object's ground-truth points in 3D (:172-173) and dropped if that point is not in view (:176-178);
+        any other point counts as missing (:183-185)."""
+    N, O, C, S = kp_point.shape[:4]
+    status = np.full((N, O, C, S), EVAL_EMPTY, np.int32)
+    gt_point = np.zeros((N, O, C, S, 3), np.float64)
+    err = np.zeros((N, O, C, S), np.float64)
+    err_xy = np.zeros((N, O, C, S), np.float64)
+    gt_object = np.full((N, O), -1, np.int32)
+    scene_points = np.asarray(scene_points, dtype=np.float64)
+    identity = np.eye(4)
+    for n in range(N):
+        T = np.asarray(T_WC[n], dtype=np.float64)
+        T_CW = np.eye(4)
+        T_CW[:3, :3] = T[:3, :3].T
+        T_CW[:3, 3] = -T_CW[:3, :3] @ T[:3, 3]                      # linalg.py:9-13
+        scene_C = (T_CW[:3, :3] @ scene_points[..., None])[..., 0] + T_CW[:3, 3]   # linalg.py:15-20
+        centers_C = scene_C[:, 0]
+        for o in range(int(n_objects[n])):
+            centre = kp_point[n, o, 0, 0]
+            d = np.linalg.norm(centers_C[:, :2] - centre[:2], axis=1)
+            g = int(d.argmin())
+            gt_object[n, o] = g
+            object_points = scene_C[g]
+            visible = _in_frame(project_points(object_points[0:1], identity, cam)[0], image_size)
+            for c in range(C):
+                for s in range(int(kp_count[n, o, c])):
+                    if not visible:
+                        status[n, o, c, s] = EVAL_OBJECT_NOT_IN_VIEW
+                        continue
+                    point = kp_point[n, o, c, s]
+                    if not (point < max_coordinate).all():
+                        status[n, o, c, s] = EVAL_MISSING
+                        continue
+                    k = int(np.linalg.norm(object_points - point, axis=1).argmin())
+                    gt = object_points[k]
+                    if not _in_frame(project_points(gt[None], identity, cam)[0], image_size):
+                        status[n, o, c, s] = EVAL_POINT_NOT_IN_VIEW
+                        continue
+                    status[n, o, c, s] = EVAL_MATCHED
+                    gt_point[n, o, c, s] = gt
+                    err[n, o, c, s] = np.linalg.norm(gt - point)
+                    err_xy[n, o, c, s] = np.linalg.norm(gt[:2] - point[:2])
+    return {'status': status, 'gt_point': gt_point, 'err': err, 'err_xy': err_xy, 'gt_object': gt_object}
+
+
+def evaluation_summary(status, err, err_xy):
+    """Results.print_results (eval_model.py:192-232): the row of the printed table, errors in cm."""
+    matched = status == EVAL_MATCHED
+    missing = int((status == EVAL_MISSING).sum())
+    e = err[matched] * 100.0
+    exy = err_xy[matched] * 100.0
+    n_points = int(matched.sum()) + missing
+    return {
+        'mean': float(e.mean()), 'mean_xy': float(exy.mean()), 'std': float(e.std()),
+        'small': float((err[matched] < 0.03).sum()) / float(n_points),
+        'percentile25': float(np.percentile(e, 25)), 'percentile75': float(np.percentile(e, 75)),
+        'missing_percentage': float(missing) / float(n_points) * 100.0, 'points': n_points,
+    }
