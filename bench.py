@@ -110,17 +110,17 @@ def cpu_baseline(workload, heat, depth, centers, budget_s=12.0):
     from oracle import c_oracle
     w = WORKLOADS[workload]
     camera = synthetic.default_camera(w['size'])
-    cores = c_oracle.max_threads()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else c_oracle.max_threads()
     probe = min(64, heat.shape[0])
     h, d, c = heat[:probe].cpu().numpy(), depth[:probe].cpu().numpy(), centers[:probe].cpu().numpy()
-    c_oracle.decode(h, d, c, w['cfg'], camera)                       # warm-up (thread pool, page faults)
+    c_oracle.decode(h, d, c, w['cfg'], camera, threads=cores)                       # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
-    c_oracle.decode(h, d, c, w['cfg'], camera)
+    c_oracle.decode(h, d, c, w['cfg'], camera, threads=cores)
     rate = probe / (time.perf_counter() - t0)
     sample = int(max(probe, min(heat.shape[0], rate * budget_s)))
     h, d, c = heat[:sample].cpu().numpy(), depth[:sample].cpu().numpy(), centers[:sample].cpu().numpy()
     t0 = time.perf_counter()
-    c_oracle.decode(h, d, c, w['cfg'], camera)
+    c_oracle.decode(h, d, c, w['cfg'], camera, threads=cores)
     elapsed = time.perf_counter() - t0
     return {'value': sample / elapsed, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': f"first {sample} frames of {workload} (C/OpenMP restatement oracle/okp_oracle.c, {elapsed:.2f} s)"}
@@ -146,13 +146,14 @@ def run_reference(args):
         h, d, c, _ = synthetic.torch_grid_batch(sample, w['cfg'], w['size'], seed=1004, grid=w['grid'], device=device, chunk=64)
         heat, depth, centers = h.cpu().numpy(), d.cpu().numpy(), c.cpu().numpy()
     sample = heat.shape[0]
-    cores = c_oracle.max_threads()
+    # every host core, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     for _ in range(max(args.warmup, 1)):
-        c_oracle.decode(heat, depth, centers, w['cfg'], camera)
+        c_oracle.decode(heat, depth, centers, w['cfg'], camera, threads=cores)
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        c_oracle.decode(heat, depth, centers, w['cfg'], camera)
+        c_oracle.decode(heat, depth, centers, w['cfg'], camera, threads=cores)
         times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     value = sample / (ms / 1e3)
@@ -174,7 +175,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from object_keypoints_b200 import KeypointDecoder, synthetic
-    from object_keypoints_b200.sharding import gather_keypoint_records, record_tensor
+    from object_keypoints_b200.pipeline import DecodeTables
+    from object_keypoints_b200.sharding import RecordExchange
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -193,14 +195,26 @@ def run_ours(args):
     camera = synthetic.default_camera(w['size'])
     heat, depth, centers = make_inputs(args.workload, device, seed=rank)
     decoder = KeypointDecoder(w['cfg'], w['size'], camera=camera, device=device)
-    tables = decoder.tables(frames)
+    # two table sets: the gather of step k (own stream) overlaps the decode of step k + 1
+    table_sets = [decoder.tables(frames), DecodeTables(frames, decoder.C, decoder.cfg, decoder.params, device)]
+    tables = table_sets[0]
+    exchange = RecordExchange(tables, world=world, rank=rank, transport=args.transport) if world > 1 else None
     gathered = None
+    table_free = [None, None]
+    steps_done = [0]
 
     def step():
-        decoder.extract_peaks(heat, tables)
-        decoder.group_objects(depth, centers, tables)
+        index = steps_done[0] % 2
+        steps_done[0] += 1
+        current = table_sets[index]
+        if table_free[index] is not None:
+            torch.cuda.current_stream().wait_event(table_free[index])     # its previous gather has read it
+        decoder.extract_peaks(heat, current)
+        decoder.group_objects(depth, centers, current)
         if world > 1:
-            return gather_keypoint_records(tables, world)
+            result, done = exchange.exchange(current)
+            table_free[index] = done
+            return result
         return None
 
     def barrier():
@@ -222,12 +236,19 @@ def run_ours(args):
     barrier()
     start.record()
     for i in range(args.steps):
+        index = steps_done[0] % 2
+        steps_done[0] += 1
+        current = table_sets[index]
+        if table_free[index] is not None:
+            torch.cuda.current_stream().wait_event(table_free[index])
         k1_events[i][0].record()
-        decoder.extract_peaks(heat, tables)
+        decoder.extract_peaks(heat, current)
         k1_events[i][1].record()
-        decoder.group_objects(depth, centers, tables)
+        decoder.group_objects(depth, centers, current)
         if world > 1:
-            gathered = gather_keypoint_records(tables, world)
+            gathered, table_free[index] = exchange.exchange(current)
+    if world > 1:
+        exchange.finish()                               # every gather of the K steps is inside the timed region
     stop.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -260,6 +281,9 @@ def run_ours(args):
     # sanity: the decode found the objects that were drawn (guards against timing an empty kernel)
     found = float((tables['n_objects'] > 0).float().mean())
     assert found > 0.99, f"only {found:.3f} of the frames produced objects"
+    if world > 1:                                           # the gathered records hold every rank's frames
+        objects = gathered[:, 0].reshape(world, frames)
+        assert bool((objects > 0).float().mean(dim=1).gt(0.99).all()), "gathered records are incomplete"
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -279,7 +303,11 @@ def run_ours(args):
             'config': {'workload': args.workload, 'keypoint_config': w['config'], 'frames_per_gpu': frames,
                        'prediction_size': [H, W], 'objects_per_frame': w['grid'][0] * w['grid'][1],
                        'l2': f"inputs {algorithmic_bytes / 1e6:.0f} MB heatmaps per step exceed the 126 MB L2; no flush needed",
-                       'parallelism': f"frames sharded over {world} GPU(s), all_gather of 3D keypoint records"},
+                       'parallelism': f"frames sharded over {world} GPU(s); per step one gather of the 3D keypoint records"
+                                      + (f" ({exchange.transport}: "
+                                         + ('pack kernel stores straight into every peer over NVLink' if exchange.transport == 'peer'
+                                            else 'pack kernel + NCCL all_gather') + ", overlapped with the next step's decode)"
+                                         if world > 1 else "")},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                          'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peak_kind,
                          'kernel': 'K1 peaks (box sum + NMS + centroid) + merge', 'kernel_ms': k1_ms,
@@ -289,7 +317,7 @@ def run_ours(args):
                     'host_input_bytes_per_step': sum(t.numel() * t.element_size() for t in host),
                     'note': 'heatmaps copied from pinned host memory in chunks overlapped with decode; depth and centre '
                             'maps (gather-only) are read in place from pinned host memory over PCIe'},
-            'gpu_launches': args.steps * 3,
+            'gpu_launches': args.steps * (3 + (1 if world > 1 else 0)),
             'clocks': clocks,
         }
         if not args.no_cpu_baseline and world == 1:
@@ -310,6 +338,8 @@ def main():
     ap.add_argument('--e2e-frames', type=int, default=1024)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
+                    help="N > 1: how the keypoint records are gathered (sharding.RecordExchange)")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

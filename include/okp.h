@@ -252,6 +252,20 @@ int okp_eval_match_f64(const double* kp_point_dev, const int32_t* kp_count_dev, 
  * deviations, sum of xy errors, 0, 0), metres, deterministically (fixed merge order). */
 int okp_eval_summary_f64(const double* frame_stats_dev, int N, double* totals_dev, void* stream);
 
+/* Multi-GPU exchange (the reference is single-GPU, batch 1: pipeline.py:183). Frames
+ * shard independently; the only cross-GPU step is the gather of the per-frame 3D keypoint records. A record
+ * is okp_record_doubles(O, C, S) = 2 + O*C + O*C*S*3 float64: n_objects, flags, kp_count[O,C],
+ * kp_point[O,C,S,3] -- what ObjectKeypointPipeline.__call__ returns per frame (pipeline.py:195-199). */
+int okp_record_doubles(int O, int C, int S);
+
+/* Packs the N records of `tables` and stores them at rows [first_row, first_row + N) of every destination
+ * buffer (`destinations`: HOST array of n_destinations <= 16 DEVICE pointers to [rows, R] float64 buffers).
+ * One destination = the pack step in front of an NCCL all_gather. With the peer-mapped buffers of all ranks
+ * as destinations (first_row = rank * N) this call is the all_gather itself: the stores go over NVLink
+ * while the kernel packs; the caller provides the cross-rank barrier before the buffers are read. */
+int okp_pack_records_f64(const OkpDecodeTables* tables, int N, int O, int C, int S, long long first_row,
+                         double* const* destinations, int n_destinations, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ EXPORTS = [
     'okp_detection_to_point_f32', 'okp_triangulate_f64', 'okp_reprojection_filter_f64',
     'okp_triangulate_robust_f64', 'okp_host_alias', 'okp_correct_matches_f64', 'okp_stereo_associate_f64',
     'okp_extract_peaks_bf16', 'okp_group_objects_bf16', 'okp_decode_bf16',
-    'okp_eval_match_f64', 'okp_eval_summary_f64',
+    'okp_eval_match_f64', 'okp_eval_summary_f64', 'okp_record_doubles', 'okp_pack_records_f64',
 ]
 
 
@@ -106,6 +106,10 @@ def lib():
                                      vp, vp, vp, vp, vp, vp, vp]
     L.okp_eval_summary_f64.restype = i32
     L.okp_eval_summary_f64.argtypes = [vp, i32, vp, vp]
+    L.okp_record_doubles.restype = i32
+    L.okp_record_doubles.argtypes = [i32, i32, i32]
+    L.okp_pack_records_f64.restype = i32
+    L.okp_pack_records_f64.argtypes = [P(_abi.OkpDecodeTables), i32, i32, i32, i32, ctypes.c_longlong, P(vp), i32, vp]
     _LIB = L
     return L
 

@@ -12,6 +12,7 @@
 #include "okp_dlt.cuh"
 #include "okp_stereo.cuh"
 #include "okp_eval.cuh"
+#include "okp_records.cuh"
 
 namespace {
 
@@ -180,8 +181,14 @@ int group_objects(const T* depth_dev, const T* centers_dev, int N, int C, int H,
     OkpCamera cam;
     memset(&cam, 0, sizeof(cam));
     if (camera) cam = *camera;
-    okp_group_kernel<128, T><<<N, 128, 0, (cudaStream_t)stream>>>(depth_dev, centers_dev, N, C, H, W, config, cam,
-                                                                  camera != nullptr, *params, S, *tables);
+    const int K = params->max_peaks, O = params->max_objects;
+    bool stash = true;
+    size_t smem = okp_group_smem_bytes(C, K, O, S, true);
+    if (smem > 160 * 1024) { stash = false; smem = okp_group_smem_bytes(C, K, O, S, false); }
+    auto kernel = okp_group_kernel<128, T>;
+    if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<N, 128, smem, (cudaStream_t)stream>>>(depth_dev, centers_dev, N, C, H, W, config, cam, camera != nullptr,
+                                                   *params, S, stash ? 1 : 0, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }
@@ -370,6 +377,34 @@ int okp_eval_summary_f64(const double* frame_stats_dev, int N, double* totals_de
     if (N < 0) return OKP_E_SHAPE;
     if (!totals_dev || (N > 0 && !frame_stats_dev)) return OKP_E_NULL;
     okp_eval_summary_kernel<256><<<1, 256, 0, (cudaStream_t)stream>>>(frame_stats_dev, N, totals_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_record_doubles(int O, int C, int S) {
+    if (O < 1 || O > OKP_MAX_OBJECTS || C < 1 || C > OKP_MAX_MAPS || S < 1 || S > OKP_MAX_SLOTS) return 0;
+    return 2 + O * C + O * C * S * 3;
+}
+
+int okp_pack_records_f64(const OkpDecodeTables* tables, int N, int O, int C, int S, long long first_row,
+                         double* const* destinations, int n_destinations, void* stream) {
+    if (N < 0 || first_row < 0 || okp_record_doubles(O, C, S) == 0) return OKP_E_SHAPE;
+    if (n_destinations < 1 || n_destinations > OKP_MAX_PEERS) return OKP_E_SHAPE;
+    if (N == 0) return OKP_OK;
+    if (!tables || !destinations || !tables->n_objects || !tables->flags || !tables->kp_count || !tables->kp_point)
+        return OKP_E_NULL;
+    OkpPeerBuffers peers;
+    memset(&peers, 0, sizeof(peers));
+    for (int d = 0; d < n_destinations; ++d) {
+        if (!destinations[d]) return OKP_E_NULL;
+        peers.dst[d] = destinations[d];
+    }
+    const long long total = (long long)N * okp_record_doubles(O, C, S);
+    long long blocks = (total + 255) / 256;
+    if (blocks > kSmCount * 8) blocks = kSmCount * 8;
+    okp_pack_records_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        tables->n_objects, tables->flags, tables->kp_count, tables->kp_point, N, O * C, O * C * S * 3, first_row,
+        n_destinations, peers);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

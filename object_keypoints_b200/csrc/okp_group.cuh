@@ -78,68 +78,103 @@ __device__ __noinline__ void okp_cluster_detections(const float* __restrict__ xy
 #undef OKP_PT
 }
 
+// Shared-memory budget of okp_group_kernel for a problem size (bytes); `stash` = the kept keypoints are also
+// held in shared memory for the 3D lift (dropped when the worst-case capacities would not fit).
+static inline size_t okp_group_smem_bytes(int C, int K, int O, int S, bool stash) {
+    size_t bytes = (size_t)C * K * (2 * sizeof(double) + 2 * sizeof(float) + sizeof(float) + sizeof(int));
+    bytes += (size_t)O * C * sizeof(int);
+    if (stash) bytes += (size_t)O * C * S * 2 * sizeof(float);
+    return bytes;
+}
+
+// Latency is what this kernel is made of (a frame is ~40 peaks): the frame's peak records are pulled into
+// shared memory with ONE round trip, every later phase works on shared memory, and results leave as
+// fire-and-forget stores. Global round trips on the critical path: counts -> records -> centre-vector
+// gather -> depth gather.
 template <int THREADS, typename E>
 __global__ void __launch_bounds__(THREADS)
 okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int N, int C, int H, int W,
-                 OkpConfig config, OkpCamera cam, int have_camera, OkpDecodeParams prm, int S, OkpDecodeTables t) {
+                 OkpConfig config, OkpCamera cam, int have_camera, OkpDecodeParams prm, int S, int stash, OkpDecodeTables t) {
     const int n = blockIdx.x;
     if (n >= N) return;
     const int K = prm.max_peaks, O = prm.max_objects, V = prm.max_votes, T = C - 1;
     const size_t HW = (size_t)H * W;
+    extern __shared__ __align__(16) unsigned char group_smem[];
+    double* s_vote = reinterpret_cast<double*>(group_smem);                 // [C][K][2] predicted centre of a spoke peak
+    float* s_xy = reinterpret_cast<float*>(s_vote + (size_t)C * K * 2);     // [C][K][2] centroid (x, y)
+    float* s_conf = s_xy + (size_t)C * K * 2;                               // [C][K]
+    int* s_obj = reinterpret_cast<int*>(s_conf + (size_t)C * K);            // [C][K]    object of a peak, -1 = none
+    int* s_kept = s_obj + (size_t)C * K;                                    // [O][C]    keypoints kept per (object, map)
+    float* s_kept_xy = reinterpret_cast<float*>(s_kept + (size_t)O * C);    // [O][C][S][2] (only with stash)
     __shared__ double s_center[OKP_MAX_OBJECTS][2];
     __shared__ unsigned int s_flags;
     __shared__ int s_counts[OKP_MAX_MAPS];
 
+    const size_t m0 = (size_t)n * C;
     if (threadIdx.x == 0) s_flags = 0;
     if (threadIdx.x < C) {
-        const int c = t.peak_count[(size_t)n * C + threadIdx.x];
+        const int c = t.peak_count[m0 + threadIdx.x];
         s_counts[threadIdx.x] = c < K ? c : K;
+        if (c > K) atomicOr(&s_flags, OKP_FLAG_PEAK_OVERFLOW);
     }
-    // reset this frame's object tables
-    for (int i = threadIdx.x; i < O * C; i += THREADS) {
-        const size_t oc = (size_t)n * O * C + i;
-        t.kp_assigned[oc] = 0;
-        t.kp_count[oc] = 0;
-        for (int s = 0; s < S; ++s) {
-            t.kp_peak[oc * S + s] = -1;
-            t.kp_xy[(oc * S + s) * 2] = 0.0f; t.kp_xy[(oc * S + s) * 2 + 1] = 0.0f;
-            t.kp_point[(oc * S + s) * 3] = 0.0; t.kp_point[(oc * S + s) * 3 + 1] = 0.0; t.kp_point[(oc * S + s) * 3 + 2] = 0.0;
-        }
+    // reset this frame's object tables (flat, coalesced; every region is contiguous per frame)
+    {
+        const int oc = O * C, ocs = oc * S;
+        int32_t* assigned = t.kp_assigned + (size_t)n * oc;
+        int32_t* count = t.kp_count + (size_t)n * oc;
+        for (int i = threadIdx.x; i < oc; i += THREADS) { assigned[i] = 0; count[i] = 0; }
+        int32_t* peak = t.kp_peak + (size_t)n * ocs;
+        for (int i = threadIdx.x; i < ocs; i += THREADS) peak[i] = -1;
+        float* xy = t.kp_xy + (size_t)n * ocs * 2;
+        for (int i = threadIdx.x; i < ocs * 2; i += THREADS) xy[i] = 0.0f;
+        double* point = t.kp_point + (size_t)n * ocs * 3;
+        for (int i = threadIdx.x; i < ocs * 3; i += THREADS) point[i] = 0.0;
+        int32_t* nv = t.n_votes + (size_t)n * O;
+        for (int i = threadIdx.x; i < O; i += THREADS) nv[i] = 0;
+        double* votes = t.votes + (size_t)n * O * V * 2;
+        for (int i = threadIdx.x; i < O * V * 2; i += THREADS) votes[i] = 0.0;
     }
-    for (int i = threadIdx.x; i < O; i += THREADS) t.n_votes[(size_t)n * O + i] = 0;
-    for (int i = threadIdx.x; i < O * V * 2; i += THREADS) t.votes[(size_t)n * O * V * 2 + i] = 0.0;
     __syncthreads();
-    if (threadIdx.x < C && t.peak_count[(size_t)n * C + threadIdx.x] > K) atomicOr(&s_flags, OKP_FLAG_PEAK_OVERFLOW);
 
-    const size_t m0 = (size_t)n * C;
     const int n_center = s_counts[0];
     if (n_center == 0) {                                   // pipeline.py:105-106
-        __syncthreads();
         if (threadIdx.x == 0) { t.n_objects[n] = 0; t.flags[n] = s_flags | OKP_FLAG_NO_CENTERS; }
         return;
     }
     const int n_obj = n_center < O ? n_center : O;
     if (threadIdx.x == 0 && n_center > O) atomicOr(&s_flags, OKP_FLAG_OBJECT_OVERFLOW);
-    for (int o = threadIdx.x; o < n_obj; o += THREADS) {   // pipeline.py:109-114: one object per centre peak
-        s_center[o][0] = (double)t.peak_xy[(m0 * K + o) * 2];
-        s_center[o][1] = (double)t.peak_xy[(m0 * K + o) * 2 + 1];
-        t.peak_object[m0 * K + o] = o;
+
+    // ---- the frame's peak records into shared memory (one round trip); spoke peaks fetch their centre vector
+    // in the same pass and vote as soon as the centres are known ----
+    for (int i = threadIdx.x; i < C * K; i += THREADS) {
+        const int c = i / K, k = i - c * K;
+        if (k >= s_counts[c]) continue;
+        const size_t s = (m0 + c) * K + k;
+        const float2 p = *reinterpret_cast<const float2*>(t.peak_xy + 2 * s);
+        s_xy[2 * i] = p.x; s_xy[2 * i + 1] = p.y;
+        s_conf[i] = t.peak_conf[s];
+        if (c == 0) {                                      // pipeline.py:109-114: one object per centre peak
+            const int o = k < n_obj ? k : -1;
+            s_obj[i] = o;
+            if (o >= 0) { s_center[o][0] = (double)p.x; s_center[o][1] = (double)p.y; t.peak_object[s] = o; }
+        } else {
+            const int xi = okp_clamp(__float2int_rn(p.x), 0, W - 1);      // np.round = half to even
+            const int yi = okp_clamp(__float2int_rn(p.y), 0, H - 1);
+            const E* cmap = centers + ((size_t)n * T + (c - 1)) * 2 * HW;
+            const double vx = ((double)xi + 0.5) + (double)okp_ld<E>(cmap + (size_t)yi * W + xi);
+            const double vy = ((double)yi + 0.5) + (double)okp_ld<E>(cmap + HW + (size_t)yi * W + xi);
+            s_vote[2 * i] = vx; s_vote[2 * i + 1] = vy;
+            t.peak_vote[2 * s] = vx;
+            t.peak_vote[2 * s + 1] = vy;
+        }
     }
     __syncthreads();
 
     // ---- spoke peaks vote for a centre (pipeline.py:115-128) ----
-    for (int i = threadIdx.x; i < T * K; i += THREADS) {
-        const int c = 1 + i / K, k = i - (c - 1) * K;
+    for (int i = K + threadIdx.x; i < C * K; i += THREADS) {
+        const int c = i / K, k = i - c * K;
         if (k >= s_counts[c]) continue;
-        const size_t s = ((size_t)n * C + c) * K + k;
-        const float px = t.peak_xy[2 * s], py = t.peak_xy[2 * s + 1];
-        const int xi = okp_clamp(__float2int_rn(px), 0, W - 1);      // np.round = half to even
-        const int yi = okp_clamp(__float2int_rn(py), 0, H - 1);
-        const E* cmap = centers + ((size_t)n * T + (c - 1)) * 2 * HW;
-        const double vx = ((double)xi + 0.5) + (double)okp_ld<E>(cmap + (size_t)yi * W + xi);
-        const double vy = ((double)yi + 0.5) + (double)okp_ld<E>(cmap + HW + (size_t)yi * W + xi);
-        t.peak_vote[2 * s] = vx;
-        t.peak_vote[2 * s + 1] = vy;
+        const double vx = s_vote[2 * i], vy = s_vote[2 * i + 1];
         int arg = 0;
         double dmin = 0.0;
         for (int o = 0; o < n_obj; ++o) {
@@ -149,10 +184,10 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
         }
         if (dmin > prm.outlier_distance) {
             atomicOr(&s_flags, OKP_FLAG_OUTLIER_SKIPPED);              // the reference prints and skips
-            t.peak_object[s] = -1;
-        } else {
-            t.peak_object[s] = arg;
+            arg = -1;
         }
+        s_obj[i] = arg;
+        t.peak_object[(m0 + c) * K + k] = arg;
     }
     __syncthreads();
 
@@ -161,12 +196,11 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
         const size_t ob = (size_t)n * O + o;
         int nv = 0;
         for (int c = 1; c < C; ++c) {
-            const size_t m = (size_t)n * C + c;
             for (int k = 0; k < s_counts[c]; ++k) {
-                if (t.peak_object[m * K + k] != o) continue;
+                if (s_obj[c * K + k] != o) continue;
                 if (nv < V) {
-                    t.votes[(ob * V + nv) * 2] = t.peak_vote[(m * K + k) * 2];
-                    t.votes[(ob * V + nv) * 2 + 1] = t.peak_vote[(m * K + k) * 2 + 1];
+                    t.votes[(ob * V + nv) * 2] = s_vote[(c * K + k) * 2];
+                    t.votes[(ob * V + nv) * 2 + 1] = s_vote[(c * K + k) * 2 + 1];
                 } else {
                     atomicOr(&s_flags, OKP_FLAG_VOTE_OVERFLOW);
                 }
@@ -176,64 +210,76 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
         t.n_votes[ob] = nv;
     }
 
-    // ---- per (object, map): resolve over-detection, then lift to 3D ----
+    // ---- per (object, map): resolve over-detection ----
+    float* kept_xy = stash ? s_kept_xy : t.kp_xy + (size_t)n * O * C * S * 2;
     for (int i = threadIdx.x; i < n_obj * C; i += THREADS) {
         const int o = i / C, c = i - o * C;
-        const size_t m = (size_t)n * C + c;
         const size_t oc = ((size_t)n * O + o) * C + c;
         const int limit = config.cfg[c];
+        const int* obj = s_obj + c * K;
+        const float* xy = s_xy + (size_t)c * K * 2;
         int cnt = 0;
-        for (int k = 0; k < s_counts[c]; ++k) cnt += (t.peak_object[m * K + k] == o);
+        for (int k = 0; k < s_counts[c]; ++k) cnt += (obj[k] == o);
         t.kp_assigned[oc] = cnt;
+        s_kept[i] = 0;
         if (cnt == 0) continue;                            // pipeline.py:150-152: empty array
         float pts[OKP_MAX_SLOTS][2];
         int ids[OKP_MAX_SLOTS];
         int kept = 0;
         if (cnt <= limit) {
             for (int k = 0; k < s_counts[c]; ++k)
-                if (t.peak_object[m * K + k] == o) {
+                if (obj[k] == o) {
                     ids[kept] = k;
-                    pts[kept][0] = t.peak_xy[(m * K + k) * 2];
-                    pts[kept][1] = t.peak_xy[(m * K + k) * 2 + 1];
+                    pts[kept][0] = xy[2 * k];
+                    pts[kept][1] = xy[2 * k + 1];
                     ++kept;
                 }
         } else if (limit == 1) {                           // pipeline.py:139-142: most confident detection
             int arg = -1;
             float best = 0.0f;
             for (int k = 0; k < s_counts[c]; ++k)
-                if (t.peak_object[m * K + k] == o) {
-                    const float conf = t.peak_conf[m * K + k];
+                if (obj[k] == o) {
+                    const float conf = s_conf[c * K + k];
                     if (arg < 0 || conf > best) { best = conf; arg = k; }   // first maximum, like np.argmax
                 }
             ids[0] = arg;
-            pts[0][0] = t.peak_xy[(m * K + arg) * 2];
-            pts[0][1] = t.peak_xy[(m * K + arg) * 2 + 1];
+            pts[0][0] = xy[2 * arg];
+            pts[0][1] = xy[2 * arg + 1];
             kept = 1;
             atomicOr(&s_flags, OKP_FLAG_ARGMAX_RESOLVED);
         } else {                                           // pipeline.py:143-148: cluster
             unsigned char members[OKP_MAX_PEAKS];
             int g = 0;
             for (int k = 0; k < s_counts[c]; ++k)
-                if (t.peak_object[m * K + k] == o) members[g++] = (unsigned char)k;
+                if (obj[k] == o) members[g++] = (unsigned char)k;
             kept = limit;
-            okp_cluster_detections(t.peak_xy + m * K * 2, members, g, kept, prm.kmeans_iterations, &pts[0][0]);
+            okp_cluster_detections(xy, members, g, kept, prm.kmeans_iterations, &pts[0][0]);
             for (int s = 0; s < kept; ++s) ids[s] = -1;
             atomicOr(&s_flags, OKP_FLAG_CLUSTERED);
         }
         t.kp_count[oc] = kept;
+        s_kept[i] = kept;
         for (int s = 0; s < kept; ++s) {
             t.kp_peak[oc * S + s] = ids[s];
             t.kp_xy[(oc * S + s) * 2] = pts[s][0];
             t.kp_xy[(oc * S + s) * 2 + 1] = pts[s][1];
-            if (have_camera) {
-                double p3[3];
-                okp_detection_to_point(pts[s][0], pts[s][1], depth + m * HW, H, W, cam, prm.compat_clip_bug, p3);
-                t.kp_point[(oc * S + s) * 3] = p3[0];
-                t.kp_point[(oc * S + s) * 3 + 1] = p3[1];
-                t.kp_point[(oc * S + s) * 3 + 2] = p3[2];
-            }
+            if (stash) { s_kept_xy[((size_t)i * S + s) * 2] = pts[s][0]; s_kept_xy[((size_t)i * S + s) * 2 + 1] = pts[s][1]; }
         }
     }
-    __syncthreads();
+    __syncthreads();                                       // also makes the kp_xy stores visible to the block (no stash)
+
+    // ---- lift every kept keypoint to 3D, one thread each (pipeline.py:164-171, 189-199) ----
+    if (have_camera) {
+        for (int i = threadIdx.x; i < n_obj * C * S; i += THREADS) {
+            const int ocl = i / S, s = i - ocl * S;        // ocl = o * C + c inside the frame
+            if (s >= s_kept[ocl]) continue;
+            const int c = ocl % C;
+            double p3[3];
+            okp_detection_to_point(kept_xy[((size_t)ocl * S + s) * 2], kept_xy[((size_t)ocl * S + s) * 2 + 1],
+                                   depth + (m0 + c) * HW, H, W, cam, prm.compat_clip_bug, p3);
+            double* out = t.kp_point + (((size_t)n * O * C + ocl) * S + s) * 3;
+            out[0] = p3[0]; out[1] = p3[1]; out[2] = p3[2];
+        }
+    }
     if (threadIdx.x == 0) { t.n_objects[n] = n_obj; t.flags[n] = s_flags; }
 }

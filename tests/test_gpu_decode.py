@@ -384,3 +384,23 @@ def test_bf16_peak_extraction_shapes_noise_and_overflow(H, W, N, C, K):
     np.testing.assert_array_equal(got['peak_yx'], want['peak_yx'])
     for key in ['peak_score', 'peak_xy', 'peak_conf']:
         np.testing.assert_array_equal(got[key].view(np.uint32), want[key].view(np.uint32), err_msg=key)
+
+
+def test_record_pack_kernel_equals_the_torch_packing():
+    """okp_pack_records_f64 (the pack / peer-store step of sharding.RecordExchange) against
+    sharding.record_tensor, on the tables of a real decode; several exchanges through the slot ring."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic, sharding
+    cfg = [1, 3]
+    batch = synthetic.make_batch(21, cfg, (64, 64), seed=17, objects=(1, 3))
+    decoder = KeypointDecoder(cfg, (64, 64), camera=synthetic.default_camera((64, 64)))
+    tables = decoder.decode_batch(batch.heat, batch.depth, batch.centers)
+    exchange = sharding.RecordExchange(tables, world=1, rank=0)
+    assert exchange.transport == 'local' and exchange.R == 2 + 16 * 3 + 16 * 3 * 3 * 3
+    want = sharding.record_tensor(tables)
+    for _ in range(4):
+        got, done = exchange.exchange(tables)
+        done.synchronize()
+        assert torch.equal(got, want)
+    back = sharding.unpack_records(got, tables)
+    assert torch.equal(back['kp_point'], tables['kp_point']) and torch.equal(back['n_objects'], tables['n_objects'])
