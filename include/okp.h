@@ -9,7 +9,8 @@
  *   - plain C types only; every buffer is owned and sized by the caller (PyTorch in this
  *     repo); the library allocates nothing and keeps no global state;
  *   - pointers named *_dev / inside OkpDecodeTables are DEVICE pointers; keypoint_config,
- *     OkpCamera and OkpDecodeParams are read on the HOST at call time;
+ *     OkpCamera and OkpDecodeParams are read on the HOST at call time; every table array starts
+ *     on a 16-byte boundary (OKP_E_UNSUPPORTED otherwise);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default
  *     stream) and the call returns without synchronising;
  *   - return value: OKP_OK or a negative OKP_E_* code (okp_strerror). Data-dependent

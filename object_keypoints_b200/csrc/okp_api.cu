@@ -7,6 +7,7 @@
 #include "okp_common.cuh"
 #include "okp_peaks.cuh"
 #include "okp_peaks_strip.cuh"
+#include "okp_peaks_stream.cuh"
 #include "okp_geometry.cuh"
 #include "okp_group.cuh"
 #include "okp_dlt.cuh"
@@ -121,6 +122,9 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     if (!tables->peak_count || !tables->peak_yx || !tables->peak_score || !tables->peak_xy || !tables->peak_conf ||
         !tables->peak_object || !tables->peak_vote)
         return OKP_E_NULL;
+    // the table writers use 8- and 16-byte vector stores (int2 / float2 / double2 rows)
+    if (((uintptr_t)tables->peak_yx & 7u) || ((uintptr_t)tables->peak_xy & 7u) || ((uintptr_t)tables->peak_vote & 15u))
+        return OKP_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     const int K = params->max_peaks;
     const int maps = N * C;
@@ -133,7 +137,14 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     OkpPeakRecord* tile_peaks = (OkpPeakRecord*)(base + align_up(tiles * sizeof(int32_t), 256));
 
     if (strip) {
-        rc = okp_strip_launch<T>(heat_dev, p.sp, params->threshold, *tables, s);
+        // persistent warp-specialised form by default; OKP_PEAKS_KERNEL=strip selects the one-shot kernel (A/B, tuning)
+        OkpStreamPlan stream_plan;
+        const char* which = getenv("OKP_PEAKS_KERNEL");
+        const bool one_shot = which && strcmp(which, "strip") == 0;
+        if (!one_shot && okp_stream_plan(maps, H, W, K, (int)sizeof(T), &stream_plan))
+            rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, s);
+        else
+            rc = okp_strip_launch<T>(heat_dev, p.sp, params->threshold, *tables, s);
         if (rc != OKP_OK) return rc;
         // maps with more than K peaks ("first K in raster order") are redone here; a no-op otherwise
         auto kernel = okp_peaks_overflow_kernel<256, T>;

@@ -1,0 +1,370 @@
+// okp_peaks_stream.cuh -- persistent, warp-specialised form of the strip kernel (okp_peaks_strip.cuh).
+//
+// Same arithmetic (okp_strip_step / okp_strip_batch, the bounded filter + exact check) and the same
+// shared-memory stage layout, different control flow. The one-shot kernel gives every group of M maps its
+// own CTA: mbarrier set-up, a pipeline fill, the streaming phase, and then an epilogue (exact box sums of
+// the candidates, ordering, table writes) during which the CTA's TMA pipeline is empty and its compute
+// warps are idle at four __syncthreads. At 180x320 that is ~8 % of a CTA's life, at the network's 64x64
+// (14 row batches per map) it is half of it (profiles/r01f_k1_ncu.md: 0.38 of the HBM peak).
+//
+// Here a CTA is resident for the whole launch and walks over groups g = blockIdx.x, + gridDim.x, ...:
+//   * the producer lane streams the batches of consecutive groups back to back (the ring of NS stages
+//     never drains between groups);
+//   * the compute warps go from the last batch of a group straight into the first batch of the next; their
+//     candidates go into one of two candidate buffers;
+//   * epilogue warps consume a finished buffer (exact sums from L2, undecided neighbours, raster ranks,
+//     table writes) WHILE the compute warps stream the next group. Hand-over is one mbarrier arrive per
+//     warp per group (cand_full / cand_free), not per row batch, so it costs nothing (the r01b design paid
+//     42 % of its issue slots for per-batch hand-over spins).
+#pragma once
+#include "okp_peaks_strip.cuh"
+
+struct OkpStreamPlan {
+    OkpStripPlan s;               // geometry, M, NS, stage layout (smem offsets below replace s.off_*)
+    int groups;                   // ceil(maps / M)
+    int EW;                       // epilogue warps
+    int off_pending[2], off_count[2];   // candidate lists and [n_pending[M], redo[M]] per buffer
+    int off_peaks, off_items, off_misc, off_mbar;
+    int smem_bytes;
+    int threads;                  // compute warps + producer warp + epilogue warps
+};
+
+__device__ __forceinline__ void okp_named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(OKP_STRIP_MAX_THREADS, 1)
+okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ heat, OkpStreamPlan sp,
+                        float threshold, float thr_lo, OkpDecodeTables t) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int RB = OKP_STRIP_RB;
+    const OkpStripPlan& p = sp.s;
+    const int NS = p.NS;
+    OkpStripPeak* peaks = reinterpret_cast<OkpStripPeak*>(smem + sp.off_peaks);                // [M][PK] (epilogue only)
+    uint32_t* items = reinterpret_cast<uint32_t*>(smem + sp.off_items);                        // [IC]
+    int* n_peaks = reinterpret_cast<int*>(smem + sp.off_misc);                                 // [M]
+    int* n_items = n_peaks + p.M;                                                              // [1]
+    int* cand_start = n_items + 1;                                                             // [M + 1] prefix of candidate counts
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.off_mbar);       // [NS] TMA landed
+    uint64_t* done = full + OKP_STRIP_MAX_NS;                               // [NS] compute warps finished the batch
+    uint64_t* cand_full = done + OKP_STRIP_MAX_NS;                          // [2] candidate buffer complete
+    uint64_t* cand_free = cand_full + 2;                                    // [2] epilogue finished with the buffer
+
+    const int tid = threadIdx.x;
+    const int H = p.H, W = p.W;
+    const int compute_warps = (p.threads + 31) >> 5;
+    const int warp = tid >> 5;
+
+    for (int b = 0; b < 2; ++b) {
+        int* count = reinterpret_cast<int*>(smem + sp.off_count[b]);
+        for (int i = tid; i < 2 * p.M; i += blockDim.x) count[i] = 0;
+    }
+    for (int i = tid; i < p.M + 1; i += blockDim.x) n_peaks[i] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { okp_mbar_init(full + i, 1); okp_mbar_init(done + i, compute_warps); }
+        for (int i = 0; i < 2; ++i) { okp_mbar_init(cand_full + i, compute_warps); okp_mbar_init(cand_free + i, sp.EW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int my_groups = blockIdx.x < sp.groups ? (sp.groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    if (warp == compute_warps) {
+        // ------------------------------- producer: one lane, batches of consecutive groups back to back ---
+        if ((tid & 31) == 0) {
+            const CUtensorMap* tmap_ptr = &tmap;
+            int stage = 0;
+            uint32_t parity = 0;
+            long long q = 0;
+            for (int it = 0; it < my_groups; ++it) {
+                const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
+                for (int b = 0; b < p.nb; ++b, ++q) {
+                    if (q >= NS) {
+                        while (!okp_mbar_try_wait(done + stage, parity)) __nanosleep(64);
+                    }
+                    uint64_t* bar = full + stage;
+                    unsigned char* dst = smem + (size_t)stage * p.stage_bytes;
+                    okp_mbar_expect_tx(bar, (uint32_t)(p.halves * p.half_bytes));
+                    okp_tma_load_3d(dst, tmap_ptr, -4 - p.lead[0], b * RB - 2, first_map, bar);
+                    if (p.halves == 2)
+                        okp_tma_load_3d(dst + p.half_stride, tmap_ptr, 4 * p.half_strips - 4 - p.lead[1], b * RB - 2, first_map, bar);
+                    if (++stage == NS) { stage = 0; if (q >= NS) parity ^= 1u; }
+                }
+            }
+        }
+    } else if (warp < compute_warps) {
+        // ------------------------------- compute warps: the stream ---------------------------------------
+        const bool active = tid < p.threads;
+        const int ct = active ? tid : p.threads - 1;
+        const int mm = ct / p.strips;
+        const int s = ct - mm * p.strips;
+        const int half = s >= p.half_strips ? 1 : 0;
+        OkpStripLane L;
+        L.H = H; L.W = W; L.thr_lo = thr_lo; L.PK = p.PK;
+        L.xs = 4 * s;
+        L.vmask = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) L.vmask |= (L.xs + c - 2 >= 0 && L.xs + c - 2 < W) ? (1u << c) : 0u;
+        if (!active) L.vmask = 0;
+        if (active && (tid & 31) > 0 && s > 0) L.vmask |= 16u;
+        if (active && (tid & 31) < 31 && s + 1 < p.strips && tid + 1 < p.threads) L.vmask |= 32u;
+        const int thread_raw = half * p.half_stride +
+                               (mm * RB * p.BW + p.lead[half] + 4 * (s - half * p.half_strips)) * (int)sizeof(T);
+        const int row_pitch = p.BW * (int)sizeof(T);
+        int stage = 0;
+        uint32_t full_parity = 0;
+        for (int it = 0; it < my_groups; ++it) {
+            const int buf = it & 1;
+            if (it >= 2) okp_mbar_wait(cand_free + buf, (uint32_t)(((it >> 1) - 1) & 1));   // the epilogue released the buffer
+            int* count = reinterpret_cast<int*>(smem + sp.off_count[buf]);
+            L.pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]) + (size_t)mm * p.PK;
+            L.n_pending = count + mm;
+            float pr[5][4], hp[4], sv[5][4];
+            uint32_t sign = 0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { pr[i][j] = 0.0f; sv[i][j] = -INFINITY; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hp[j] = 0.0f;
+            for (int b = 0; b < p.nb; ++b) {
+                okp_mbar_wait(full + stage, full_parity);
+                const unsigned char* raw = smem + (size_t)stage * p.stage_bytes + thread_raw;
+                const int y0 = b * RB - 4;
+                if (b >= 2 && y0 + 4 < H)
+                    okp_strip_batch<false, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
+                else
+                    okp_strip_batch<true, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
+                __syncwarp();
+                if ((tid & 31) == 0) okp_mbar_arrive(done + stage);
+                if (++stage == NS) { stage = 0; full_parity ^= 1u; }
+            }
+            if (active && (sign >> 31)) count[p.M + mm] = 1;          // redo: benign race, every writer stores 1
+            __syncwarp();
+            if ((tid & 31) == 0) okp_mbar_arrive(cand_full + buf);
+        }
+    } else {
+        // ------------------------------- epilogue warps: one finished candidate buffer at a time ---------
+        const int et = tid - (compute_warps + 1) * 32;                // thread index among the epilogue warps
+        const int ethreads = sp.EW * 32;
+        for (int it = 0; it < my_groups; ++it) {
+            const int buf = it & 1;
+            const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
+            okp_mbar_wait(cand_full + buf, (uint32_t)((it >> 1) & 1));
+            OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]);
+            int* n_pending = reinterpret_cast<int*>(smem + sp.off_count[buf]);
+            int* redo = n_pending + p.M;
+
+            // candidates are few and sit at the front of each map's list: index them densely so that every
+            // lane has one (all loads of a pass in flight together) instead of walking M * PK mostly empty slots
+            if (et == 0) {
+                int at = 0;
+                for (int mm = 0; mm < p.M; ++mm) {
+                    cand_start[mm] = at;
+                    at += first_map + mm < p.maps ? okp_min(n_pending[mm], p.PK) : 0;
+                }
+                cand_start[p.M] = at;
+            }
+            okp_named_barrier(1, ethreads);
+            const int candidates = cand_start[p.M];
+
+            // A: exact box sum (the reference's raster-order adds) and centroid of every candidate
+            for (int idx = et; idx < candidates; idx += ethreads) {
+                int lo = 0, hi = p.M;                                 // last mm with cand_start[mm] <= idx
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
+                const int mm = lo, i = mm * p.PK + (idx - cand_start[mm]);
+                OkpStripPeak pk;
+                pk.key = -1; pk.score = 0.0f; pk.cx = 0.0f; pk.cy = 0.0f; pk.conf = 0.0f;
+                {
+                    const OkpStripCandidate cd = pending[i];
+                    const int y = cd.key / W, x = cd.key - y * W;
+                    const T* src = heat + (size_t)(first_map + mm) * H * W;
+                    float q[25];
+#pragma unroll
+                    for (int k = 0; k < 25; ++k) {
+                        const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+                        const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+                        q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;
+                    }
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 25; ++k) sum = __fadd_rn(sum, q[k]);
+                    if (sum > threshold) {
+                        float sy = 0.0f, sx = 0.0f, spr = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 25; ++k) {
+                            const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+                            const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+                            if (in) {
+                                sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
+                                sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
+                                spr = __fadd_rn(spr, q[k]);
+                            }
+                        }
+                        pk.key = cd.key;
+                        pk.score = sum;
+                        pk.cx = __fdiv_rn(sx, spr);
+                        pk.cy = __fdiv_rn(sy, spr);
+                        pk.conf = spr;
+                        uint32_t ties = cd.ties;
+                        ties &= (y >= 2 ? 0x1Fu : 0u) | (y >= 1 ? 0x3E0u : 0u) | 0x6C00u | (y + 1 < H ? 0xF8000u : 0u) | (y + 2 < H ? 0x1F00000u : 0u);
+                        ties &= (x >= 2 ? 0x108421u : 0u) | (x >= 1 ? 0x210842u : 0u) | 0x421084u | (x + 1 < W ? 0x842108u : 0u) | (x + 2 < W ? 0x1084210u : 0u);
+                        if (ties) {
+                            const int at = atomicAdd(n_items, __popc(ties));
+                            if (at + __popc(ties) > p.IC) {
+                                redo[mm] = 1;
+                                for (int n = at; n < p.IC; ++n) items[n] = 0xFFFFFFFFu;
+                            } else {
+                                int n = at;
+                                while (ties) {
+                                    const int k = __ffs(ties) - 1;
+                                    ties &= ties - 1;
+                                    items[n++] = ((uint32_t)i << 5) | (uint32_t)k;
+                                }
+                            }
+                        }
+                    }
+                }
+                peaks[i] = pk;
+            }
+            okp_named_barrier(1, ethreads);
+
+            // B: undecided neighbours -- exact box sum against the candidate's
+            {
+                const int total_items = okp_min(*n_items, p.IC);
+                for (int n = et; n < total_items; n += ethreads) {
+                    const uint32_t item = items[n];
+                    if (item == 0xFFFFFFFFu) continue;
+                    const int i = (int)(item >> 5), k = (int)(item & 31u);
+                    const int mm = i / p.PK;
+                    const int key = pending[i].key;
+                    const int y = key / W, x = key - y * W;
+                    const T* src = heat + (size_t)(first_map + mm) * H * W;
+                    if (okp_exact_box_sum<T>(src, H, W, y + k / 5 - 2, x + k % 5 - 2) > peaks[i].score) peaks[i].key = -1;
+                }
+            }
+            okp_named_barrier(1, ethreads);
+            for (int idx = et; idx < candidates; idx += ethreads) {
+                int lo = 0, hi = p.M;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
+                if (peaks[lo * p.PK + (idx - cand_start[lo])].key >= 0) atomicAdd(n_peaks + lo, 1);
+            }
+            okp_named_barrier(1, ethreads);
+
+            // C: raster order (rank by key), final tables, unused slots cleared
+            for (int i = et; i < p.M * p.K; i += ethreads) {
+                const int mm = i / p.K, slot = i - mm * p.K;
+                const int map = first_map + mm;
+                if (map >= p.maps) continue;
+                const int total = (redo[mm] || n_pending[mm] > p.PK) ? p.K + 1 : n_peaks[mm];
+                if (slot == 0) t.peak_count[map] = total;
+                if (total > p.K) continue;
+                const size_t dst = (size_t)map * p.K + slot;
+                t.peak_object[dst] = -1;
+                reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
+                if (slot >= total) {
+                    reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(-1, -1);
+                    t.peak_score[dst] = 0.0f;
+                    reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(0.0f, 0.0f);
+                    t.peak_conf[dst] = 0.0f;
+                }
+            }
+            for (int idx = et; idx < candidates; idx += ethreads) {
+                int lo = 0, hi = p.M;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
+                const int mm = lo, i = mm * p.PK + (idx - cand_start[mm]);
+                const OkpStripPeak pk = peaks[i];
+                if (pk.key < 0) continue;
+                if (redo[mm] || n_pending[mm] > p.PK || n_peaks[mm] > p.K) continue;
+                const OkpStripPeak* mine = peaks + (size_t)mm * p.PK;
+                const int np = n_pending[mm];
+                int rank = 0;
+                for (int j = 0; j < np; ++j) { const int kj = mine[j].key; rank += (kj >= 0 && kj < pk.key); }
+                const size_t dst = (size_t)(first_map + mm) * p.K + rank;
+                const int y = pk.key / W;
+                reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(y, pk.key - y * W);
+                t.peak_score[dst] = pk.score;
+                reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(pk.cx, pk.cy);
+                t.peak_conf[dst] = pk.conf;
+            }
+            okp_named_barrier(1, ethreads);
+            // hand the buffer back, cleared
+            for (int i = et; i < 2 * p.M; i += ethreads) n_pending[i] = 0;
+            for (int i = et; i < p.M + 1; i += ethreads) n_peaks[i] = 0;
+            okp_named_barrier(1, ethreads);
+            if ((et & 31) == 0) okp_mbar_arrive(cand_free + buf);
+        }
+    }
+}
+
+static inline bool okp_stream_plan(int maps, int H, int W, int K, int esize, OkpStreamPlan* out) {
+    OkpStreamPlan sp;
+    memset(&sp, 0, sizeof(sp));
+    if (!okp_strip_plan(maps, H, W, K, esize, &sp.s)) return false;
+    OkpStripPlan& p = sp.s;
+    // two epilogue warps where they fit beside the compute warps in 320 threads (two CTAs per SM at 96 registers), else
+    // one: small maps (64x64: 14 row batches per group) finish a group every few microseconds (sweep: profiles/r01k)
+    const int compute_threads = (sp.s.threads + 31) / 32 * 32;
+    sp.EW = okp_env_int("OKP_STREAM_EPILOGUE_WARPS", 1, 4, compute_threads + 32 + 64 <= 320 ? 2 : 1);
+    // the second candidate buffer costs PK * 8 bytes per map: give it back from the per-CTA budget by re-planning M
+    const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;
+    const int compute_limit = OKP_STRIP_MAX_THREADS - 32 - sp.EW * 32;
+    for (;;) {
+        int off = p.NS * p.stage_bytes;
+        for (int b = 0; b < 2; ++b) { sp.off_pending[b] = off; off += p.M * p.PK * (int)sizeof(OkpStripCandidate); }
+        sp.off_peaks = off; off += p.M * p.PK * (int)sizeof(OkpStripPeak);
+        sp.off_items = off; off += p.IC * 4;
+        for (int b = 0; b < 2; ++b) { sp.off_count[b] = off; off += 2 * p.M * 4; }
+        sp.off_misc = off; off += (2 * p.M + 2) * 4;
+        off = okp_round_up_int(off, 8);
+        sp.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 4) * 8;
+        sp.smem_bytes = off;
+        if ((off <= budget && p.threads <= compute_limit) || p.M == 1) break;
+        --p.M;                                             // shrink the group until it fits
+        p.threads = p.M * p.strips;
+        p.IC = p.M * 64;
+        p.half_bytes = p.M * OKP_STRIP_RB * p.BW * esize;
+        p.half_stride = okp_round_up_int(p.half_bytes, 128);
+        p.stage_bytes = p.halves * p.half_stride;
+    }
+    if (sp.smem_bytes > 224 * 1024 || p.threads > compute_limit) return false;
+    sp.groups = (maps + p.M - 1) / p.M;
+    sp.threads = (p.threads + 31) / 32 * 32 + 32 + sp.EW * 32;
+    *out = sp;
+    return true;
+}
+
+template <typename T>
+static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, float threshold,
+                                    const OkpDecodeTables& tables, cudaStream_t stream) {
+    const OkpStripPlan& p = sp.s;
+    OkpEncodeTiledFn encode = okp_encode_tiled_fn();
+    if (!encode) return OKP_E_CUDA;
+    if (((uintptr_t)heat & 15u) != 0) return OKP_E_UNSUPPORTED;
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.maps};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(T), (cuuint64_t)p.W * p.H * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)p.BW, (cuuint32_t)OKP_STRIP_RB, (cuuint32_t)p.M};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    const CUtensorMapDataType dtype = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUresult r = encode(&tmap, dtype, 3, (void*)heat, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return OKP_E_CUDA;
+    auto kernel = okp_peaks_stream_kernel<T>;
+    OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.smem_bytes));
+    int per_sm = 0;
+    OKP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, sp.threads, sp.smem_bytes));
+    if (per_sm < 1) return OKP_E_UNSUPPORTED;
+    int device = 0, sms = 148;
+    OKP_CUDA_CHECK(cudaGetDevice(&device));
+    OKP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    long long grid = (long long)per_sm * sms;               // persistent: every CTA resident, groups dealt round-robin
+    if (grid > sp.groups) grid = sp.groups;
+    const float thr_lo = threshold - OKP_STRIP_THRESHOLD_SLACK * fabsf(threshold);
+    kernel<<<(unsigned)grid, sp.threads, sp.smem_bytes, stream>>>(tmap, heat, sp, threshold, thr_lo, tables);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}

@@ -17,8 +17,8 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_r
 timeout 600 python tools/bench_config5.py 256 5 > $out/config5.json 2> $out/config5.err; tail -2 $out/config5.err; cat $out/config5.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:okp_ -c 60 --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-frames 256 --e2e-steps 1 > $out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:okp_peaks_strip -s 2 -c 1 -o $out/prof_k1_f32 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:okp_peaks_st -s 2 -c 1 -o $out/prof_k1_f32 \
     python tools/bench_k1.py 180x320 4096 2 f32 > $out/ncu_full_f32.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:okp_peaks_strip -s 2 -c 1 -o $out/prof_k1_bf16 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:okp_peaks_st -s 2 -c 1 -o $out/prof_k1_bf16 \
     python tools/bench_k1.py 180x320 4096 2 bf16 > $out/ncu_full_bf16.log 2>&1
 ls -la $out
