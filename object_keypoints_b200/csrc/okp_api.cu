@@ -194,12 +194,16 @@ int group_objects(const T* depth_dev, const T* centers_dev, int N, int C, int H,
     if (camera) cam = *camera;
     const int K = params->max_peaks, O = params->max_objects;
     bool stash = true;
-    size_t smem = okp_group_smem_bytes(C, K, O, S, true);
-    if (smem > 160 * 1024) { stash = false; smem = okp_group_smem_bytes(C, K, O, S, false); }
-    auto kernel = okp_group_kernel<128, T>;
+    size_t per_frame = okp_group_smem_bytes(C, K, O, S, true);
+    if (per_frame > 160 * 1024) { stash = false; per_frame = okp_group_smem_bytes(C, K, O, S, false); }
+    int warps = (int)((size_t)(48 * 1024) / per_frame);          // frames per CTA: one warp each
+    if (warps > 4) warps = 4;
+    if (warps < 1) warps = 1;
+    const size_t smem = per_frame * warps;
+    auto kernel = okp_group_kernel<T>;
     if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<N, 128, smem, (cudaStream_t)stream>>>(depth_dev, centers_dev, N, C, H, W, config, cam, camera != nullptr,
-                                                   *params, S, stash ? 1 : 0, *tables);
+    kernel<<<(N + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
+        depth_dev, centers_dev, N, C, H, W, config, cam, camera != nullptr, *params, S, stash ? 1 : 0, (int)per_frame, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

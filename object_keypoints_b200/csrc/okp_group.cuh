@@ -78,43 +78,53 @@ __device__ __noinline__ void okp_cluster_detections(const float* __restrict__ xy
 #undef OKP_PT
 }
 
-// Shared-memory budget of okp_group_kernel for a problem size (bytes); `stash` = the kept keypoints are also
+// Shared-memory bytes ONE frame (= one warp) of okp_group_kernel needs; `stash` = the kept keypoints are also
 // held in shared memory for the 3D lift (dropped when the worst-case capacities would not fit).
 static inline size_t okp_group_smem_bytes(int C, int K, int O, int S, bool stash) {
-    size_t bytes = (size_t)C * K * (2 * sizeof(double) + 2 * sizeof(float) + sizeof(float) + sizeof(int));
+    size_t bytes = (size_t)O * 2 * sizeof(double);                                                  // centres
+    bytes += (size_t)C * K * (2 * sizeof(double) + 2 * sizeof(float) + sizeof(float) + sizeof(int));
     bytes += (size_t)O * C * sizeof(int);
     if (stash) bytes += (size_t)O * C * S * 2 * sizeof(float);
-    return bytes;
+    bytes += (OKP_MAX_MAPS + 1) * sizeof(int);                                                      // counts, flags
+    return (bytes + 15) / 16 * 16;
 }
 
-// Latency is what this kernel is made of (a frame is ~40 peaks): the frame's peak records are pulled into
-// shared memory with ONE round trip, every later phase works on shared memory, and results leave as
-// fire-and-forget stores. Global round trips on the critical path: counts -> records -> centre-vector
-// gather -> depth gather.
-template <int THREADS, typename E>
-__global__ void __launch_bounds__(THREADS)
+// Latency is what this kernel is made of (a frame is ~40 peaks, and every 3D lift is a serial float64
+// Newton + tan chain of a few microseconds): ONE WARP PER FRAME, several frames per CTA, so that an SM holds
+// 64 frames whose chains overlap (the CTA-per-frame form held 16 and took 4x longer). The frame's peak
+// records are pulled into shared memory with one round trip, every later phase works on shared memory, and
+// results leave as fire-and-forget stores. Global round trips on the critical path: counts -> records ->
+// centre-vector gather -> depth gather. No block-level barrier anywhere: warps are independent.
+template <typename E>
+__global__ void __launch_bounds__(128)
 okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int N, int C, int H, int W,
-                 OkpConfig config, OkpCamera cam, int have_camera, OkpDecodeParams prm, int S, int stash, OkpDecodeTables t) {
-    const int n = blockIdx.x;
+                 OkpConfig config, OkpCamera cam, int have_camera, OkpDecodeParams prm, int S, int stash,
+                 int frame_smem_bytes, OkpDecodeTables t) {
+    constexpr int THREADS = 32;                            // a frame's team: the strides below
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= N) return;
     const int K = prm.max_peaks, O = prm.max_objects, V = prm.max_votes, T = C - 1;
     const size_t HW = (size_t)H * W;
     extern __shared__ __align__(16) unsigned char group_smem[];
-    double* s_vote = reinterpret_cast<double*>(group_smem);                 // [C][K][2] predicted centre of a spoke peak
+    unsigned char* mine = group_smem + (size_t)(threadIdx.x >> 5) * frame_smem_bytes;
+    double (*s_center)[2] = reinterpret_cast<double (*)[2]>(mine);          // [O][2]
+    double* s_vote = reinterpret_cast<double*>(mine) + (size_t)O * 2;       // [C][K][2] predicted centre of a spoke peak
     float* s_xy = reinterpret_cast<float*>(s_vote + (size_t)C * K * 2);     // [C][K][2] centroid (x, y)
     float* s_conf = s_xy + (size_t)C * K * 2;                               // [C][K]
     int* s_obj = reinterpret_cast<int*>(s_conf + (size_t)C * K);            // [C][K]    object of a peak, -1 = none
     int* s_kept = s_obj + (size_t)C * K;                                    // [O][C]    keypoints kept per (object, map)
-    float* s_kept_xy = reinterpret_cast<float*>(s_kept + (size_t)O * C);    // [O][C][S][2] (only with stash)
-    __shared__ double s_center[OKP_MAX_OBJECTS][2];
-    __shared__ unsigned int s_flags;
-    __shared__ int s_counts[OKP_MAX_MAPS];
+    int* s_counts = s_kept + (size_t)O * C;                                 // [OKP_MAX_MAPS]
+    unsigned int* s_flags_ptr = reinterpret_cast<unsigned int*>(s_counts + OKP_MAX_MAPS);
+    float* s_kept_xy = reinterpret_cast<float*>(s_flags_ptr + 1);           // [O][C][S][2] (only with stash)
+#define s_flags (*s_flags_ptr)
 
     const size_t m0 = (size_t)n * C;
-    if (threadIdx.x == 0) s_flags = 0;
-    if (threadIdx.x < C) {
-        const int c = t.peak_count[m0 + threadIdx.x];
-        s_counts[threadIdx.x] = c < K ? c : K;
+    if (lane == 0) s_flags = 0;
+    __syncwarp();
+    if (lane < C) {
+        const int c = t.peak_count[m0 + lane];
+        s_counts[lane] = c < K ? c : K;
         if (c > K) atomicOr(&s_flags, OKP_FLAG_PEAK_OVERFLOW);
     }
     // reset this frame's object tables (flat, coalesced; every region is contiguous per frame)
@@ -122,31 +132,31 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
         const int oc = O * C, ocs = oc * S;
         int32_t* assigned = t.kp_assigned + (size_t)n * oc;
         int32_t* count = t.kp_count + (size_t)n * oc;
-        for (int i = threadIdx.x; i < oc; i += THREADS) { assigned[i] = 0; count[i] = 0; }
+        for (int i = lane; i < oc; i += THREADS) { assigned[i] = 0; count[i] = 0; }
         int32_t* peak = t.kp_peak + (size_t)n * ocs;
-        for (int i = threadIdx.x; i < ocs; i += THREADS) peak[i] = -1;
+        for (int i = lane; i < ocs; i += THREADS) peak[i] = -1;
         float* xy = t.kp_xy + (size_t)n * ocs * 2;
-        for (int i = threadIdx.x; i < ocs * 2; i += THREADS) xy[i] = 0.0f;
+        for (int i = lane; i < ocs * 2; i += THREADS) xy[i] = 0.0f;
         double* point = t.kp_point + (size_t)n * ocs * 3;
-        for (int i = threadIdx.x; i < ocs * 3; i += THREADS) point[i] = 0.0;
+        for (int i = lane; i < ocs * 3; i += THREADS) point[i] = 0.0;
         int32_t* nv = t.n_votes + (size_t)n * O;
-        for (int i = threadIdx.x; i < O; i += THREADS) nv[i] = 0;
+        for (int i = lane; i < O; i += THREADS) nv[i] = 0;
         double* votes = t.votes + (size_t)n * O * V * 2;
-        for (int i = threadIdx.x; i < O * V * 2; i += THREADS) votes[i] = 0.0;
+        for (int i = lane; i < O * V * 2; i += THREADS) votes[i] = 0.0;
     }
-    __syncthreads();
+    __syncwarp();
 
     const int n_center = s_counts[0];
     if (n_center == 0) {                                   // pipeline.py:105-106
-        if (threadIdx.x == 0) { t.n_objects[n] = 0; t.flags[n] = s_flags | OKP_FLAG_NO_CENTERS; }
+        if (lane == 0) { t.n_objects[n] = 0; t.flags[n] = s_flags | OKP_FLAG_NO_CENTERS; }
         return;
     }
     const int n_obj = n_center < O ? n_center : O;
-    if (threadIdx.x == 0 && n_center > O) atomicOr(&s_flags, OKP_FLAG_OBJECT_OVERFLOW);
+    if (lane == 0 && n_center > O) atomicOr(&s_flags, OKP_FLAG_OBJECT_OVERFLOW);
 
     // ---- the frame's peak records into shared memory (one round trip); spoke peaks fetch their centre vector
     // in the same pass and vote as soon as the centres are known ----
-    for (int i = threadIdx.x; i < C * K; i += THREADS) {
+    for (int i = lane; i < C * K; i += THREADS) {
         const int c = i / K, k = i - c * K;
         if (k >= s_counts[c]) continue;
         const size_t s = (m0 + c) * K + k;
@@ -168,10 +178,10 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
             t.peak_vote[2 * s + 1] = vy;
         }
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- spoke peaks vote for a centre (pipeline.py:115-128) ----
-    for (int i = K + threadIdx.x; i < C * K; i += THREADS) {
+    for (int i = K + lane; i < C * K; i += THREADS) {
         const int c = i / K, k = i - c * K;
         if (k >= s_counts[c]) continue;
         const double vx = s_vote[2 * i], vy = s_vote[2 * i + 1];
@@ -189,10 +199,10 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
         s_obj[i] = arg;
         t.peak_object[(m0 + c) * K + k] = arg;
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- votes per object, in assignment order (type-major, raster order inside a type) ----
-    for (int o = threadIdx.x; o < n_obj; o += THREADS) {
+    for (int o = lane; o < n_obj; o += THREADS) {
         const size_t ob = (size_t)n * O + o;
         int nv = 0;
         for (int c = 1; c < C; ++c) {
@@ -212,7 +222,7 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
 
     // ---- per (object, map): resolve over-detection ----
     float* kept_xy = stash ? s_kept_xy : t.kp_xy + (size_t)n * O * C * S * 2;
-    for (int i = threadIdx.x; i < n_obj * C; i += THREADS) {
+    for (int i = lane; i < n_obj * C; i += THREADS) {
         const int o = i / C, c = i - o * C;
         const size_t oc = ((size_t)n * O + o) * C + c;
         const int limit = config.cfg[c];
@@ -266,11 +276,11 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
             if (stash) { s_kept_xy[((size_t)i * S + s) * 2] = pts[s][0]; s_kept_xy[((size_t)i * S + s) * 2 + 1] = pts[s][1]; }
         }
     }
-    __syncthreads();                                       // also makes the kp_xy stores visible to the block (no stash)
+    __syncwarp();                                       // also makes the kp_xy stores visible to the block (no stash)
 
     // ---- lift every kept keypoint to 3D, one thread each (pipeline.py:164-171, 189-199) ----
     if (have_camera) {
-        for (int i = threadIdx.x; i < n_obj * C * S; i += THREADS) {
+        for (int i = lane; i < n_obj * C * S; i += THREADS) {
             const int ocl = i / S, s = i - ocl * S;        // ocl = o * C + c inside the frame
             if (s >= s_kept[ocl]) continue;
             const int c = ocl % C;
@@ -281,5 +291,7 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
             out[0] = p3[0]; out[1] = p3[1]; out[2] = p3[2];
         }
     }
-    if (threadIdx.x == 0) { t.n_objects[n] = n_obj; t.flags[n] = s_flags; }
+    __syncwarp();
+    if (lane == 0) { t.n_objects[n] = n_obj; t.flags[n] = s_flags; }
+#undef s_flags
 }

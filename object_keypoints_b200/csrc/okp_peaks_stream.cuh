@@ -183,25 +183,44 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
                     const int y = cd.key / W, x = cd.key - y * W;
                     const T* src = heat + (size_t)(first_map + mm) * H * W;
                     float q[25];
+                    // almost every candidate is an interior pixel: 25 unconditional loads at constant offsets
+                    // (a fifth of the instructions of the border-checked form, which matters because the
+                    // epilogue warps are latency-bound: profiles/r01m_k1_64x64_ncu.md)
+                    const bool interior = y >= 2 && y + 2 < H && x >= 2 && x + 2 < W;
+                    if (interior) {
+                        const T* corner = src + (size_t)(y - 2) * W + (x - 2);
 #pragma unroll
-                    for (int k = 0; k < 25; ++k) {
-                        const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                        const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                        q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;
+                        for (int k = 0; k < 25; ++k) q[k] = okp_ld<T>(corner + (size_t)(k / 5) * W + k % 5);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 25; ++k) {
+                            const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+                            const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+                            q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;
+                        }
                     }
                     float sum = 0.0f;
 #pragma unroll
                     for (int k = 0; k < 25; ++k) sum = __fadd_rn(sum, q[k]);
                     if (sum > threshold) {
                         float sy = 0.0f, sx = 0.0f, spr = 0.0f;
+                        if (interior) {                           // same operations in the same order, nothing masked
 #pragma unroll
-                        for (int k = 0; k < 25; ++k) {
-                            const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                            const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                            if (in) {
-                                sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
-                                sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
+                            for (int k = 0; k < 25; ++k) {
+                                sy = __fadd_rn(sy, __fmul_rn(q[k], (float)(y + k / 5 - 2)));
+                                sx = __fadd_rn(sx, __fmul_rn(q[k], (float)(x + k % 5 - 2)));
                                 spr = __fadd_rn(spr, q[k]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 25; ++k) {
+                                const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+                                const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+                                if (in) {
+                                    sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
+                                    sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
+                                    spr = __fadd_rn(spr, q[k]);
+                                }
                             }
                         }
                         pk.key = cd.key;
@@ -255,21 +274,21 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
             okp_named_barrier(1, ethreads);
 
             // C: raster order (rank by key), final tables, unused slots cleared
-            for (int i = et; i < p.M * p.K; i += ethreads) {
-                const int mm = i / p.K, slot = i - mm * p.K;
+            for (int mm = 0; mm < p.M && first_map + mm < p.maps; ++mm) {
                 const int map = first_map + mm;
-                if (map >= p.maps) continue;
                 const int total = (redo[mm] || n_pending[mm] > p.PK) ? p.K + 1 : n_peaks[mm];
-                if (slot == 0) t.peak_count[map] = total;
-                if (total > p.K) continue;
-                const size_t dst = (size_t)map * p.K + slot;
-                t.peak_object[dst] = -1;
-                reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
-                if (slot >= total) {
-                    reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(-1, -1);
-                    t.peak_score[dst] = 0.0f;
-                    reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(0.0f, 0.0f);
-                    t.peak_conf[dst] = 0.0f;
+                if (et == 0) t.peak_count[map] = total;
+                if (total > p.K) continue;                       // tables of this map are written by the overflow path
+                for (int slot = et; slot < p.K; slot += ethreads) {
+                    const size_t dst = (size_t)map * p.K + slot;
+                    t.peak_object[dst] = -1;
+                    reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
+                    if (slot >= total) {
+                        reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(-1, -1);
+                        t.peak_score[dst] = 0.0f;
+                        reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(0.0f, 0.0f);
+                        t.peak_conf[dst] = 0.0f;
+                    }
                 }
             }
             for (int idx = et; idx < candidates; idx += ethreads) {
@@ -305,13 +324,10 @@ static inline bool okp_stream_plan(int maps, int H, int W, int K, int esize, Okp
     memset(&sp, 0, sizeof(sp));
     if (!okp_strip_plan(maps, H, W, K, esize, &sp.s)) return false;
     OkpStripPlan& p = sp.s;
-    // two epilogue warps where they fit beside the compute warps in 320 threads (two CTAs per SM at 96 registers), else
-    // one: small maps (64x64: 14 row batches per group) finish a group every few microseconds (sweep: profiles/r01k)
-    const int compute_threads = (sp.s.threads + 31) / 32 * 32;
-    sp.EW = okp_env_int("OKP_STREAM_EPILOGUE_WARPS", 1, 4, compute_threads + 32 + 64 <= 320 ? 2 : 1);
+    sp.EW = okp_env_int("OKP_STREAM_EPILOGUE_WARPS", 0, 4, 0);    // 0: decided below, once M is known
     // the second candidate buffer costs PK * 8 bytes per map: give it back from the per-CTA budget by re-planning M
     const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;
-    const int compute_limit = OKP_STRIP_MAX_THREADS - 32 - sp.EW * 32;
+    const int compute_limit = OKP_STRIP_MAX_THREADS - 32 - (sp.EW ? sp.EW : 2) * 32;
     for (;;) {
         int off = p.NS * p.stage_bytes;
         for (int b = 0; b < 2; ++b) { sp.off_pending[b] = off; off += p.M * p.PK * (int)sizeof(OkpStripCandidate); }
@@ -331,6 +347,10 @@ static inline bool okp_stream_plan(int maps, int H, int W, int K, int esize, Okp
         p.stage_bytes = p.halves * p.half_stride;
     }
     if (sp.smem_bytes > 224 * 1024 || p.threads > compute_limit) return false;
+    // two epilogue warps where they fit beside the compute warps in 320 threads (two CTAs per SM at 96 registers), else
+    // one: small maps (64x64: 14 row batches per group) finish a group every few microseconds and one warp cannot keep
+    // up (profiles/r01m_k1_64x64_ncu.md)
+    if (sp.EW == 0) sp.EW = (p.threads + 31) / 32 * 32 + 32 + 64 <= 320 ? 2 : 1;
     sp.groups = (maps + p.M - 1) / p.M;
     sp.threads = (p.threads + 31) / 32 * 32 + 32 + sp.EW * 32;
     *out = sp;
