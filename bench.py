@@ -198,7 +198,8 @@ def run_ours(args):
     # two table sets: the gather of step k (own stream) overlaps the decode of step k + 1
     table_sets = [decoder.tables(frames), DecodeTables(frames, decoder.C, decoder.cfg, decoder.params, device)]
     tables = table_sets[0]
-    exchange = RecordExchange(tables, world=world, rank=rank, transport=args.transport) if world > 1 else None
+    root = 0 if args.exchange == 'gather' else None
+    exchange = RecordExchange(tables, world=world, rank=rank, transport=args.transport, root=root) if world > 1 else None
     gathered = None
     table_free = [None, None]
     steps_done = [0]
@@ -281,7 +282,7 @@ def run_ours(args):
     # sanity: the decode found the objects that were drawn (guards against timing an empty kernel)
     found = float((tables['n_objects'] > 0).float().mean())
     assert found > 0.99, f"only {found:.3f} of the frames produced objects"
-    if world > 1:                                           # the gathered records hold every rank's frames
+    if world > 1 and (rank == 0 or args.exchange == 'allgather'):   # the gathered records hold every rank's frames
         objects = gathered[:, 0].reshape(world, frames)
         assert bool((objects > 0).float().mean(dim=1).gt(0.99).all()), "gathered records are incomplete"
 
@@ -303,7 +304,7 @@ def run_ours(args):
             'config': {'workload': args.workload, 'keypoint_config': w['config'], 'frames_per_gpu': frames,
                        'prediction_size': [H, W], 'objects_per_frame': w['grid'][0] * w['grid'][1],
                        'l2': f"inputs {algorithmic_bytes / 1e6:.0f} MB heatmaps per step exceed the 126 MB L2; no flush needed",
-                       'parallelism': f"frames sharded over {world} GPU(s); per step one gather of the 3D keypoint records"
+                       'parallelism': f"frames sharded over {world} GPU(s); per step one {'gather to rank 0' if args.exchange == 'gather' else 'all_gather'} of the 3D keypoint records"
                                       + (f" ({exchange.transport}: "
                                          + ('pack kernel stores straight into every peer over NVLink' if exchange.transport == 'peer'
                                             else 'pack kernel + NCCL all_gather') + ", overlapped with the next step's decode)"
@@ -338,6 +339,8 @@ def main():
     ap.add_argument('--e2e-frames', type=int, default=1024)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exchange', default='gather', choices=['gather', 'allgather'],
+                    help="N > 1: gather the records to rank 0 (north_star) or to every rank")
     ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
                     help="N > 1: how the keypoint records are gathered (sharding.RecordExchange)")
     args = ap.parse_args()

@@ -415,9 +415,9 @@ int okp_pack_records_f64(const OkpDecodeTables* tables, int N, int O, int C, int
         peers.dst[d] = destinations[d];
     }
     const long long total = (long long)N * okp_record_doubles(O, C, S);
-    long long blocks = (total + 255) / 256;
-    if (blocks > kSmCount * 8) blocks = kSmCount * 8;
-    okp_pack_records_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    long long blocks = (total + 127) / 128;
+    if (blocks > kSmCount * 2) blocks = kSmCount * 2;
+    okp_pack_records_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
         tables->n_objects, tables->flags, tables->kp_count, tables->kp_point, N, O * C, O * C * S * 3, first_row,
         n_destinations, peers);
     OKP_CUDA_CHECK(cudaGetLastError());

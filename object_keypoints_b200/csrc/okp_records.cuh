@@ -16,7 +16,10 @@
 
 struct OkpPeerBuffers { double* dst[OKP_MAX_PEERS]; };
 
-__global__ void __launch_bounds__(256)
+// 128 threads x <= 32 registers and no shared memory: a block fits into the 4096 registers per SM that two resident
+// CTAs of the persistent K1 (okp_peaks_stream_kernel) leave free, so the exchange of step k really runs beside the
+// decode of step k + 1 instead of waiting for an SM to drain.
+__global__ void __launch_bounds__(128, 16)
 okp_pack_records_kernel(const int32_t* __restrict__ n_objects, const uint32_t* __restrict__ flags,
                         const int32_t* __restrict__ kp_count, const double* __restrict__ kp_point, int N, int n_count,
                         int n_point, long long first_row, int n_dst, OkpPeerBuffers peers) {
@@ -30,6 +33,8 @@ okp_pack_records_kernel(const int32_t* __restrict__ n_objects, const uint32_t* _
         else if (j < 2 + n_count) v = (double)kp_count[(size_t)n * n_count + (j - 2)];
         else v = kp_point[(size_t)n * n_point + (j - 2 - n_count)];
         const long long at = first_row * R + i;
-        for (int d = 0; d < n_dst; ++d) peers.dst[d][at] = v;
+#pragma unroll
+        for (int d = 0; d < OKP_MAX_PEERS; ++d)          // constant indices: the pointers stay in the parameter bank
+            if (d < n_dst) peers.dst[d][at] = v;
     }
 }

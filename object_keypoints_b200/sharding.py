@@ -77,9 +77,13 @@ class RecordExchange:
               device-side barrier. No NCCL on the data path.
       'nccl'  the same kernel packs into a local send buffer, NCCL all_gather_into_tensor moves it.
       'auto'  'peer' when symmetric memory can be set up on this box, else 'nccl'.
+
+    ``root``: None = all_gather (every rank ends up with every record); an integer = gather to that rank only
+    (north_star: "a final NVLink gather of the 3D keypoints"): each rank stores its records once, into the root's
+    buffer, instead of ``world`` times -- the other ranks' returned tensors then hold only their own rows.
     """
 
-    def __init__(self, tables, world=None, rank=None, transport='auto', depth=3, group=None):
+    def __init__(self, tables, world=None, rank=None, transport='auto', depth=3, group=None, root=None):
         import ctypes
         from . import _lib
         self._ctypes, self._lib_module, self._lib = ctypes, _lib, _lib.lib()
@@ -92,6 +96,7 @@ class RecordExchange:
         _, self.O, self.C, self.S = (int(v) for v in t['kp_point'].shape[:4])
         self.R = int(self._lib.okp_record_doubles(self.O, self.C, self.S))
         self.depth = int(depth)
+        self.root = None if root is None else int(root)
         self.stream = torch.cuda.Stream(device=self.device)
         self.calls = 0
         self.handles = None
@@ -139,11 +144,18 @@ class RecordExchange:
         out = self.buffers[slot]
         with torch.cuda.stream(self.stream):
             if self.transport == 'peer':
-                self._pack(tables, self.rank * self.N, [int(p) for p in self.handles[slot].buffer_ptrs])
+                peers = [int(p) for p in self.handles[slot].buffer_ptrs]
+                if self.root is not None:                   # gather: one copy, into the root's buffer (and our own rows)
+                    peers = [peers[self.root]] if self.rank == self.root else [peers[self.root], peers[self.rank]]
+                self._pack(tables, self.rank * self.N, peers)
                 self.handles[slot].barrier(channel=0)       # every rank's stores have landed everywhere
             elif self.transport == 'nccl':
                 self._pack(tables, 0, [self.send[slot].data_ptr()])
-                dist.all_gather_into_tensor(out, self.send[slot], group=self.group)
+                if self.root is None:
+                    dist.all_gather_into_tensor(out, self.send[slot], group=self.group)
+                else:
+                    rows = [out[r * self.N:(r + 1) * self.N] for r in range(self.world)] if self.rank == self.root else None
+                    dist.gather(self.send[slot], rows, dst=self.root, group=self.group)
             else:
                 self._pack(tables, 0, [out.data_ptr()])
             self.done[slot].record(self.stream)

@@ -15,21 +15,26 @@ dist.init_process_group('nccl', device_id=device)
 cfg, size, frames = [1, 3], (64, 64), 257
 decoder = KeypointDecoder(cfg, size, camera=synthetic.default_camera(size), device=device)
 report = {}
-for transport in ('nccl', 'peer'):
+for transport, root in (('nccl', None), ('peer', None), ('nccl', 0), ('peer', 0), ('peer', world - 1)):
+    label = f"{transport}/{'allgather' if root is None else 'gather->' + str(root)}"
     try:
         exchange = None
         for step in range(5):
             batch = synthetic.make_batch(frames, cfg, size, seed=100 * step + rank, objects=(1, 3))
             tables = decoder.decode_batch(batch.heat, batch.depth, batch.centers)
             if exchange is None:
-                exchange = sharding.RecordExchange(tables, world=world, rank=rank, transport=transport)
+                exchange = sharding.RecordExchange(tables, world=world, rank=rank, transport=transport, root=root)
             got, done = exchange.exchange(tables)
             want = sharding.gather_keypoint_records(tables, world)
             done.synchronize()
-            assert torch.equal(got, want), f"{transport}: step {step} differs on rank {rank}"
-        report[transport] = 'ok'
+            if root is None or rank == root:
+                assert torch.equal(got, want), f"{label}: step {step} differs on rank {rank}"
+            else:                                            # a non-root rank only holds its own rows
+                mine = slice(rank * frames, (rank + 1) * frames)
+                assert transport == 'nccl' or torch.equal(got[mine], want[mine]), f"{label}: own rows differ on rank {rank}"
+        report[label] = 'ok'
     except Exception as error:
-        report[transport] = f"FAILED {type(error).__name__}: {error}"
+        report[label] = f"FAILED {type(error).__name__}: {error}"
     dist.barrier()
 print(f"rank {rank}/{world}: {report}", flush=True)
 dist.destroy_process_group()
