@@ -267,6 +267,19 @@ int okp_record_doubles(int O, int C, int S);
 int okp_pack_records_f64(const OkpDecodeTables* tables, int N, int O, int C, int S, long long first_row,
                          double* const* destinations, int n_destinations, void* stream);
 
+/* Ground-truth / training targets for a batch of frames. Replaces, per frame, the
+ * target construction of the reference's dataset (perception/datasets/video.py): _set_keypoints (:44-53) with the
+ * per-map normalisation target / max(target.max(), 0.5) clipped to [0, 1] (:210-211), _compute_centers (:225-242)
+ * and _compute_depth (:244-263). keypoints_dev [N,G,Kp,2] float64 (x, y) in TARGET pixels, Kp = 1 +
+ * sum(keypoint_config) with each object's centre first (:121-129); depths_dev [N,G,Kp] camera-frame z;
+ * n_objects_dev [N] objects present per frame (NULL = G). kernel_size 8, length_scale 2.0, center_radius 4.0 are
+ * the reference's constants for its 64x64 targets (:17-20). Outputs: heat_dev [N,C,H,W], centers_dev
+ * [N,C-1,2,H,W] (centre - (pixel + 0.5) inside the discs, zero elsewhere), depth_dev [N,C,H,W], float32. */
+int okp_rasterise_targets_f32(const double* keypoints_dev, const double* depths_dev, const int32_t* n_objects_dev,
+                              int N, int G, int C, int H, int W, const int32_t* keypoint_config, int kernel_size,
+                              double length_scale, double center_radius, float* heat_dev, float* centers_dev,
+                              float* depth_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

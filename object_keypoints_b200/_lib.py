@@ -19,6 +19,7 @@ EXPORTS = [
     'okp_triangulate_robust_f64', 'okp_host_alias', 'okp_correct_matches_f64', 'okp_stereo_associate_f64',
     'okp_extract_peaks_bf16', 'okp_group_objects_bf16', 'okp_decode_bf16',
     'okp_eval_match_f64', 'okp_eval_summary_f64', 'okp_record_doubles', 'okp_pack_records_f64',
+    'okp_rasterise_targets_f32',
 ]
 
 
@@ -110,6 +111,9 @@ def lib():
     L.okp_record_doubles.argtypes = [i32, i32, i32]
     L.okp_pack_records_f64.restype = i32
     L.okp_pack_records_f64.argtypes = [P(_abi.OkpDecodeTables), i32, i32, i32, i32, ctypes.c_longlong, P(vp), i32, vp]
+    L.okp_rasterise_targets_f32.restype = i32
+    L.okp_rasterise_targets_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, P(ctypes.c_int32), i32, dbl, dbl, dbl,
+                                            vp, vp, vp, vp]
     _LIB = L
     return L
 

@@ -14,6 +14,7 @@
 #include "okp_stereo.cuh"
 #include "okp_eval.cuh"
 #include "okp_records.cuh"
+#include "okp_targets.cuh"
 
 namespace {
 
@@ -420,6 +421,36 @@ int okp_pack_records_f64(const OkpDecodeTables* tables, int N, int O, int C, int
     okp_pack_records_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
         tables->n_objects, tables->flags, tables->kp_count, tables->kp_point, N, O * C, O * C * S * 3, first_row,
         n_destinations, peers);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_rasterise_targets_f32(const double* keypoints_dev, const double* depths_dev, const int32_t* n_objects_dev,
+                              int N, int G, int C, int H, int W, const int32_t* keypoint_config, int kernel_size,
+                              double length_scale, double center_radius, float* heat_dev, float* centers_dev,
+                              float* depth_dev, void* stream) {
+    int rc = check_shape(N, C, H, W);
+    if (rc != OKP_OK) return rc;
+    if (G < 1 || G > OKP_MAX_OBJECTS || kernel_size < 0 || !(length_scale > 0.0)) return OKP_E_SHAPE;
+    if (N == 0) return OKP_OK;
+    if (!keypoints_dev || !depths_dev || !heat_dev || !depth_dev || (C > 1 && (!centers_dev || !keypoint_config)))
+        return OKP_E_NULL;
+    OkpConfig config;
+    memset(&config, 0, sizeof(config));
+    config.cfg[0] = 1;                                  // video.py:75: the centre map first
+    int Kp = 1;
+    for (int i = 0; i < C - 1; ++i) {
+        if (keypoint_config[i] < 1 || keypoint_config[i] > OKP_MAX_SLOTS) return OKP_E_CAPACITY;
+        config.cfg[1 + i] = keypoint_config[i];
+        Kp += keypoint_config[i];
+    }
+    OkpTargetParams prm;
+    prm.kernel_size = kernel_size; prm.length_scale = length_scale; prm.center_radius = center_radius;
+    const size_t smem = sizeof(double) * 3 * (size_t)G * Kp;
+    auto kernel = okp_rasterise_targets_kernel<256>;
+    if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)((long long)N * C), 256, smem, (cudaStream_t)stream>>>(
+        keypoints_dev, depths_dev, n_objects_dev, N, G, Kp, C, H, W, config, prm, heat_dev, centers_dev, depth_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

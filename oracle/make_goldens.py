@@ -521,6 +521,45 @@ def evaluation_case(camera_utils, seed=31, frames=40, cfg=(1, 3)):
                                               'missing_percentage', 'points']), **camera_arrays(camera))
 
 
+def targets_case(video, seed=41, frames=6, cfg=(1, 3), size=(64, 64)):
+    """Ground-truth targets by the UNMODIFIED reference: video._set_keypoints with the loop and normalisation of
+    SceneDataset._extract_example (video.py:195-211) and the bound methods _compute_centers / _compute_depth
+    (:225-263) of a bare SceneDataset whose image size equals the target size (scale factor 1). Points near and
+    beyond every border, overlapping discs (later keypoints overwrite earlier ones) and crowded maps (sum > 1 ->
+    normalisation) are included."""
+    rng = np.random.default_rng(seed)
+    full = [1] + list(cfg)
+    Kp, C, (H, W) = sum(full), len(full), size
+    G = 3
+    ds = object.__new__(video.SceneDataset)
+    ds.keypoint_config, ds.n_keypoints, ds.n_objects, ds.keypoint_maps = full, Kp, G, C
+    ds.target_size, ds.image_size = np.array(size), (size[0], size[1])
+    ds.target_pixel_indices = video._pixel_indices(*size)
+    keypoints = np.zeros((frames, G, Kp, 2))
+    depths = rng.uniform(0.4, 1.5, (frames, G, Kp))
+    heat = np.zeros((frames, C, H, W), np.float32)
+    centers = np.zeros((frames, C - 1, 2, H, W), np.float32)
+    depth = np.zeros((frames, C, H, W), np.float32)
+    for n in range(frames):
+        for g in range(G):
+            centre = rng.uniform(-6, 70, 2) if n % 2 else rng.uniform(8, 56, 2)
+            keypoints[n, g, 1:] = centre + rng.normal(0, 3.0 if n < 4 else 0.7, (Kp - 1, 2))
+            keypoints[n, g, 0] = keypoints[n, g, 1:].mean(axis=0)
+        target = np.zeros((C, H, W), np.float32)
+        for g in range(G):                                       # video.py:197-205
+            for i, count in enumerate(full):
+                start = sum(full[:i])
+                video._set_keypoints(target[i], keypoints[n, g, start:start + count])
+        peak = np.maximum(target.max(axis=2).max(axis=1), 0.5)   # video.py:210-211
+        heat[n] = np.clip(target / peak[:, None, None], 0.0, 1.0)
+        flat = keypoints[n].reshape(G * Kp, 2)
+        centers[n] = ds._compute_centers(flat)
+        depth[n] = ds._compute_depth(flat, np.concatenate([np.zeros((G * Kp, 2)), depths[n].reshape(-1, 1)], axis=1))
+    assert heat.max() == 1.0 and (centers != 0).any() and (depth != 0).any()
+    return dict(keypoints=keypoints, depths=depths, keypoint_config=np.array(cfg, np.int32), size=np.array(size, np.int32),
+                ref_heat=heat, ref_centers=centers, ref_depth=depth)
+
+
 def types_namespace(**kw):
     import types
     return types.SimpleNamespace(**kw)
@@ -534,6 +573,9 @@ def main():
         return
     if '--only-producer' in sys.argv:
         save('producer_valve.npz', **producer_case())
+        return
+    if '--only-targets' in sys.argv:
+        save('targets_64.npz', **targets_case(video))
         return
     if '--only-evaluation' in sys.argv:
         save('evaluation.npz', **evaluation_case(camera_utils))
@@ -578,6 +620,9 @@ def main():
 
     # 9: evaluation bookkeeping (scripts/eval_model.py Results)
     save('evaluation.npz', **evaluation_case(camera_utils))
+
+    # 10: ground-truth target rasterisation (perception/datasets/video.py)
+    save('targets_64.npz', **targets_case(video))
 
     # 8: the keypoint network (input producer of BASELINE config 5)
     save('producer_valve.npz', **producer_case())

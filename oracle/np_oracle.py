@@ -586,3 +586,55 @@ def evaluation_summary(status, err, err_xy):
         'percentile25': float(np.percentile(e, 25)), 'percentile75': float(np.percentile(e, 75)),
         'missing_percentage': float(missing) / float(n_points) * 100.0, 'points': n_points,
     }
+
+
+# ------------------------------------------------------------------------------------------
+# training / ground-truth targets, perception/datasets/video.py:17-20,44-53,
+# 195-213,225-263 (_set_keypoints, the normalisation in _extract_example, _compute_centers, _compute_depth)
+# ------------------------------------------------------------------------------------------
+def rasterise_targets(keypoints, depths, keypoint_config, size, kernel_size=8, length_scale=2.0, center_radius=4.0):
+    """One frame. keypoints [G, Kp, 2] float64 (x, y) in TARGET pixels, Kp = sum([1] + keypoint_config) with the
+    object's centre first (video.py:121-129); depths [G, Kp] camera-frame z. -> heat [C,H,W], centers [C-1,2,H,W],
+    depth [C,H,W] float32. kernel_size = int(64 / 8), length_scale = 64 / 32, center_radius = 64 / 16 (video.py:17-20)."""
+    full = [1] + [int(v) for v in keypoint_config]
+    C, (H, W) = len(full), size
+    G = keypoints.shape[0]
+    heat = np.zeros((C, H, W), np.float32)
+    centers = np.zeros((C - 1, 2, H, W), np.float32)
+    depth = np.zeros((C, H, W), np.float32)
+    jj, ii = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    px = (np.arange(W, dtype=np.float32) + np.float32(0.5))[None, :].astype(np.float64)      # _pixel_indices: float32 (j + 0.5)
+    py = (np.arange(H, dtype=np.float32) + np.float32(0.5))[:, None].astype(np.float64)
+    for g in range(G):                                            # video.py:197-205
+        for i, count in enumerate(full):
+            start = sum(full[:i])
+            for x, y in keypoints[g, start:start + count]:        # _set_keypoints, video.py:44-53
+                ix, iy = int(np.float64(x).astype(np.int32)), int(np.float64(y).astype(np.int32))
+                x0, y0 = max(ix - kernel_size, 0), max(iy - kernel_size, 0)
+                x1, y1 = min(ix + kernel_size + 1, W), min(iy + kernel_size + 1, H)
+                if x1 <= x0 or y1 <= y0:
+                    continue
+                d2 = (x - jj[y0:y1, x0:x1]) ** 2 + (y - ii[y0:y1, x0:x1]) ** 2
+                value = np.exp(-d2 / length_scale ** 2)            # float64 (numba: float64 index, float64 scale)
+                heat[i, y0:y1, x0:x1] = (heat[i, y0:y1, x0:x1].astype(np.float64) + value).astype(np.float32)
+    for g in range(G):                                            # _compute_centers, video.py:225-242
+        cx, cy = keypoints[g, 0]
+        k = 1
+        for i, count in enumerate(full[1:]):
+            for _ in range(count):
+                x, y = keypoints[g, k]
+                within = np.sqrt((x - px) ** 2 + (y - py) ** 2) < center_radius
+                centers[i, 0][within] = (cx - px + 0 * py)[within].astype(np.float32)
+                centers[i, 1][within] = (cy - py + 0 * px)[within].astype(np.float32)
+                k += 1
+    for g in range(G):                                            # _compute_depth, video.py:244-263
+        k = 0
+        for i, count in enumerate(full):
+            for _ in range(count):
+                x, y = keypoints[g, k]
+                within = np.sqrt((x - px) ** 2 + (y - py) ** 2) < center_radius
+                depth[i][within] = np.float32(depths[g, k])
+                k += 1
+    peak = np.maximum(heat.max(axis=2).max(axis=1), np.float32(0.5))     # video.py:210-211
+    heat = np.clip(heat / peak[:, None, None], 0.0, 1.0).astype(np.float32)
+    return heat, centers, depth
