@@ -80,7 +80,7 @@ class RecordExchange:
 
     ``root``: None = all_gather (every rank ends up with every record); an integer = gather to that rank only
     (north_star: "a final NVLink gather of the 3D keypoints"): each rank stores its records once, into the root's
-    buffer, instead of ``world`` times -- the other ranks' returned tensors then hold only their own rows.
+    buffer, instead of ``world`` times -- only the root's returned tensor is meaningful.
     """
 
     def __init__(self, tables, world=None, rank=None, transport='auto', depth=3, group=None, root=None):
@@ -146,7 +146,7 @@ class RecordExchange:
             if self.transport == 'peer':
                 peers = [int(p) for p in self.handles[slot].buffer_ptrs]
                 if self.root is not None:                   # gather: one copy, into the root's buffer (and our own rows)
-                    peers = [peers[self.root]] if self.rank == self.root else [peers[self.root], peers[self.rank]]
+                    peers = [peers[self.root]]
                 self._pack(tables, self.rank * self.N, peers)
                 self.handles[slot].barrier(channel=0)       # every rank's stores have landed everywhere
             elif self.transport == 'nccl':

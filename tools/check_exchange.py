@@ -29,9 +29,6 @@ for transport, root in (('nccl', None), ('peer', None), ('nccl', 0), ('peer', 0)
             done.synchronize()
             if root is None or rank == root:
                 assert torch.equal(got, want), f"{label}: step {step} differs on rank {rank}"
-            else:                                            # a non-root rank only holds its own rows
-                mine = slice(rank * frames, (rank + 1) * frames)
-                assert transport == 'nccl' or torch.equal(got[mine], want[mine]), f"{label}: own rows differ on rank {rank}"
         report[label] = 'ok'
     except Exception as error:
         report[label] = f"FAILED {type(error).__name__}: {error}"
