@@ -1,16 +1,14 @@
 #!/bin/bash
-# Short GPU call while iterating on K1: parity tests, K1 timing at both shapes, optional knob sweep.
-# usage (under gpurun): bash tools/gpu_quick.sh <tag> [sweep]
-tag=${1:-quick}
+# Short GPU call: parity tests, K1 + grouping timings at both shapes and element types, one bench line.
+# usage (under gpurun): bash tools/gpu_quick.sh <tag>
+tag=${1:-q}
 out=gpurun_out/$tag
 mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
-tail -15 $out/pytest_gpu.log
-timeout 300 python tools/bench_k1.py 180x320 2048 10 > $out/bench_k1.log 2>&1
-timeout 300 python tools/bench_k1.py 64x64 32768 10 >> $out/bench_k1.log 2>&1
+tail -12 $out/pytest_gpu.log
+for dt in f32 bf16; do
+  timeout 120 python tools/bench_k1.py 180x320 4096 10 $dt >> $out/bench_k1.log 2>&1
+  timeout 120 python tools/bench_k1.py 64x64 32768 10 $dt >> $out/bench_k1.log 2>&1
+done
 cat $out/bench_k1.log
-if [ "$2" = "sweep" ]; then
-  timeout 600 python tools/sweep_k1.py 180x320 2048 5 > $out/sweep_k1.log 2>&1
-  timeout 300 python tools/sweep_k1.py 64x64 32768 5 >> $out/sweep_k1.log 2>&1
-  grep "best" -B 30 $out/sweep_k1.log
-fi
+timeout 300 python bench.py --steps 20 --warmup 3 > $out/bench.json 2> $out/bench.err; tail -3 $out/bench.err; cut -c1-400 $out/bench.json

@@ -1,4 +1,6 @@
 #!/bin/bash
+# Knob sweep of the persistent K1 (epilogue warps, TMA stages) after the parity tests.
+# usage (under gpurun): bash tools/gpu_sweep.sh <tag>
 tag=${1:-ab3}
 out=gpurun_out/$tag
 mkdir -p $out
