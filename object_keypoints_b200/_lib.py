@@ -112,7 +112,7 @@ def lib():
     L.okp_pack_records_f64.restype = i32
     L.okp_pack_records_f64.argtypes = [P(_abi.OkpDecodeTables), i32, i32, i32, i32, ctypes.c_longlong, P(vp), i32, vp]
     L.okp_rasterise_targets_f32.restype = i32
-    L.okp_rasterise_targets_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, P(ctypes.c_int32), i32, dbl, dbl, dbl,
+    L.okp_rasterise_targets_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, P(ctypes.c_int32), i32, dbl, dbl,
                                             vp, vp, vp, vp]
     _LIB = L
     return L

@@ -34,6 +34,34 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, name), f"libokp.so does not export {name}"
 
 
+def header_prototypes():
+    """name -> list of parameter declarations, parsed from include/okp.h."""
+    text = open(os.path.join(ROOT, 'include', 'okp.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    out = {}
+    for name, params in re.findall(r'\b(okp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', text, flags=re.S):
+        params = params.strip()
+        out[name] = [] if params in ('', 'void') else [p.strip() for p in params.split(',')]
+    return out
+
+
+def test_ctypes_signatures_agree_with_the_header(lib):
+    """Every binding in _lib.py takes as many arguments as the prototype declares, pointers where the header has
+    pointers and floating-point types where it has double / float (catches a drifted binding without a GPU)."""
+    prototypes = header_prototypes()
+    assert sorted(prototypes) == sorted(_lib.EXPORTS)
+    for name, params in prototypes.items():
+        argtypes = getattr(lib, name).argtypes
+        assert argtypes is not None, f"{name}: no argtypes declared"
+        assert len(argtypes) == len(params), f"{name}: header has {len(params)} parameters, the binding {len(argtypes)}"
+        for declaration, ctype in zip(params, argtypes):
+            is_pointer = '*' in declaration
+            bound_pointer = ctype is ctypes.c_void_p or ctype is ctypes.c_char_p or hasattr(ctype, 'contents')
+            assert is_pointer == bound_pointer, f"{name}: '{declaration}' bound as {ctype}"
+            if not is_pointer and re.match(r'(const\s+)?double\b', declaration):
+                assert ctype is ctypes.c_double, f"{name}: '{declaration}' bound as {ctype}"
+
+
 def test_version_and_strerror(lib):
     assert lib.okp_version() == 1
     assert lib.okp_strerror(0) == b"ok"
