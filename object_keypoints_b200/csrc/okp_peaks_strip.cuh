@@ -178,8 +178,22 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     if (!__any_sync(0xffffffffu, fmaxf(fmaxf(b[0], b[1]), fmaxf(b[2], b[3])) > L.thr_lo)) return;
     const float ninf = -INFINITY;
     const uint32_t vmask = L.vmask;
+    const float tie = OKP_STRIP_TIE;
     // rows yc-2, yc-1 (slots I+1, I+2) and yc+1, yc+2 (slots I+4, I) may lie outside the image: max_pool2d pads with -inf
     const bool up2 = !EDGE || yc >= 2, up1 = !EDGE || yc >= 1, dn1 = !EDGE || yc + 1 < L.H, dn2 = !EDGE || yc + 2 < L.H;
+    // second gate, still from registers only: a peak is at least a VERTICAL local maximum, so a row in which no pixel
+    // above the threshold is (within the tie band) as large as the pixels right above and below it cannot hold a
+    // candidate. A blob's box sum stays above the threshold over ~10 rows but has its vertical maximum in one or two
+    // of them: this skips the 5x5 neighbourhood test (a third of the kernel's instructions, r01l) for nine busy rows in ten.
+    {
+        bool possible = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float v = fmaxf(up1 ? sv[(I + 2) % 5][c] : ninf, dn1 ? sv[(I + 4) % 5][c] : ninf);
+            possible = possible || (b[c] > L.thr_lo && b[c] * tie >= v);
+        }
+        if (!__any_sync(0xffffffffu, possible)) return;
+    }
     float own[4], cm[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -199,7 +213,6 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     const float q0 = fmaxf(fmaxf(l2, l3), fmaxf(cm[1], cm[2])), q3 = fmaxf(fmaxf(cm[1], cm[2]), fmaxf(r0, r1));
     const float others[4] = {fmaxf(own[0], q0), fmaxf(fmaxf(l3, cm[0]), fmaxf(own[1], fmaxf(cm[2], cm[3]))),
                              fmaxf(fmaxf(cm[0], cm[1]), fmaxf(own[2], fmaxf(cm[3], r0))), fmaxf(own[3], q3)};
-    const float tie = OKP_STRIP_TIE;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         // a candidate: above the threshold, inside the image, and no visible neighbour is provably larger
