@@ -186,13 +186,13 @@ __device__ __forceinline__ void okp_strip_step(const float4 lo, const float4 hi,
     // candidate. A blob's box sum stays above the threshold over ~10 rows but has its vertical maximum in one or two
     // of them: this skips the 5x5 neighbourhood test (a third of the kernel's instructions, r01l) for nine busy rows in ten.
     {
-        bool possible = false;
+        int possible = 0;                                         // bitwise on purpose: no short-circuit branches
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float v = fmaxf(up1 ? sv[(I + 2) % 5][c] : ninf, dn1 ? sv[(I + 4) % 5][c] : ninf);
-            possible = possible || (b[c] > L.thr_lo && b[c] * tie >= v);
+            possible |= (int)(b[c] > L.thr_lo) & (int)(b[c] * tie >= v);
         }
-        if (!__any_sync(0xffffffffu, possible)) return;
+        if (!__any_sync(0xffffffffu, possible != 0)) return;
     }
     float own[4], cm[4];
 #pragma unroll
