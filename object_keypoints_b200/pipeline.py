@@ -58,23 +58,33 @@ def _as_device_map(x, device):
 
 
 class DecodeTables:
-    """The OkpDecodeTables record as torch tensors on one device (layout: include/okp.h)."""
+    """The OkpDecodeTables record as torch tensors on one device (layout: include/okp.h). All tables are views
+    into ONE allocation (each starting on a 256-byte boundary), so that the synchronising host copy of a decode --
+    what the reference-style per-frame ``__call__`` does after every frame -- is a single transfer."""
+    ALIGN = 256
 
     def __init__(self, N, C, keypoint_config, params, device):
         self.N, self.C = N, C
-        self.tensors = {}
+        self._layout = []
+        offset = 0
         for name, dtype, shape in _abi.table_shapes(N, C, keypoint_config, params):
-            self.tensors[name] = torch.zeros(shape, dtype=_TORCH_DTYPES[np.dtype(dtype)], device=device)
+            nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+            self._layout.append((name, np.dtype(dtype), tuple(shape), offset, nbytes))
+            offset += (nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(max(offset, self.ALIGN), dtype=torch.uint8, device=device)
+        self.tensors = {}
+        for name, dtype, shape, start, nbytes in self._layout:
+            self.tensors[name] = self.flat[start:start + nbytes].view(_TORCH_DTYPES[dtype]).reshape(shape)
         self.struct = _abi.OkpDecodeTables(**{k: v.data_ptr() for k, v in self.tensors.items()})
 
     def __getitem__(self, name):
         return self.tensors[name]
 
     def numpy(self):
-        """Synchronising copy of every table to host NumPy arrays (flags as uint32)."""
-        out = {k: v.cpu().numpy() for k, v in self.tensors.items()}
-        out['flags'] = out['flags'].view(np.uint32)
-        return out
+        """Synchronising copy of every table to host NumPy arrays (flags as uint32): one device-to-host transfer."""
+        host = self.flat.cpu().numpy()
+        return {name: host[start:start + nbytes].view(np.uint32 if name == 'flags' else dtype).reshape(shape)
+                for name, dtype, shape, start, nbytes in self._layout}
 
 
 class KeypointDecoder:

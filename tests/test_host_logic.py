@@ -91,3 +91,27 @@ def test_synthetic_generator_is_deterministic_and_separated():
     g = load_golden('valve_64.npz')
     again = synthetic.make_batch(48, [1, 3], (64, 64), seed=1001, objects=(1, 2))
     np.testing.assert_array_equal(again.heat[g['source_frames']], g['heat'])
+
+
+def test_decode_tables_are_views_into_one_allocation():
+    """DecodeTables: every table 256-byte aligned inside one buffer, numpy() = one copy with the right dtypes."""
+    import torch
+    from object_keypoints_b200 import _abi
+    from object_keypoints_b200.pipeline import DecodeTables
+    params = _abi.make_params()
+    t = DecodeTables(5, 3, [1, 3], params, torch.device('cpu'))
+    base = t.flat.data_ptr()
+    shapes = {name: tuple(shape) for name, _, shape in _abi.table_shapes(5, 3, [1, 3], params)}
+    for name, tensor in t.tensors.items():
+        assert (tensor.data_ptr() - base) % DecodeTables.ALIGN == 0 and tensor.is_contiguous()
+        assert tuple(tensor.shape) == shapes[name]
+        assert getattr(t.struct, name) == tensor.data_ptr()
+    t['kp_point'][2, 1, 0, 0, 1] = 3.5
+    t['flags'][4] = 7
+    t['peak_yx'][1, 2, 3, 1] = -1
+    host = t.numpy()
+    assert host['kp_point'][2, 1, 0, 0, 1] == 3.5 and host['kp_point'].dtype == np.float64
+    assert host['flags'][4] == 7 and host['flags'].dtype == np.uint32
+    assert host['peak_yx'][1, 2, 3, 1] == -1 and host['peak_xy'].dtype == np.float32
+    empty = DecodeTables(0, 3, [1, 3], params, torch.device('cpu'))
+    assert empty.numpy()['n_objects'].shape == (0,)
