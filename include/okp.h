@@ -68,14 +68,18 @@ typedef struct OkpCamera {
 
 typedef struct OkpDecodeParams {
     float threshold;          /* 0.5 on the 5x5 box sum (pipeline.py:73) */
-    int32_t nms_size;         /* 5 (perception/models.py:55) */
-    int32_t box_sum;          /* 1: NMS runs on the 5x5 box sum (pipeline.py:70-72) */
+    int32_t nms_size;         /* 5 (perception/models.py:55); 3 = CornerNet's _nms window (py_utils/utils.py:14-19) */
+    int32_t box_sum;          /* 1: NMS runs on the 5x5 box sum (pipeline.py:70-72); 0: on the map itself */
     int32_t compat_clip_bug;  /* 1: clip (x, y) with (H-1, W-1) like pipeline.py:169; 0: with (W-1, H-1) */
     double outlier_distance;  /* 20.0 px (pipeline.py:121) */
     int32_t max_peaks;        /* K: peak slots per (frame, map) */
     int32_t max_objects;      /* O: object slots per frame */
     int32_t max_votes;        /* V: vote slots per object */
     int32_t kmeans_iterations;/* Lloyd iterations of the deterministic clustering (default 16) */
+    int32_t top_k;            /* 0: every peak, raster order (pipeline.py:73). k > 0: the k highest scores of each map,
+                                 score-descending (ties: raster order) -- CornerNet's _topk (py_utils/utils.py:27-38)
+                                 per keypoint type; exact when the map has <= max_peaks peaks above the threshold,
+                                 otherwise OKP_FLAG_PEAK_OVERFLOW is raised as usual */
 } OkpDecodeParams;
 
 /* Fixed-capacity structure-of-arrays output. N frames, C maps, K = max_peaks, O = max_objects,
@@ -112,7 +116,10 @@ size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodePar
 /* Replaces KeypointExtractionComponent.__call__ (perception/pipeline.py:64-91) including
  * perception/models.py:55-58 (nms): box sum, NMS, threshold, raster-order compaction and
  * sub-pixel centroid for every map of every frame. Fills the peak_* tables (peak_object and
- * peak_vote are reset). heat_dev: [N,C,H,W] float32 probabilities. */
+ * peak_vote are reset). heat_dev: [N,C,H,W] float32 probabilities.
+ * The reference's configuration (nms_size 5, box_sum 1, top_k 0) runs on the tuned TMA kernel; the other
+ * combinations (3x3 window, NMS on the raw map, per-type top-k: BASELINE.json's "3x3 max-pool NMS ... with
+ * per-type top-k and thresholding") run on the exact generic tile kernels. */
 int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W,
                           const OkpDecodeParams* params, const OkpDecodeTables* tables,
                           void* workspace_dev, size_t workspace_bytes, void* stream);

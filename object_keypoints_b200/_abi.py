@@ -35,7 +35,7 @@ class OkpDecodeParams(ctypes.Structure):
     _fields_ = [('threshold', ctypes.c_float), ('nms_size', ctypes.c_int32), ('box_sum', ctypes.c_int32),
                 ('compat_clip_bug', ctypes.c_int32), ('outlier_distance', ctypes.c_double),
                 ('max_peaks', ctypes.c_int32), ('max_objects', ctypes.c_int32), ('max_votes', ctypes.c_int32),
-                ('kmeans_iterations', ctypes.c_int32)]
+                ('kmeans_iterations', ctypes.c_int32), ('top_k', ctypes.c_int32)]
 
 
 # name, numpy dtype, shape as a function of the dimension dict -- order = field order in okp.h
@@ -74,12 +74,17 @@ def table_shapes(N, C, keypoint_config, params):
 
 
 def make_params(threshold=0.5, outlier_distance=20.0, max_peaks=32, max_objects=16, max_votes=16,
-                compat_clip_bug=True, kmeans_iterations=16):
+                compat_clip_bug=True, kmeans_iterations=16, nms_size=5, box_sum=True, top_k=0):
     if not (1 <= max_peaks <= OKP_MAX_PEAKS):
         raise ValueError(f"max_peaks must be in [1, {OKP_MAX_PEAKS}]")
     if not (1 <= max_objects <= OKP_MAX_OBJECTS):
         raise ValueError(f"max_objects must be in [1, {OKP_MAX_OBJECTS}]")
-    return OkpDecodeParams(threshold=threshold, nms_size=5, box_sum=1, compat_clip_bug=int(bool(compat_clip_bug)),
+    if nms_size not in (3, 5):
+        raise ValueError("nms_size must be 3 or 5")
+    if not (0 <= top_k <= max_peaks):
+        raise ValueError("top_k must be in [0, max_peaks]")
+    return OkpDecodeParams(threshold=threshold, nms_size=int(nms_size), box_sum=int(bool(box_sum)), top_k=int(top_k),
+                           compat_clip_bug=int(bool(compat_clip_bug)),
                            outlier_distance=outlier_distance, max_peaks=max_peaks, max_objects=max_objects,
                            max_votes=max_votes, kmeans_iterations=kmeans_iterations)
 

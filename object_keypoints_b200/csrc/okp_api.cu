@@ -31,11 +31,14 @@ struct PeakPlan {
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-PeakPlan plan_peaks(int maps, int H, int W, int K, int esize) {
+PeakPlan plan_peaks(int maps, int H, int W, int K, int esize, const OkpDecodeParams* prm) {
     PeakPlan p;
     memset(&p, 0, sizeof(p));
-    p.strip = okp_strip_plan(maps, H, W, K, esize, &p.sp);
+    // the tuned TMA kernels implement the reference's configuration only (5x5 window on the 5x5 box sum)
+    const bool reference_mode = prm->nms_size == 5 && prm->box_sum == 1;
+    p.strip = reference_mode && okp_strip_plan(maps, H, W, K, esize, &p.sp);
     p.geo.H = H; p.geo.W = W; p.geo.maps = maps;
+    p.geo.radius = prm->nms_size / 2; p.geo.box_sum = prm->box_sum ? 1 : 0;
     p.geo.TW = W <= 64 ? round_up(W, 8) : 64;
     p.geo.TH = H <= 64 ? H : 32;
     p.geo.tiles_x = (W + p.geo.TW - 1) / p.geo.TW;
@@ -57,7 +60,8 @@ int check_params(const OkpDecodeParams* prm) {
     if (prm->max_peaks < 1 || prm->max_peaks > OKP_MAX_PEAKS) return OKP_E_CAPACITY;
     if (prm->max_objects < 1 || prm->max_objects > OKP_MAX_OBJECTS) return OKP_E_CAPACITY;
     if (prm->max_votes < 1 || prm->max_votes > 4096) return OKP_E_CAPACITY;
-    if (prm->nms_size != 5 || prm->box_sum != 1) return OKP_E_UNSUPPORTED;
+    if ((prm->nms_size != 5 && prm->nms_size != 3) || (prm->box_sum != 0 && prm->box_sum != 1)) return OKP_E_UNSUPPORTED;
+    if (prm->top_k < 0 || prm->top_k > prm->max_peaks) return OKP_E_CAPACITY;
     return OKP_OK;
 }
 
@@ -100,7 +104,7 @@ size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodePar
     // enough for either element type (their launch plans can differ: bf16 rows need W % 8 == 0 for TMA)
     size_t need = 0;
     for (int esize = 2; esize <= 4; esize += 2) {
-        const PeakPlan p = plan_peaks(N * C, H, W, params->max_peaks, esize);
+        const PeakPlan p = plan_peaks(N * C, H, W, params->max_peaks, esize, params);
         const size_t bytes = workspace_for(p, N * C, params->max_peaks, p.strip);
         if (bytes > need) need = bytes;
     }
@@ -129,7 +133,7 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     cudaStream_t s = (cudaStream_t)stream;
     const int K = params->max_peaks;
     const int maps = N * C;
-    const PeakPlan p = plan_peaks(maps, H, W, K, (int)sizeof(T));
+    const PeakPlan p = plan_peaks(maps, H, W, K, (int)sizeof(T), params);
     const bool strip = p.strip && ((uintptr_t)heat_dev & 15u) == 0;      // TMA needs a 16-byte aligned base
     if (workspace_bytes < workspace_for(p, maps, K, strip)) return OKP_E_WORKSPACE;
     const size_t tiles = strip ? (size_t)overflow_grid(maps) * p.tiles_per_map : (size_t)maps * p.tiles_per_map;
@@ -152,6 +156,10 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
         OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
         kernel<<<overflow_grid(maps), 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks, *tables);
         OKP_CUDA_CHECK(cudaGetLastError());
+        if (params->top_k > 0) {
+            okp_topk_kernel<<<(maps + 3) / 4, 128, 0, s>>>(maps, K, params->top_k, *tables);
+            OKP_CUDA_CHECK(cudaGetLastError());
+        }
         return OKP_OK;
     }
     {
@@ -164,6 +172,10 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     okp_merge_peaks_kernel<<<(maps + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
         tile_count, tile_peaks, maps, p.tiles_per_map, W, K, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
+    if (params->top_k > 0) {
+        okp_topk_kernel<<<(maps + 3) / 4, 128, 0, s>>>(maps, K, params->top_k, *tables);
+        OKP_CUDA_CHECK(cudaGetLastError());
+    }
     return OKP_OK;
 }
 

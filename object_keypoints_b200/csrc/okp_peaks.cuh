@@ -20,6 +20,8 @@ struct OkpTileGeometry {
     int TH, TW;          // tile size (outputs)
     int tiles_y, tiles_x;
     int maps;            // N * C
+    int radius;          // NMS window radius: 2 (5x5, the reference) or 1 (3x3)
+    int box_sum;         // 1: the score is the 5x5 box sum (the reference); 0: the map value itself
 };
 
 __device__ __forceinline__ void okp_centroid_from_smem(const float* raw, int pitch, int ry, int rx, int gy, int gx,
@@ -74,17 +76,22 @@ __device__ __forceinline__ void okp_generic_tile(const T* __restrict__ heat, con
             raw[i] = v;
         }
         __syncthreads();
-        // ---- box sum on the tile + 2 px halo: 25 sequential adds, raster tap order ----
+        // ---- score on the tile + 2 px halo: box sum (25 sequential adds, raster tap order) or the value itself ----
+        const int r = g.radius;
         for (int i = threadIdx.x; i < (g.TH + 4) * SP; i += THREADS) {
             const int sy = i / SP, sx = i - sy * SP;
             const int gy = ty0 - 2 + sy, gx = tx0 - 2 + sx;
             float acc = -INFINITY;           // max_pool2d pads with -inf
             if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) {
-                acc = 0.0f;
+                if (g.box_sum) {
+                    acc = 0.0f;
 #pragma unroll
-                for (int dy = 0; dy < 5; ++dy)
+                    for (int dy = 0; dy < 5; ++dy)
 #pragma unroll
-                    for (int dx = 0; dx < 5; ++dx) acc = __fadd_rn(acc, raw[(sy + dy) * RP + sx + dx]);
+                        for (int dx = 0; dx < 5; ++dx) acc = __fadd_rn(acc, raw[(sy + dy) * RP + sx + dx]);
+                } else {
+                    acc = raw[(sy + 2) * RP + sx + 2];
+                }
             }
             score[i] = acc;
         }
@@ -97,10 +104,8 @@ __device__ __forceinline__ void okp_generic_tile(const T* __restrict__ heat, con
             const float v = score[(py + 2) * SP + px + 2];
             if (!(v > threshold)) continue;
             float m = v;
-#pragma unroll
-            for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
+            for (int dy = 2 - r; dy <= 2 + r; ++dy)
+                for (int dx = 2 - r; dx <= 2 + r; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
             if (v == m) {
                 const int slot = atomicAdd(&s_count, 1);
                 if (slot < K) keys[slot] = gy * g.W + gx;
@@ -125,8 +130,8 @@ __device__ __forceinline__ void okp_generic_tile(const T* __restrict__ heat, con
                             const float v = score[(py + 2) * SP + px + 2];
                             if (v > threshold) {
                                 float m = v;
-                                for (int dy = 0; dy < 5; ++dy)
-                                    for (int dx = 0; dx < 5; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
+                                for (int dy = 2 - r; dy <= 2 + r; ++dy)
+                                    for (int dx = 2 - r; dx <= 2 + r; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
                                 is_peak = (v == m);
                                 key = gy * g.W + gx;
                             }
@@ -277,4 +282,48 @@ okp_peaks_overflow_kernel(const T* __restrict__ heat, OkpTileGeometry g, float t
         }
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-type top-k (OkpDecodeParams.top_k > 0; BASELINE.json: "per-type top-k"; CornerNet's _topk,
+// perception/corner_net_lite/core/models/py_utils/utils.py:27-38, applied to each map): the raster-ordered
+// table of a map is re-ordered by score, descending (ties: raster order), and cut to k rows. One warp per
+// map; the rows (at most K <= 256) are ranked by counting, written back, the tail cleared. A map whose table
+// overflowed (peak_count > K) keeps its count so that OKP_FLAG_PEAK_OVERFLOW is still raised.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+okp_topk_kernel(int maps, int K, int top_k, OkpDecodeTables t) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= maps) return;
+    __shared__ float s_score[4][OKP_MAX_PEAKS], s_conf[4][OKP_MAX_PEAKS], s_xy[4][OKP_MAX_PEAKS][2];
+    __shared__ int s_yx[4][OKP_MAX_PEAKS][2];
+    const int w = threadIdx.x >> 5;
+    const int total = t.peak_count[warp];
+    const int n = total < K ? total : K;
+    const size_t base = (size_t)warp * K;
+    for (int i = lane; i < n; i += 32) {
+        s_score[w][i] = t.peak_score[base + i];
+        s_conf[w][i] = t.peak_conf[base + i];
+        s_xy[w][i][0] = t.peak_xy[2 * (base + i)]; s_xy[w][i][1] = t.peak_xy[2 * (base + i) + 1];
+        s_yx[w][i][0] = t.peak_yx[2 * (base + i)]; s_yx[w][i][1] = t.peak_yx[2 * (base + i) + 1];
+    }
+    __syncwarp();
+    const int keep = n < top_k ? n : top_k;
+    for (int i = lane; i < n; i += 32) {
+        const float mine = s_score[w][i];
+        int rank = 0;                        // rows are in raster order: an equal score further left wins
+        for (int j = 0; j < n; ++j) rank += (s_score[w][j] > mine) || (s_score[w][j] == mine && j < i);
+        if (rank < keep) {
+            t.peak_score[base + rank] = mine;
+            t.peak_conf[base + rank] = s_conf[w][i];
+            t.peak_xy[2 * (base + rank)] = s_xy[w][i][0]; t.peak_xy[2 * (base + rank) + 1] = s_xy[w][i][1];
+            t.peak_yx[2 * (base + rank)] = s_yx[w][i][0]; t.peak_yx[2 * (base + rank) + 1] = s_yx[w][i][1];
+        }
+    }
+    for (int i = keep + lane; i < n; i += 32) {
+        t.peak_score[base + i] = 0.0f; t.peak_conf[base + i] = 0.0f;
+        t.peak_xy[2 * (base + i)] = 0.0f; t.peak_xy[2 * (base + i) + 1] = 0.0f;
+        t.peak_yx[2 * (base + i)] = -1; t.peak_yx[2 * (base + i) + 1] = -1;
+    }
+    if (lane == 0 && total <= K) t.peak_count[warp] = keep;
 }

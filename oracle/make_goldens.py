@@ -560,6 +560,31 @@ def targets_case(video, seed=41, frames=6, cfg=(1, 3), size=(64, 64)):
                 ref_heat=heat, ref_centers=centers, ref_depth=depth)
 
 
+def cornernet_topk_case(seed=51, maps=6, size=(48, 64), k=20, threshold=0.3):
+    """CornerNet's own _nms(kernel=3) + _topk(K) (perception/corner_net_lite/core/models/py_utils/utils.py:14-38,
+    imported unmodified), applied to one keypoint type at a time. Maps: smooth random fields with distinct values,
+    so torch.topk's order is unambiguous, and fewer peaks above `threshold` than table slots."""
+    ref_import.load()
+    from perception.corner_net_lite.core.models.py_utils import utils as cornernet
+    rng = np.random.default_rng(seed)
+    H, W = size
+    heat = np.zeros((maps, 1, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for m in range(maps):
+        field = rng.uniform(0.0, 0.25, (H, W))
+        for _ in range(int(rng.integers(25, 40))):
+            cy, cx, a, l = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(0.35, 1.0), rng.uniform(1.0, 2.5)
+            field = np.maximum(field, a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / l ** 2))
+        heat[m, 0] = field.astype(np.float32)
+    kept = cornernet._nms(torch.from_numpy(heat), kernel=3)
+    scores, inds, classes, ys, xs = cornernet._topk(kept, K=k)
+    assert len(np.unique(scores.numpy())) == scores.numel(), "scores must be distinct"
+    assert (scores.numpy() > threshold).all() and ((kept.numpy() > threshold).sum(axis=(1, 2, 3)) <= 256).all()
+    return dict(heat=heat, k=np.int64(k), threshold=np.float32(threshold), ref_scores=scores.numpy(),
+                ref_ys=ys.numpy().astype(np.int32), ref_xs=xs.numpy().astype(np.int32),
+                ref_suppressed=kept.numpy())
+
+
 def types_namespace(**kw):
     import types
     return types.SimpleNamespace(**kw)
@@ -573,6 +598,9 @@ def main():
         return
     if '--only-producer' in sys.argv:
         save('producer_valve.npz', **producer_case())
+        return
+    if '--only-topk' in sys.argv:
+        save('cornernet_topk.npz', **cornernet_topk_case())
         return
     if '--only-targets' in sys.argv:
         save('targets_64.npz', **targets_case(video))
@@ -620,6 +648,9 @@ def main():
 
     # 9: evaluation bookkeeping (scripts/eval_model.py Results)
     save('evaluation.npz', **evaluation_case(camera_utils))
+
+    # 11: CornerNet's 3x3 NMS + top-k (the K1 parameter modes)
+    save('cornernet_topk.npz', **cornernet_topk_case())
 
     # 10: ground-truth target rasterisation (perception/datasets/video.py)
     save('targets_64.npz', **targets_case(video))

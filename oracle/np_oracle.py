@@ -638,3 +638,38 @@ def rasterise_targets(keypoints, depths, keypoint_config, size, kernel_size=8, l
     peak = np.maximum(heat.max(axis=2).max(axis=1), np.float32(0.5))     # video.py:210-211
     heat = np.clip(heat / peak[:, None, None], 0.0, 1.0).astype(np.float32)
     return heat, centers, depth
+
+
+# ------------------------------------------------------------------------------------------
+# K1 parameter modes (last paragraph; BASELINE.json: "3x3 max-pool NMS ... per-type top-k and
+# thresholding"): CornerNet's _nms / _topk, perception/corner_net_lite/core/models/py_utils/utils.py:14-38,
+# applied per keypoint type
+# ------------------------------------------------------------------------------------------
+def extract_peak_tables(heat, threshold=0.5, nms_size=5, use_box_sum=True, top_k=0, max_peaks=32):
+    """heat [N,C,H,W] -> the peak_* tables of include/okp.h for any (nms_size, box_sum, top_k) combination.
+    top_k == 0: every peak in raster order (pipeline.py:73). top_k > 0: the k highest scores of each map,
+    score-descending, equal scores in raster order (torch.topk leaves that order unspecified; _topk, utils.py:27-38)."""
+    heat = np.asarray(heat, dtype=F32)
+    N, C, H, W = heat.shape
+    K = max_peaks
+    out = {'peak_count': np.zeros((N, C), np.int32), 'peak_yx': np.full((N, C, K, 2), -1, np.int32),
+           'peak_score': np.zeros((N, C, K), F32), 'peak_xy': np.zeros((N, C, K, 2), F32),
+           'peak_conf': np.zeros((N, C, K), F32)}
+    for n in range(N):
+        for c in range(C):
+            yx, score = find_peaks(heat[n, c], threshold, nms_size, use_box_sum)
+            total = len(yx)
+            yx = yx[:K]                                          # the table keeps the first K in raster order
+            if top_k > 0:
+                order = sorted(range(len(yx)), key=lambda i: (-float(score[yx[i, 0], yx[i, 1]]), i))[:top_k]
+                yx = yx[order]
+                if total <= K:
+                    total = len(yx)
+            out['peak_count'][n, c] = total
+            for k, (y, x) in enumerate(yx):
+                xy, conf = centroid(heat[n, c], int(y), int(x))
+                out['peak_yx'][n, c, k] = (y, x)
+                out['peak_score'][n, c, k] = score[y, x]
+                out['peak_xy'][n, c, k] = xy
+                out['peak_conf'][n, c, k] = conf
+    return out

@@ -71,7 +71,8 @@ def test_version_and_strerror(lib):
 def test_struct_sizes_match_header():
     # OkpCamera: 4 + 4 + 9 doubles + 2 int32; OkpDecodeParams: see header; tables: 16 pointers
     assert ctypes.sizeof(_abi.OkpCamera) == 17 * 8 + 8
-    assert ctypes.sizeof(_abi.OkpDecodeParams) == 40
+    assert ctypes.sizeof(_abi.OkpDecodeParams) == 48
+    assert _abi.OkpDecodeParams.top_k.offset == 40
     assert ctypes.sizeof(_abi.OkpDecodeTables) == 16 * ctypes.sizeof(ctypes.c_void_p)
     assert _abi.OkpDecodeParams.outlier_distance.offset == 16
 
@@ -86,8 +87,11 @@ def test_argument_validation_happens_on_the_host(lib):
     assert lib.okp_extract_peaks_f32(None, 1, 0, 64, 64, ctypes.byref(prm), ctypes.byref(tables), None, 0, None) == -2
     assert lib.okp_extract_peaks_f32(None, 0, 3, 64, 64, ctypes.byref(prm), ctypes.byref(tables), None, 0, None) == 0
     bad = _abi.make_params()
-    bad.nms_size = 3
+    bad.nms_size = 7
     assert lib.okp_extract_peaks_f32(None, 1, 3, 64, 64, ctypes.byref(bad), ctypes.byref(tables), None, 0, None) == -4
+    bad = _abi.make_params()
+    bad.top_k = 64                                            # more than max_peaks
+    assert lib.okp_extract_peaks_f32(None, 1, 3, 64, 64, ctypes.byref(bad), ctypes.byref(tables), None, 0, None) == -3
     bad = _abi.make_params()
     bad.max_peaks = 100000
     assert lib.okp_extract_peaks_f32(None, 1, 3, 64, 64, ctypes.byref(bad), ctypes.byref(tables), None, 0, None) == -3
