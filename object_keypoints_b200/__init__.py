@@ -16,5 +16,6 @@ from .pipeline import (DecodeTables, KeypointDecoder, InferenceComponent, Keypoi
 from .triangulation import (TriangulationComponent, triangulate, triangulate_multiview, triangulate_stereo,   # noqa: F401
                             undistort_points, project_points, reprojection_filter, correct_matches, associate,
                             AssociationComponent)
+from . import evaluation, producer, sharding, targets                # noqa: F401,E402
 
 __version__ = "0.1.0"
