@@ -43,7 +43,7 @@ okp_rasterise_targets_kernel(const double* __restrict__ keypoints, const double*
     for (int i = 0; i < c; ++i) first += config.cfg[i];
     const int count = config.cfg[c];
     const double inv_scale2 = prm.length_scale * prm.length_scale;
-    const double radius2 = prm.center_radius * prm.center_radius;
+    const double radius2 = prm.center_radius * prm.center_radius * (1.0 + 1e-12);   // loose superset of the disc
     const size_t HW = (size_t)H * W;
     float* heat_map = heat + ((size_t)n * C + c) * HW;
     float* depth_map = depth + ((size_t)n * C + c) * HW;
@@ -66,8 +66,8 @@ okp_rasterise_targets_kernel(const double* __restrict__ keypoints, const double*
                     h = (float)((double)h + exp(-(dx * dx + dy * dy) / inv_scale2));
                 }
                 // _compute_depth / _compute_centers: discs around the keypoint, later keypoints overwrite
-                // sqrt only inside the disc's bounding circle: d2 >= r^2 already implies sqrt(d2) >= r (sqrt is monotone
-                // and sqrt(r^2) == r for the radii used), the reference's own comparison decides the rest
+                // sqrt only inside a slightly enlarged disc (d2 >= r^2 (1 + 1e-12) implies sqrt(d2) >= r); the reference's own
+                // comparison decides the rest
                 const double ddx = x - pxc, ddy = y - pyc, d2 = ddx * ddx + ddy * ddy;
                 if (d2 < radius2 && sqrt(d2) < prm.center_radius) {
                     z = (float)s_z[g * Kp + k];
