@@ -316,8 +316,12 @@ def run_ours(args):
             'e2e': {'value': world * e2e_frames / (e2e_ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'frames_per_step': e2e_frames, 'steps': e2e_steps,
                     'host_input_bytes_per_step': sum(t.numel() * t.element_size() for t in host),
-                    'note': 'heatmaps copied from pinned host memory in chunks overlapped with decode; depth and centre '
-                            'maps (gather-only) are read in place from pinned host memory over PCIe'},
+                    'sparse_chunks': decoder.host_chunks_sparse,
+                    'note': 'pinned host tensors in, pinned host tables out, chunks of 256 frames pipelined (host pass / PCIe / '
+                            'decode). Heatmaps: a host pass (OpenMP + AVX2, inside the timed region) marks the 4x16-pixel tiles '
+                            'within reach of a value above threshold / 25 and only those cross PCIe (bit-identical tables, '
+                            'csrc/okp_sparse.cuh; dense copy when more than half of a chunk is marked). Depth and centre maps '
+                            '(gather-only) are read in place from pinned host memory over PCIe'},
             'gpu_launches': args.steps * (3 + (1 if world > 1 else 0)),
             'clocks': clocks,
         }

@@ -287,6 +287,27 @@ int okp_rasterise_targets_f32(const double* keypoints_dev, const double* depths_
                               double length_scale, double center_radius, float* heat_dev, float* centers_dev,
                               float* depth_dev, void* stream);
 
+/* Sparse host -> device transfer of heatmaps for callers that hold them in HOST memory (the reference hands
+ * ObjectKeypointPipeline.__call__ CPU tensors, pipeline.py:24-28,184-186). A trained network's heatmaps are almost
+ * empty, and a pixel farther than 4 px from every pixel above threshold / 25 can neither be a peak nor beat one in
+ * the NMS comparison (its 5x5 box sum stays below the threshold), so replacing such regions by +0 leaves every table
+ * bit-identical (proof: csrc/okp_sparse.cuh). okp_host_pack_tiles_f32 runs on the HOST (OpenMP, `threads` <= 0 = all
+ * cores): it marks the 4 x 16-pixel tiles of heat_host [maps,H,W] that hold a value above threshold / 25, widens the
+ * marks by one tile in every direction and packs the marked tiles into packed_host [capacity_tiles, 64] with
+ * tile_ids_host [capacity_tiles] = map * tiles_per_map + tile. scratch_host: okp_host_pack_scratch_bytes() bytes;
+ * map_offsets_host: [maps + 1]. *n_tiles_out is the number of marked tiles; if it exceeds capacity_tiles nothing is
+ * packed and the caller copies the maps densely (dense inputs, e.g. an untrained network). Only for nms_size 5,
+ * box_sum 1 (the reference's configuration) and threshold > 0. */
+size_t okp_host_pack_scratch_bytes(int maps, int H, int W);
+int okp_host_pack_tiles_f32(const float* heat_host, int maps, int H, int W, float threshold,
+                            unsigned char* scratch_host, long long* map_offsets_host, int32_t* tile_ids_host,
+                            float* packed_host, long long capacity_tiles, long long* n_tiles_out, int threads);
+
+/* Device side of the sparse transfer: writes the n_tiles packed tiles into heat_dev [maps,H,W], which the caller has
+ * zeroed (cudaMemsetAsync) on the same stream. */
+int okp_scatter_tiles_f32(const float* packed_dev, const int32_t* tile_ids_dev, long long n_tiles, int maps, int H,
+                          int W, float* heat_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

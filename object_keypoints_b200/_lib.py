@@ -19,7 +19,7 @@ EXPORTS = [
     'okp_triangulate_robust_f64', 'okp_host_alias', 'okp_correct_matches_f64', 'okp_stereo_associate_f64',
     'okp_extract_peaks_bf16', 'okp_group_objects_bf16', 'okp_decode_bf16',
     'okp_eval_match_f64', 'okp_eval_summary_f64', 'okp_record_doubles', 'okp_pack_records_f64',
-    'okp_rasterise_targets_f32',
+    'okp_rasterise_targets_f32', 'okp_host_pack_scratch_bytes', 'okp_host_pack_tiles_f32', 'okp_scatter_tiles_f32',
 ]
 
 
@@ -33,8 +33,15 @@ def build(verbose=False):
     """Compile csrc/okp_api.cu for sm_100a into libokp.so (nvcc cross-compiles without a GPU)."""
     import subprocess
     src = os.path.join(_HERE, 'csrc', 'okp_api.cu')
+    # the host side of the sparse transfer is plain C++ (OpenMP + AVX2): g++ compiles it, nvcc links it in
+    host_src = os.path.join(_HERE, 'csrc', 'okp_host_pack.cpp')
+    host_obj = os.path.join(_HERE, 'csrc', 'okp_host_pack.o')
+    host = subprocess.run(['g++', '-O3', '-mavx2', '-fopenmp', '-fPIC', '-std=c++17', '-c', host_src, '-o', host_obj],
+                          capture_output=True, text=True)
+    if host.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + host.stdout + host.stderr)
     cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
-           '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static', '-o', LIBRARY_PATH, src]
+           '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static', '-o', LIBRARY_PATH, src, host_obj, '-lgomp']
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')
@@ -114,6 +121,13 @@ def lib():
     L.okp_rasterise_targets_f32.restype = i32
     L.okp_rasterise_targets_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, P(ctypes.c_int32), i32, dbl, dbl,
                                             vp, vp, vp, vp]
+    L.okp_host_pack_scratch_bytes.restype = sz
+    L.okp_host_pack_scratch_bytes.argtypes = [i32, i32, i32]
+    L.okp_host_pack_tiles_f32.restype = i32
+    L.okp_host_pack_tiles_f32.argtypes = [vp, i32, i32, i32, ctypes.c_float, vp, vp, vp, vp, ctypes.c_longlong,
+                                          P(ctypes.c_longlong), i32]
+    L.okp_scatter_tiles_f32.restype = i32
+    L.okp_scatter_tiles_f32.argtypes = [vp, vp, ctypes.c_longlong, i32, i32, i32, vp, vp]
     _LIB = L
     return L
 

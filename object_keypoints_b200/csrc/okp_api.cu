@@ -15,6 +15,7 @@
 #include "okp_eval.cuh"
 #include "okp_records.cuh"
 #include "okp_targets.cuh"
+#include "okp_sparse.cuh"
 
 namespace {
 
@@ -463,6 +464,20 @@ int okp_rasterise_targets_f32(const double* keypoints_dev, const double* depths_
     if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<(unsigned)((long long)N * C), 256, smem, (cudaStream_t)stream>>>(
         keypoints_dev, depths_dev, n_objects_dev, N, G, Kp, C, H, W, config, prm, heat_dev, centers_dev, depth_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_scatter_tiles_f32(const float* packed_dev, const int32_t* tile_ids_dev, long long n_tiles, int maps, int H, int W,
+                          float* heat_dev, void* stream) {
+    if (n_tiles < 0 || maps < 0 || H < 1 || W < 1) return OKP_E_SHAPE;
+    if (n_tiles == 0) return OKP_OK;
+    if (!packed_dev || !tile_ids_dev || !heat_dev) return OKP_E_NULL;
+    if ((uintptr_t)packed_dev & 15u) return OKP_E_UNSUPPORTED;
+    const int TX = okp_tiles_x(W), tiles = okp_tiles_y(H) * TX;
+    const long long threads = n_tiles * 16;
+    okp_scatter_tiles_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        packed_dev, tile_ids_dev, n_tiles, H, W, TX, tiles, heat_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

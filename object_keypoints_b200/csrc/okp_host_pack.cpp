@@ -1,0 +1,110 @@
+// okp_host_pack.cpp -- HOST side of the sparse heatmap transfer (see csrc/okp_sparse.cuh for the argument why
+// dropping empty regions leaves every table bit-identical). Plain C++ with OpenMP and AVX2, compiled by g++ and linked
+// into libokp.so: the pass has to run at memory speed (it reads every heatmap byte once), otherwise it would be slower
+// than the PCIe copy it replaces.
+#include <immintrin.h>
+#include <math.h>
+#include <omp.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/okp.h"
+
+#define OKP_TILE_H 4
+#define OKP_TILE_W 16
+#define OKP_TILE_FLOATS (OKP_TILE_H * OKP_TILE_W)
+
+static inline int tiles_y(int H) { return (H + OKP_TILE_H - 1) / OKP_TILE_H; }
+static inline int tiles_x(int W) { return (W + OKP_TILE_W - 1) / OKP_TILE_W; }
+
+// marks[ty * TX + tx] |= 1 if the tile holds a value that is NOT <= tau (so NaN counts as active: it must reach the
+// device unchanged). Row-wise: one pass over the map in memory order.
+static void mark_active_tiles(const float* map, int H, int W, float tau, unsigned char* marks, int TX) {
+    const __m256 vtau = _mm256_set1_ps(tau);
+    const int full = W / OKP_TILE_W;                       // tile columns that are 16 wide
+    for (int y = 0; y < H; ++y) {
+        const float* row = map + (size_t)y * W;
+        unsigned char* mrow = marks + (size_t)(y / OKP_TILE_H) * TX;
+        for (int tx = 0; tx < full; ++tx) {
+            const __m256 a = _mm256_loadu_ps(row + tx * OKP_TILE_W), b = _mm256_loadu_ps(row + tx * OKP_TILE_W + 8);
+            const __m256 hit = _mm256_or_ps(_mm256_cmp_ps(a, vtau, _CMP_NLE_UQ), _mm256_cmp_ps(b, vtau, _CMP_NLE_UQ));
+            mrow[tx] |= (unsigned char)(_mm256_movemask_ps(hit) != 0);
+        }
+        if (full < TX) {
+            unsigned char any = 0;
+            for (int x = full * OKP_TILE_W; x < W; ++x) any |= (unsigned char)!(row[x] <= tau);
+            mrow[full] |= any;
+        }
+    }
+}
+
+extern "C" size_t okp_host_pack_scratch_bytes(int maps, int H, int W) {
+    if (maps < 0 || H < 1 || W < 1) return 0;
+    return (size_t)maps * 2 * tiles_y(H) * tiles_x(W) + 64;
+}
+
+extern "C" int okp_host_pack_tiles_f32(const float* heat_host, int maps, int H, int W, float threshold,
+                                       unsigned char* scratch_host, long long* map_offsets_host,
+                                       int32_t* tile_ids_host, float* packed_host, long long capacity_tiles,
+                                       long long* n_tiles_out, int threads) {
+    if (maps < 0 || H < 1 || W < 1) return OKP_E_SHAPE;
+    if (!n_tiles_out) return OKP_E_NULL;
+    *n_tiles_out = 0;
+    if (maps == 0) return OKP_OK;
+    if (!heat_host || !scratch_host || !map_offsets_host || !tile_ids_host || !packed_host) return OKP_E_NULL;
+    const int TY = tiles_y(H), TX = tiles_x(W), tiles = TY * TX;
+    if ((long long)maps * tiles > 0x7fffffffLL) return OKP_E_SHAPE;
+    // a box sum above the threshold needs a value above threshold / 25; the slack covers the 24 float32 roundings
+    const float tau = threshold > 0.0f ? threshold / 25.0f * (1.0f - 1e-5f) : -INFINITY;
+    if (threads <= 0) threads = omp_get_max_threads();
+    // pass 1: per map, activity marks -> marks widened by one tile in every direction, and their count
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
+    for (int m = 0; m < maps; ++m) {
+        unsigned char* raw = scratch_host + (size_t)m * 2 * tiles;
+        unsigned char* wide = raw + tiles;
+        memset(raw, 0, (size_t)tiles);
+        mark_active_tiles(heat_host + (size_t)m * H * W, H, W, tau, raw, TX);
+        long long count = 0;
+        for (int ty = 0; ty < TY; ++ty)
+            for (int tx = 0; tx < TX; ++tx) {
+                unsigned char any = 0;
+                for (int y = ty > 0 ? ty - 1 : 0; y <= ty + 1 && y < TY; ++y)
+                    for (int x = tx > 0 ? tx - 1 : 0; x <= tx + 1 && x < TX; ++x) any |= raw[y * TX + x];
+                wide[ty * TX + tx] = any;
+                count += any;
+            }
+        map_offsets_host[m + 1] = count;
+    }
+    map_offsets_host[0] = 0;
+    for (int m = 0; m < maps; ++m) map_offsets_host[m + 1] += map_offsets_host[m];
+    const long long total = map_offsets_host[maps];
+    *n_tiles_out = total;
+    if (total > capacity_tiles) return OKP_OK;            // the caller sees n_tiles > capacity and sends the maps densely
+    // pass 2: pack the marked tiles (positions beyond the map's edge are filled with +0)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
+    for (int m = 0; m < maps; ++m) {
+        const unsigned char* wide = scratch_host + (size_t)m * 2 * tiles + tiles;
+        const float* map = heat_host + (size_t)m * H * W;
+        long long at = map_offsets_host[m];
+        for (int t = 0; t < tiles; ++t) {
+            if (!wide[t]) continue;
+            const int ty = t / TX, tx = t - ty * TX;
+            const int y0 = ty * OKP_TILE_H, x0 = tx * OKP_TILE_W;
+            float* dst = packed_host + at * OKP_TILE_FLOATS;
+            if (y0 + OKP_TILE_H <= H && x0 + OKP_TILE_W <= W) {
+                for (int r = 0; r < OKP_TILE_H; ++r) {
+                    const float* src = map + (size_t)(y0 + r) * W + x0;
+                    _mm256_storeu_ps(dst + r * OKP_TILE_W, _mm256_loadu_ps(src));
+                    _mm256_storeu_ps(dst + r * OKP_TILE_W + 8, _mm256_loadu_ps(src + 8));
+                }
+            } else {
+                for (int r = 0; r < OKP_TILE_H; ++r)
+                    for (int c = 0; c < OKP_TILE_W; ++c)
+                        dst[r * OKP_TILE_W + c] = (y0 + r < H && x0 + c < W) ? map[(size_t)(y0 + r) * W + x0 + c] : 0.0f;
+            }
+            tile_ids_host[at] = m * tiles + t;
+            ++at;
+        }
+    }
+    return OKP_OK;
+}

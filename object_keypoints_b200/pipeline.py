@@ -36,6 +36,14 @@ def _stream_handle(stream=None):
     return ctypes.c_void_p(stream.cuda_stream)
 
 
+def _host_threads():
+    """Threads for the host pass of the sparse transfer: this process's share of the cores (the affinity mask divided
+    by the ranks torchrun started on this node), whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    import os
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    return max(1, cores // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))
+
+
 def _as_device_f32(x, device):
     """NumPy array / CPU tensor / CUDA tensor -> contiguous float32 CUDA tensor."""
     if isinstance(x, np.ndarray):
@@ -191,31 +199,57 @@ class KeypointDecoder:
             return None
         return alias.value
 
-    def decode_host_batch(self, heat, depth, centers, chunk_frames=256):
+    SPARSE_CAPACITY = 0.5          # fall back to the dense copy when more than this share of a chunk's tiles is marked
+
+    def _sparse_ok(self, heat, sparse):
+        """The sparse transfer holds for the reference's configuration only (csrc/okp_sparse.cuh)."""
+        if sparse in (False, 'off', None):
+            return False
+        return (self.params.nms_size == 5 and self.params.box_sum == 1 and self.params.threshold > 0.0 and
+                heat.device.type == 'cpu' and heat.dtype == torch.float32 and heat.is_contiguous())
+
+    def decode_host_batch(self, heat, depth, centers, chunk_frames=256, sparse='auto'):
         """End-to-end form for HOST inputs, the shape the reference's caller has (CPU tensors out of
-        InferenceComponent, pipeline.py:24-28). The batch is cut into chunks; the heatmaps of chunk
-        i+1 are copied host->device on a copy stream while chunk i is decoded. Depth and centre maps
-        are only gathered from (3 floats per spoke peak), so when they live in pinned host memory the
-        kernels read them in place over PCIe and 2/3 of the frame's bytes never cross the bus; pageable
-        tensors are copied like the heatmaps. The object tables of every chunk are copied back into
-        pinned host tensors. Returns a dict of CPU tensors (synchronised)."""
+        InferenceComponent, pipeline.py:24-28). The batch is cut into chunks that are pipelined: while chunk i is
+        decoded, chunk i+1 crosses PCIe and chunk i+2 is prepared on the host.
+
+        Heatmaps: with ``sparse='auto'`` a host pass (okp_host_pack_tiles_f32, OpenMP + AVX2, in a worker thread)
+        marks the 4x16-pixel tiles within reach of a value above threshold / 25 and only those cross the bus; the
+        device scatters them into a zeroed map (okp_scatter_tiles_f32). Everything farther than 4 px from such a
+        value cannot change any table (csrc/okp_sparse.cuh), so the result is bit-identical to the dense copy,
+        which is still used per chunk when more than half of its tiles are marked (dense maps) or with
+        ``sparse=False``. Depth and centre maps are only gathered from (3 values per spoke peak): when they live in
+        pinned host memory the kernels read them in place over PCIe; pageable tensors are copied like dense
+        heatmaps. The object tables of every chunk are copied back into pinned host tensors.
+        Returns a dict of CPU tensors (synchronised)."""
         N = int(heat.shape[0])
         chunk = max(1, min(chunk_frames, N))
         depth_alias = self._host_alias(depth)
         centers_alias = self._host_alias(centers)
         in_place = depth_alias is not None and centers_alias is not None
-        key = ('host', N, chunk, in_place)
+        use_sparse = self._sparse_ok(heat, sparse)
+        key = ('host', N, chunk, in_place, use_sparse)
+        tiles_per_map = ((self.H + 3) // 4) * ((self.W + 15) // 16)
+        capacity = max(1, int(self.SPARSE_CAPACITY * chunk * self.C * tiles_per_map))
         if key not in self._tables:
             staging = []
-            for _ in range(2):
+            for _ in range(3 if use_sparse else 2):
                 slot = {
                     'heat': torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device),
                     'tables': DecodeTables(chunk, self.C, self.cfg, self.params, self.device),
-                    'ready': torch.cuda.Event(), 'done': torch.cuda.Event(),
+                    'ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'copied': torch.cuda.Event(),
                 }
                 if not in_place:
                     slot['depth'] = torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device)
                     slot['centers'] = torch.empty((chunk, self.C - 1, 2, self.H, self.W), dtype=torch.float32, device=self.device)
+                if use_sparse:
+                    maps = chunk * self.C
+                    slot['packed_host'] = torch.empty((capacity, 64), dtype=torch.float32).pin_memory()
+                    slot['ids_host'] = torch.empty(capacity, dtype=torch.int32).pin_memory()
+                    slot['packed'] = torch.empty((capacity, 64), dtype=torch.float32, device=self.device)
+                    slot['ids'] = torch.empty(capacity, dtype=torch.int32, device=self.device)
+                    slot['scratch'] = np.zeros(self._lib.okp_host_pack_scratch_bytes(maps, self.H, self.W), np.uint8)
+                    slot['offsets'] = np.zeros(maps + 1, np.int64)
                 staging.append(slot)
             like = staging[0]['tables']
             result = {name: torch.empty((N,) + tuple(like[name].shape[1:]), dtype=like[name].dtype).pin_memory()
@@ -228,33 +262,78 @@ class KeypointDecoder:
         centers_frame = (self.C - 1) * 2 * self.H * self.W * 4
         cam = ctypes.byref(self._camera) if self._camera is not None else None
         self.host_bytes_copied = 0
-        for index, f0 in enumerate(range(0, N, chunk)):
-            f1 = min(f0 + chunk, N)
-            n = f1 - f0
-            slot = staging[index % 2]
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(slot['done'])          # the slot's previous decode + read-back finished
-                slot['heat'][:n].copy_(heat[f0:f1], non_blocking=True)
-                self.host_bytes_copied += n * depth_frame
-                if not in_place:
-                    slot['depth'][:n].copy_(depth[f0:f1], non_blocking=True)
-                    slot['centers'][:n].copy_(centers[f0:f1], non_blocking=True)
-                    self.host_bytes_copied += n * (depth_frame + centers_frame)
-                slot['ready'].record(copy_stream)
-            compute.wait_event(slot['ready'])
-            tables = slot['tables'] if n == chunk else self.tables(n)
-            if in_place:
-                ws = self._workspace_for(n)
-                rc = self._lib.okp_decode_f32(slot['heat'].data_ptr(), depth_alias + f0 * depth_frame,
-                                              centers_alias + f0 * centers_frame, n, self.C, self.H, self.W,
-                                              self._cfg_array, cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
-                                              ws.data_ptr(), ws.numel(), _stream_handle(compute))
-                _lib.check(rc, 'okp_decode_f32')
-            else:
-                self.decode_batch(slot['heat'][:n], slot['depth'][:n], slot['centers'][:n], tables=tables)
-            for name in self.HOST_RESULT_TABLES:
-                result[name][f0:f1].copy_(tables[name][:n], non_blocking=True)
-            slot['done'].record(compute)
+        self.host_chunks_sparse = 0
+        starts = list(range(0, N, chunk))
+
+        def pack(index):
+            """Host pass for chunk `index` into its slot's pinned staging; returns the number of marked tiles."""
+            slot = staging[index % len(staging)]
+            slot['copied'].synchronize()                  # the slot's previous transfer has left the pinned buffers
+            f0 = starts[index]
+            n = min(f0 + chunk, N) - f0
+            count = ctypes.c_longlong()
+            rc = self._lib.okp_host_pack_tiles_f32(
+                ctypes.c_void_p(heat.data_ptr() + f0 * depth_frame), n * self.C, self.H, self.W,
+                ctypes.c_float(self.params.threshold), ctypes.c_void_p(slot['scratch'].ctypes.data),
+                ctypes.c_void_p(slot['offsets'].ctypes.data), ctypes.c_void_p(slot['ids_host'].data_ptr()),
+                ctypes.c_void_p(slot['packed_host'].data_ptr()), capacity, ctypes.byref(count), _host_threads())
+            _lib.check(rc, 'okp_host_pack_tiles_f32')
+            return int(count.value)
+
+        pending = None
+        executor = None
+        if use_sparse:
+            from concurrent.futures import ThreadPoolExecutor
+            executor = ThreadPoolExecutor(max_workers=1)
+            pending = executor.submit(pack, 0)
+        try:
+            for index, f0 in enumerate(starts):
+                f1 = min(f0 + chunk, N)
+                n = f1 - f0
+                slot = staging[index % len(staging)]
+                n_tiles = None
+                if use_sparse:
+                    n_tiles = pending.result()
+                    pending = executor.submit(pack, index + 1) if index + 1 < len(starts) else None
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(slot['done'])          # the slot's previous decode + read-back finished
+                    if n_tiles is not None and n_tiles <= capacity:
+                        slot['packed'][:n_tiles].copy_(slot['packed_host'][:n_tiles], non_blocking=True)
+                        slot['ids'][:n_tiles].copy_(slot['ids_host'][:n_tiles], non_blocking=True)
+                        slot['copied'].record(copy_stream)
+                        slot['heat'][:n].zero_()
+                        rc = self._lib.okp_scatter_tiles_f32(slot['packed'].data_ptr(), slot['ids'].data_ptr(), n_tiles,
+                                                             n * self.C, self.H, self.W, slot['heat'].data_ptr(),
+                                                             ctypes.c_void_p(copy_stream.cuda_stream))
+                        _lib.check(rc, 'okp_scatter_tiles_f32')
+                        self.host_bytes_copied += n_tiles * (64 * 4 + 4)
+                        self.host_chunks_sparse += 1
+                    else:
+                        slot['heat'][:n].copy_(heat[f0:f1], non_blocking=True)
+                        slot['copied'].record(copy_stream)
+                        self.host_bytes_copied += n * depth_frame
+                    if not in_place:
+                        slot['depth'][:n].copy_(depth[f0:f1], non_blocking=True)
+                        slot['centers'][:n].copy_(centers[f0:f1], non_blocking=True)
+                        self.host_bytes_copied += n * (depth_frame + centers_frame)
+                    slot['ready'].record(copy_stream)
+                compute.wait_event(slot['ready'])
+                tables = slot['tables'] if n == chunk else self.tables(n)
+                if in_place:
+                    ws = self._workspace_for(n)
+                    rc = self._lib.okp_decode_f32(slot['heat'].data_ptr(), depth_alias + f0 * depth_frame,
+                                                  centers_alias + f0 * centers_frame, n, self.C, self.H, self.W,
+                                                  self._cfg_array, cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                                                  ws.data_ptr(), ws.numel(), _stream_handle(compute))
+                    _lib.check(rc, 'okp_decode_f32')
+                else:
+                    self.decode_batch(slot['heat'][:n], slot['depth'][:n], slot['centers'][:n], tables=tables)
+                for name in self.HOST_RESULT_TABLES:
+                    result[name][f0:f1].copy_(tables[name][:n], non_blocking=True)
+                slot['done'].record(compute)
+        finally:
+            if executor is not None:
+                executor.shutdown(wait=True)
         compute.synchronize()
         return result
 

@@ -306,7 +306,7 @@ def test_host_batch_in_place_gather_equals_device_decode():
     assert decoder._host_alias(pinned[1]) is not None, "pinned host memory must be device-accessible on this box"
     assert decoder._host_alias(host[1]) is None
     for inputs, copied_maps in ((pinned, 1), (host, 3)):
-        got = decoder.decode_host_batch(*inputs, chunk_frames=16)
+        got = decoder.decode_host_batch(*inputs, chunk_frames=16, sparse=False)
         for name in KeypointDecoder.HOST_RESULT_TABLES:
             np.testing.assert_array_equal(got[name].numpy().view(np.uint8), want[name].view(np.uint8), err_msg=name)
         if copied_maps == 1:
@@ -404,3 +404,45 @@ def test_record_pack_kernel_equals_the_torch_packing():
         assert torch.equal(got, want)
     back = sharding.unpack_records(got, tables)
     assert torch.equal(back['kp_point'], tables['kp_point']) and torch.equal(back['n_objects'], tables['n_objects'])
+
+
+def test_sparse_host_transfer_gives_the_tables_of_the_dense_copy():
+    """decode_host_batch(sparse='auto'): only the tiles within reach of a value above threshold / 25 cross PCIe
+    (okp_host_pack_tiles_f32 + okp_scatter_tiles_f32); tables must be bitwise those of the dense copy -- clean frames,
+    the adversarial maps (plateaus, ties, borders, negative values) and dense maps (fallback to the dense copy)."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    from test_filter_bound import cases
+    cfg = [1, 3]
+    camera = synthetic.default_camera((64, 64))
+    batch = synthetic.make_batch(41, cfg, (64, 64), seed=13, objects=(1, 3))
+    heat = batch.heat.copy()
+    heat[5] = 0.5                                                        # a dense frame inside a sparse chunk
+    heat[7, 1, 30:34, 30:34] = np.nan
+    heat[9, 2, 10, 10] = -0.3
+    adversarial = [p for p in cases().values() if p.shape == (64, 64)]
+    for i, p in enumerate(adversarial[:12]):
+        heat[20 + i, i % 3] = p
+    decoder = KeypointDecoder(cfg, (64, 64), camera=camera, max_peaks=64)
+    host = [torch.from_numpy(a).pin_memory() for a in (heat, batch.depth, batch.centers)]
+    dense = decoder.decode_host_batch(*host, chunk_frames=8, sparse=False)
+    dense = {k: v.clone() for k, v in dense.items()}
+    dense_bytes = decoder.host_bytes_copied
+    sparse = decoder.decode_host_batch(*host, chunk_frames=8, sparse='auto')
+    assert decoder.host_chunks_sparse >= 4 and decoder.host_bytes_copied < 0.6 * dense_bytes
+    for name in KeypointDecoder.HOST_RESULT_TABLES:
+        np.testing.assert_array_equal(sparse[name].numpy().view(np.uint8), dense[name].numpy().view(np.uint8), err_msg=name)
+    # all-dense input: every chunk falls back to the plain copy
+    full = [torch.from_numpy(np.full_like(heat[:8], 0.4)).pin_memory(), host[1][:8], host[2][:8]]
+    decoder.decode_host_batch(*full, chunk_frames=8, sparse='auto')
+    assert decoder.host_chunks_sparse == 0 and decoder.host_bytes_copied == full[0].numel() * 4
+    # 180x320 (partial tile rows: 180 = 45 x 4, 320 = 20 x 16) and a ragged size, pageable heatmaps
+    for size in ((180, 320), (37, 93)):
+        b = synthetic.make_batch(6, cfg, size, seed=size[0], objects=(1, 2), **(dict(center_separation=18.0, spoke_radius=(4.0, 6.0), peak_separation=5.0, border=3.0) if size[0] < 64 else {}))
+        dec = KeypointDecoder(cfg, size, camera=synthetic.default_camera((180, 320)) if size == (180, 320) else camera)
+        inputs = [torch.from_numpy(a) for a in (b.heat, b.depth, b.centers)]
+        want = {k: v.clone() for k, v in dec.decode_host_batch(*inputs, chunk_frames=4, sparse=False).items()}
+        got = dec.decode_host_batch(*inputs, chunk_frames=4, sparse='auto')
+        assert dec.host_chunks_sparse == 2
+        for name in KeypointDecoder.HOST_RESULT_TABLES:
+            np.testing.assert_array_equal(got[name].numpy().view(np.uint8), want[name].numpy().view(np.uint8), err_msg=name)
