@@ -340,7 +340,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='config4_180x320', choices=sorted(WORKLOADS))
     ap.add_argument('--frames', type=int, default=0, help="frames per GPU (default: the workload's)")
-    ap.add_argument('--e2e-frames', type=int, default=1024)
+    ap.add_argument('--e2e-frames', type=int, default=2048)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--exchange', default='gather', choices=['gather', 'allgather'],

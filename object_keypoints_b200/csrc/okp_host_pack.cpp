@@ -22,18 +22,38 @@ static inline int tiles_x(int W) { return (W + OKP_TILE_W - 1) / OKP_TILE_W; }
 static void mark_active_tiles(const float* map, int H, int W, float tau, unsigned char* marks, int TX) {
     const __m256 vtau = _mm256_set1_ps(tau);
     const int full = W / OKP_TILE_W;                       // tile columns that are 16 wide
-    for (int y = 0; y < H; ++y) {
-        const float* row = map + (size_t)y * W;
-        unsigned char* mrow = marks + (size_t)(y / OKP_TILE_H) * TX;
-        for (int tx = 0; tx < full; ++tx) {
-            const __m256 a = _mm256_loadu_ps(row + tx * OKP_TILE_W), b = _mm256_loadu_ps(row + tx * OKP_TILE_W + 8);
-            const __m256 hit = _mm256_or_ps(_mm256_cmp_ps(a, vtau, _CMP_NLE_UQ), _mm256_cmp_ps(b, vtau, _CMP_NLE_UQ));
-            mrow[tx] |= (unsigned char)(_mm256_movemask_ps(hit) != 0);
+    const int TY = tiles_y(H);
+    for (int ty = 0; ty < TY; ++ty) {
+        const int y0 = ty * OKP_TILE_H, rows = y0 + OKP_TILE_H <= H ? OKP_TILE_H : H - y0;
+        const float* base = map + (size_t)y0 * W;
+        unsigned char* mrow = marks + (size_t)ty * TX;
+        if (rows == OKP_TILE_H) {                          // four row streams, one mark store per tile
+            const float *r0 = base, *r1 = base + W, *r2 = base + 2 * (size_t)W, *r3 = base + 3 * (size_t)W;
+            for (int tx = 0; tx < full; ++tx) {
+                const int x = tx * OKP_TILE_W;
+                __m256 hit = _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r0 + x), vtau, _CMP_NLE_UQ),
+                                          _mm256_cmp_ps(_mm256_loadu_ps(r0 + x + 8), vtau, _CMP_NLE_UQ));
+                hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r1 + x), vtau, _CMP_NLE_UQ),
+                                                     _mm256_cmp_ps(_mm256_loadu_ps(r1 + x + 8), vtau, _CMP_NLE_UQ)));
+                hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r2 + x), vtau, _CMP_NLE_UQ),
+                                                     _mm256_cmp_ps(_mm256_loadu_ps(r2 + x + 8), vtau, _CMP_NLE_UQ)));
+                hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r3 + x), vtau, _CMP_NLE_UQ),
+                                                     _mm256_cmp_ps(_mm256_loadu_ps(r3 + x + 8), vtau, _CMP_NLE_UQ)));
+                mrow[tx] = (unsigned char)(_mm256_movemask_ps(hit) != 0);
+            }
+        } else {
+            for (int tx = 0; tx < full; ++tx) {
+                unsigned char any = 0;
+                for (int r = 0; r < rows; ++r)
+                    for (int c = 0; c < OKP_TILE_W; ++c) any |= (unsigned char)!(base[(size_t)r * W + tx * OKP_TILE_W + c] <= tau);
+                mrow[tx] = any;
+            }
         }
         if (full < TX) {
             unsigned char any = 0;
-            for (int x = full * OKP_TILE_W; x < W; ++x) any |= (unsigned char)!(row[x] <= tau);
-            mrow[full] |= any;
+            for (int r = 0; r < rows; ++r)
+                for (int x = full * OKP_TILE_W; x < W; ++x) any |= (unsigned char)!(base[(size_t)r * W + x] <= tau);
+            mrow[full] = any;
         }
     }
 }
@@ -62,7 +82,6 @@ extern "C" int okp_host_pack_tiles_f32(const float* heat_host, int maps, int H, 
     for (int m = 0; m < maps; ++m) {
         unsigned char* raw = scratch_host + (size_t)m * 2 * tiles;
         unsigned char* wide = raw + tiles;
-        memset(raw, 0, (size_t)tiles);
         mark_active_tiles(heat_host + (size_t)m * H * W, H, W, tau, raw, TX);
         long long count = 0;
         for (int ty = 0; ty < TY; ++ty)

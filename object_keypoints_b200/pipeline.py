@@ -283,8 +283,10 @@ class KeypointDecoder:
         pending = None
         executor = None
         if use_sparse:
-            from concurrent.futures import ThreadPoolExecutor
-            executor = ThreadPoolExecutor(max_workers=1)
+            if getattr(self, '_pack_executor', None) is None:      # one long-lived worker: its OpenMP team is reused
+                from concurrent.futures import ThreadPoolExecutor
+                self._pack_executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix='okp-pack')
+            executor = self._pack_executor
             pending = executor.submit(pack, 0)
         try:
             for index, f0 in enumerate(starts):
@@ -332,8 +334,8 @@ class KeypointDecoder:
                     result[name][f0:f1].copy_(tables[name][:n], non_blocking=True)
                 slot['done'].record(compute)
         finally:
-            if executor is not None:
-                executor.shutdown(wait=True)
+            if pending is not None:                           # an exception above: do not leave a pass running
+                pending.cancel() or pending.exception()
         compute.synchronize()
         return result
 
