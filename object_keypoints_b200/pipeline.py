@@ -13,6 +13,7 @@ Two levels:
   interface, converting the tables to the reference's nested lists / dicts.
 """
 import ctypes
+import time
 
 import numpy as np
 import torch
@@ -216,9 +217,11 @@ class KeypointDecoder:
         Heatmaps: with ``sparse='auto'`` a host pass (okp_host_pack_tiles_f32, OpenMP + AVX2, in a worker thread)
         marks the 4x16-pixel tiles within reach of a value above threshold / 25 and only those cross the bus; the
         device scatters them into a zeroed map (okp_scatter_tiles_f32). Everything farther than 4 px from such a
-        value cannot change any table (csrc/okp_sparse.cuh), so the result is bit-identical to the dense copy,
-        which is still used per chunk when more than half of its tiles are marked (dense maps) or with
-        ``sparse=False``. Depth and centre maps are only gathered from (3 values per spoke peak): when they live in
+        value cannot change any table (csrc/okp_sparse.cuh), so the result is bit-identical to the dense copy.
+        The host pass is bound by host memory bandwidth and the dense copy by PCIe, so both run side by side: chunks
+        are handed to the host pass one after the other, and whenever the copy engine has fewer than two dense
+        chunks queued the next chunk goes over the bus as it is. A chunk with more than half of its tiles marked
+        (dense maps) is copied densely too; ``sparse=False`` disables the host pass. Depth and centre maps are only gathered from (3 values per spoke peak): when they live in
         pinned host memory the kernels read them in place over PCIe; pageable tensors are copied like dense
         heatmaps. The object tables of every chunk are copied back into pinned host tensors.
         Returns a dict of CPU tensors (synchronised)."""
@@ -233,7 +236,7 @@ class KeypointDecoder:
         capacity = max(1, int(self.SPARSE_CAPACITY * chunk * self.C * tiles_per_map))
         if key not in self._tables:
             staging = []
-            for _ in range(3 if use_sparse else 2):
+            for slot_index in range(5 if use_sparse else 2):       # sparse: three packing slots, two dense-copy slots
                 slot = {
                     'heat': torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device),
                     'tables': DecodeTables(chunk, self.C, self.cfg, self.params, self.device),
@@ -242,7 +245,7 @@ class KeypointDecoder:
                 if not in_place:
                     slot['depth'] = torch.empty((chunk, self.C, self.H, self.W), dtype=torch.float32, device=self.device)
                     slot['centers'] = torch.empty((chunk, self.C - 1, 2, self.H, self.W), dtype=torch.float32, device=self.device)
-                if use_sparse:
+                if use_sparse and slot_index < 3:
                     maps = chunk * self.C
                     slot['packed_host'] = torch.empty((capacity, 64), dtype=torch.float32).pin_memory()
                     slot['ids_host'] = torch.empty(capacity, dtype=torch.int32).pin_memory()
@@ -265,9 +268,8 @@ class KeypointDecoder:
         self.host_chunks_sparse = 0
         starts = list(range(0, N, chunk))
 
-        def pack(index):
-            """Host pass for chunk `index` into its slot's pinned staging; returns the number of marked tiles."""
-            slot = staging[index % len(staging)]
+        def pack(index, slot):
+            """Host pass for chunk `index` into the slot's pinned staging; returns the number of marked tiles."""
             slot['copied'].synchronize()                  # the slot's previous transfer has left the pinned buffers
             f0 = starts[index]
             n = min(f0 + chunk, N) - f0
@@ -280,62 +282,93 @@ class KeypointDecoder:
             _lib.check(rc, 'okp_host_pack_tiles_f32')
             return int(count.value)
 
-        pending = None
-        executor = None
+        def enqueue(index, slot, n_tiles):
+            """Transfer (sparse if n_tiles fits, else dense) + decode + read-back of chunk `index`, all asynchronous."""
+            f0 = starts[index]
+            f1 = min(f0 + chunk, N)
+            n = f1 - f0
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(slot['done'])              # the slot's previous decode + read-back finished
+                if n_tiles is not None and n_tiles <= capacity:
+                    slot['packed'][:n_tiles].copy_(slot['packed_host'][:n_tiles], non_blocking=True)
+                    slot['ids'][:n_tiles].copy_(slot['ids_host'][:n_tiles], non_blocking=True)
+                    slot['copied'].record(copy_stream)
+                    slot['heat'][:n].zero_()
+                    rc = self._lib.okp_scatter_tiles_f32(slot['packed'].data_ptr(), slot['ids'].data_ptr(), n_tiles,
+                                                         n * self.C, self.H, self.W, slot['heat'].data_ptr(),
+                                                         ctypes.c_void_p(copy_stream.cuda_stream))
+                    _lib.check(rc, 'okp_scatter_tiles_f32')
+                    self.host_bytes_copied += n_tiles * (64 * 4 + 4)
+                    self.host_chunks_sparse += 1
+                else:
+                    slot['heat'][:n].copy_(heat[f0:f1], non_blocking=True)
+                    slot['copied'].record(copy_stream)
+                    self.host_bytes_copied += n * depth_frame
+                if not in_place:
+                    slot['depth'][:n].copy_(depth[f0:f1], non_blocking=True)
+                    slot['centers'][:n].copy_(centers[f0:f1], non_blocking=True)
+                    self.host_bytes_copied += n * (depth_frame + centers_frame)
+                slot['ready'].record(copy_stream)
+            compute.wait_event(slot['ready'])
+            tables = slot['tables'] if n == chunk else self.tables(n)
+            if in_place:
+                ws = self._workspace_for(n)
+                rc = self._lib.okp_decode_f32(slot['heat'].data_ptr(), depth_alias + f0 * depth_frame,
+                                              centers_alias + f0 * centers_frame, n, self.C, self.H, self.W,
+                                              self._cfg_array, cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                                              ws.data_ptr(), ws.numel(), _stream_handle(compute))
+                _lib.check(rc, 'okp_decode_f32')
+            else:
+                self.decode_batch(slot['heat'][:n], slot['depth'][:n], slot['centers'][:n], tables=tables)
+            for name in self.HOST_RESULT_TABLES:
+                result[name][f0:f1].copy_(tables[name][:n], non_blocking=True)
+            slot['done'].record(compute)
+
+        # Chunks are independent (each writes its own rows of the result), so they are handed out to two producers
+        # that run side by side: the host pass (CPU-bound; its chunks need a sixth of the PCIe time) and, with
+        # sparse='auto', the plain dense copy (PCIe-bound; needs no CPU) whenever the copy engine has less than two
+        # dense chunks queued. Host memory bandwidth and the PCIe link are both kept busy.
+        claimed = 0
+        sparse_slots = staging[:3] if use_sparse else []
+        dense_slots = staging[3:] if use_sparse else staging
+        packing = None                                            # (future, chunk index, slot)
+        packed_chunks = dense_chunks = 0
+        dense_events = []
         if use_sparse:
             if getattr(self, '_pack_executor', None) is None:      # one long-lived worker: its OpenMP team is reused
                 from concurrent.futures import ThreadPoolExecutor
                 self._pack_executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix='okp-pack')
-            executor = self._pack_executor
-            pending = executor.submit(pack, 0)
+            packing = (self._pack_executor.submit(pack, 0, sparse_slots[0]), 0, sparse_slots[0])
+            claimed = 1
         try:
-            for index, f0 in enumerate(starts):
-                f1 = min(f0 + chunk, N)
-                n = f1 - f0
-                slot = staging[index % len(staging)]
-                n_tiles = None
-                if use_sparse:
-                    n_tiles = pending.result()
-                    pending = executor.submit(pack, index + 1) if index + 1 < len(starts) else None
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(slot['done'])          # the slot's previous decode + read-back finished
-                    if n_tiles is not None and n_tiles <= capacity:
-                        slot['packed'][:n_tiles].copy_(slot['packed_host'][:n_tiles], non_blocking=True)
-                        slot['ids'][:n_tiles].copy_(slot['ids_host'][:n_tiles], non_blocking=True)
-                        slot['copied'].record(copy_stream)
-                        slot['heat'][:n].zero_()
-                        rc = self._lib.okp_scatter_tiles_f32(slot['packed'].data_ptr(), slot['ids'].data_ptr(), n_tiles,
-                                                             n * self.C, self.H, self.W, slot['heat'].data_ptr(),
-                                                             ctypes.c_void_p(copy_stream.cuda_stream))
-                        _lib.check(rc, 'okp_scatter_tiles_f32')
-                        self.host_bytes_copied += n_tiles * (64 * 4 + 4)
-                        self.host_chunks_sparse += 1
-                    else:
-                        slot['heat'][:n].copy_(heat[f0:f1], non_blocking=True)
-                        slot['copied'].record(copy_stream)
-                        self.host_bytes_copied += n * depth_frame
-                    if not in_place:
-                        slot['depth'][:n].copy_(depth[f0:f1], non_blocking=True)
-                        slot['centers'][:n].copy_(centers[f0:f1], non_blocking=True)
-                        self.host_bytes_copied += n * (depth_frame + centers_frame)
-                    slot['ready'].record(copy_stream)
-                compute.wait_event(slot['ready'])
-                tables = slot['tables'] if n == chunk else self.tables(n)
-                if in_place:
-                    ws = self._workspace_for(n)
-                    rc = self._lib.okp_decode_f32(slot['heat'].data_ptr(), depth_alias + f0 * depth_frame,
-                                                  centers_alias + f0 * centers_frame, n, self.C, self.H, self.W,
-                                                  self._cfg_array, cam, ctypes.byref(self.params), ctypes.byref(tables.struct),
-                                                  ws.data_ptr(), ws.numel(), _stream_handle(compute))
-                    _lib.check(rc, 'okp_decode_f32')
-                else:
-                    self.decode_batch(slot['heat'][:n], slot['depth'][:n], slot['centers'][:n], tables=tables)
-                for name in self.HOST_RESULT_TABLES:
-                    result[name][f0:f1].copy_(tables[name][:n], non_blocking=True)
-                slot['done'].record(compute)
+            while claimed < len(starts) or packing is not None:
+                progressed = False
+                if packing is not None and packing[0].done():
+                    future, index, slot = packing
+                    n_tiles = future.result()
+                    packed_chunks += 1
+                    packing = None
+                    if claimed < len(starts):
+                        nxt = sparse_slots[packed_chunks % len(sparse_slots)]
+                        packing = (self._pack_executor.submit(pack, claimed, nxt), claimed, nxt)
+                        claimed += 1
+                    enqueue(index, slot, n_tiles)
+                    progressed = True
+                elif claimed < len(starts) and dense_slots:
+                    dense_events = [e for e in dense_events if not e.query()]
+                    if not use_sparse or len(dense_events) < 2:
+                        slot = dense_slots[dense_chunks % len(dense_slots)]
+                        dense_chunks += 1
+                        enqueue(claimed, slot, None)
+                        claimed += 1
+                        if use_sparse:
+                            dense_events.append(slot['ready'])
+                        progressed = True
+                if not progressed:
+                    time.sleep(5e-5)
         finally:
-            if pending is not None:                           # an exception above: do not leave a pass running
-                pending.cancel() or pending.exception()
+            if packing is not None:                                # an exception above: do not leave a pass running
+                packing[0].cancel() or packing[0].exception()
         compute.synchronize()
         return result
 
