@@ -221,7 +221,8 @@ class KeypointDecoder:
         The host pass is bound by host memory bandwidth and the dense copy by PCIe, so both run side by side: chunks
         are handed to the host pass one after the other, and whenever the copy engine has fewer than two dense
         chunks queued the next chunk goes over the bus as it is. A chunk with more than half of its tiles marked
-        (dense maps) is copied densely too; ``sparse=False`` disables the host pass. Depth and centre maps are only gathered from (3 values per spoke peak): when they live in
+        (dense maps) is copied densely too; ``sparse=False`` disables the host pass, ``sparse='only'`` the side-by-side
+        dense copies. Depth and centre maps are only gathered from (3 values per spoke peak): when they live in
         pinned host memory the kernels read them in place over PCIe; pageable tensors are copied like dense
         heatmaps. The object tables of every chunk are copied back into pinned host tensors.
         Returns a dict of CPU tensors (synchronised)."""
@@ -356,7 +357,7 @@ class KeypointDecoder:
                     progressed = True
                 elif claimed < len(starts) and dense_slots:
                     dense_events = [e for e in dense_events if not e.query()]
-                    if not use_sparse or len(dense_events) < 2:
+                    if not use_sparse or (sparse != 'only' and len(dense_events) < 2):
                         slot = dense_slots[dense_chunks % len(dense_slots)]
                         dense_chunks += 1
                         enqueue(claimed, slot, None)

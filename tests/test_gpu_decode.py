@@ -424,14 +424,17 @@ def test_sparse_host_transfer_gives_the_tables_of_the_dense_copy():
     for i, p in enumerate(adversarial[:12]):
         heat[20 + i, i % 3] = p
     decoder = KeypointDecoder(cfg, (64, 64), camera=camera, max_peaks=64)
+    decoder.SPARSE_CAPACITY = 1.0                                        # 64x64 blobs mark most 4x16 tiles: pack them anyway
     host = [torch.from_numpy(a).pin_memory() for a in (heat, batch.depth, batch.centers)]
     dense = decoder.decode_host_batch(*host, chunk_frames=8, sparse=False)
     dense = {k: v.clone() for k, v in dense.items()}
     dense_bytes = decoder.host_bytes_copied
-    sparse = decoder.decode_host_batch(*host, chunk_frames=8, sparse='auto')
-    assert decoder.host_chunks_sparse >= 1 and decoder.host_bytes_copied < dense_bytes     # the rest went densely, side by side
-    for name in KeypointDecoder.HOST_RESULT_TABLES:
-        np.testing.assert_array_equal(sparse[name].numpy().view(np.uint8), dense[name].numpy().view(np.uint8), err_msg=name)
+    for mode, least in (('only', 6), ('auto', 1)):                       # every chunk packed / packed and dense side by side
+        sparse = decoder.decode_host_batch(*host, chunk_frames=8, sparse=mode)
+        assert decoder.host_chunks_sparse >= least and decoder.host_bytes_copied < dense_bytes
+        for name in KeypointDecoder.HOST_RESULT_TABLES:
+            np.testing.assert_array_equal(sparse[name].numpy().view(np.uint8), dense[name].numpy().view(np.uint8), err_msg=name)
+    decoder.SPARSE_CAPACITY = 0.5
     # all-dense input: every chunk falls back to the plain copy
     full = [torch.from_numpy(np.full_like(heat[:8], 0.4)).pin_memory(), host[1][:8], host[2][:8]]
     decoder.decode_host_batch(*full, chunk_frames=8, sparse='auto')
@@ -442,7 +445,8 @@ def test_sparse_host_transfer_gives_the_tables_of_the_dense_copy():
         dec = KeypointDecoder(cfg, size, camera=synthetic.default_camera((180, 320)) if size == (180, 320) else camera)
         inputs = [torch.from_numpy(a) for a in (b.heat, b.depth, b.centers)]
         want = {k: v.clone() for k, v in dec.decode_host_batch(*inputs, chunk_frames=4, sparse=False).items()}
-        got = dec.decode_host_batch(*inputs, chunk_frames=4, sparse='auto')
-        assert dec.host_chunks_sparse >= 1
+        dec.SPARSE_CAPACITY = 1.0
+        got = dec.decode_host_batch(*inputs, chunk_frames=4, sparse='only')
+        assert dec.host_chunks_sparse == 2
         for name in KeypointDecoder.HOST_RESULT_TABLES:
             np.testing.assert_array_equal(got[name].numpy().view(np.uint8), want[name].numpy().view(np.uint8), err_msg=name)
