@@ -317,7 +317,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': d2h, 'frames_per_step': e2e_frames, 'steps': e2e_steps,
                     'host_input_bytes_per_step': sum(t.numel() * t.element_size() for t in host),
                     'sparse_chunks': decoder.host_chunks_sparse,
-                    'note': 'pinned host tensors in, pinned host tables out, chunks of 256 frames pipelined (host pass / PCIe / '
+                    'note': 'pinned host tensors in, pinned host tables out, chunks of 128 frames pipelined (host pass / PCIe / '
                             'decode). Heatmaps: a host pass (OpenMP + AVX2, inside the timed region) marks the 4x16-pixel tiles '
                             'within reach of a value above threshold / 25 and only those cross PCIe (bit-identical tables, '
                             'csrc/okp_sparse.cuh; dense copy when more than half of a chunk is marked). Depth and centre maps '

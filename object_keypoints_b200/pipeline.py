@@ -209,7 +209,7 @@ class KeypointDecoder:
         return (self.params.nms_size == 5 and self.params.box_sum == 1 and self.params.threshold > 0.0 and
                 heat.device.type == 'cpu' and heat.dtype == torch.float32 and heat.is_contiguous())
 
-    def decode_host_batch(self, heat, depth, centers, chunk_frames=256, sparse='auto'):
+    def decode_host_batch(self, heat, depth, centers, chunk_frames=128, sparse='auto'):
         """End-to-end form for HOST inputs, the shape the reference's caller has (CPU tensors out of
         InferenceComponent, pipeline.py:24-28). The batch is cut into chunks that are pipelined: while chunk i is
         decoded, chunk i+1 crosses PCIe and chunk i+2 is prepared on the host.
