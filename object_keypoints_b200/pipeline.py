@@ -272,6 +272,7 @@ class KeypointDecoder:
         def pack(index, slot):
             """Host pass for chunk `index` into the slot's pinned staging; returns the number of marked tiles."""
             slot['copied'].synchronize()                  # the slot's previous transfer has left the pinned buffers
+            began = time.perf_counter()
             f0 = starts[index]
             n = min(f0 + chunk, N) - f0
             count = ctypes.c_longlong()
@@ -281,6 +282,7 @@ class KeypointDecoder:
                 ctypes.c_void_p(slot['offsets'].ctypes.data), ctypes.c_void_p(slot['ids_host'].data_ptr()),
                 ctypes.c_void_p(slot['packed_host'].data_ptr()), capacity, ctypes.byref(count), _host_threads())
             _lib.check(rc, 'okp_host_pack_tiles_f32')
+            self._pack_seconds = time.perf_counter() - began
             return int(count.value)
 
         def enqueue(index, slot, n_tiles):
@@ -330,6 +332,8 @@ class KeypointDecoder:
         # sparse='auto', the plain dense copy (PCIe-bound; needs no CPU) whenever the copy engine has less than two
         # dense chunks queued. Host memory bandwidth and the PCIe link are both kept busy.
         claimed = 0
+        dense_seconds = chunk * depth_frame / 50e9              # a dense chunk on a Gen5 x16 link
+        self._pack_seconds = getattr(self, '_pack_seconds', 0.0)   # the last pass's duration (previous call included)
         sparse_slots = staging[:3] if use_sparse else []
         dense_slots = staging[3:] if use_sparse else staging
         packing = None                                            # (future, chunk index, slot)
@@ -349,7 +353,10 @@ class KeypointDecoder:
                     n_tiles = future.result()
                     packed_chunks += 1
                     packing = None
-                    if claimed < len(starts):
+                    # the pass takes another chunk only if it will be done before the copy engine could have moved all
+                    # the remaining chunks densely (few host threads per rank, the last chunks of a batch)
+                    remaining = len(starts) - claimed
+                    if remaining > 0 and (sparse == 'only' or self._pack_seconds <= remaining * dense_seconds):
                         nxt = sparse_slots[packed_chunks % len(sparse_slots)]
                         packing = (self._pack_executor.submit(pack, claimed, nxt), claimed, nxt)
                         claimed += 1
