@@ -201,10 +201,16 @@ class KeypointDecoder:
         return alias.value
 
     SPARSE_CAPACITY = 0.5          # fall back to the dense copy when more than this share of a chunk's tiles is marked
+    SPARSE_MIN_THREADS = 8         # sparse='auto' needs this many host threads per rank to beat the plain copy
 
     def _sparse_ok(self, heat, sparse):
         """The sparse transfer holds for the reference's configuration only (csrc/okp_sparse.cuh)."""
         if sparse in (False, 'off', None):
+            return False
+        # the pass reads every heatmap byte from host memory: it only pays while PCIe, not host DRAM, is the limit, i.e.
+        # with enough host threads for this rank (8 threads pack at about the rate of one Gen5 x16 link; with 4 or 8
+        # ranks per node the DMA engines alone saturate host memory, measured 262 k frames/s on 8 GPUs)
+        if sparse == 'auto' and _host_threads() < self.SPARSE_MIN_THREADS:
             return False
         return (self.params.nms_size == 5 and self.params.box_sum == 1 and self.params.threshold > 0.0 and
                 heat.device.type == 'cpu' and heat.dtype == torch.float32 and heat.is_contiguous())
