@@ -425,6 +425,7 @@ def test_sparse_host_transfer_gives_the_tables_of_the_dense_copy():
         heat[20 + i, i % 3] = p
     decoder = KeypointDecoder(cfg, (64, 64), camera=camera, max_peaks=64)
     decoder.SPARSE_CAPACITY = 1.0                                        # 64x64 blobs mark most 4x16 tiles: pack them anyway
+    decoder.SPARSE_MIN_THREADS = 1                                       # whatever the box's core count
     host = [torch.from_numpy(a).pin_memory() for a in (heat, batch.depth, batch.centers)]
     dense = decoder.decode_host_batch(*host, chunk_frames=8, sparse=False)
     dense = {k: v.clone() for k, v in dense.items()}
