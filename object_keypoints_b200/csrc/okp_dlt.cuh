@@ -30,6 +30,15 @@ __device__ __forceinline__ void okp_givens_append(double (&R)[4][4], double (&a)
 // Smallest right singular vector of the 4x4 matrix R (destroyed). One-sided (Hestenes) Jacobi.
 __device__ __forceinline__ void okp_smallest_right_singular_vector(double (&R)[4][4], double (&h)[4]) {
     double Vm[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    // a column whose norm has fallen below 1e-15 of the matrix norm is rounding noise (exactly consistent observations:
+    // the smallest singular value is 0); rotating against it changes nothing representable and the relative test below
+    // would never be met, so such pairs count as converged (same statement in oracle/okp_oracle.c)
+    double negligible = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) negligible += R[r][c] * R[r][c];
+    negligible *= 1e-30;
     for (int sweep = 0; sweep < 60; ++sweep) {
         bool rotated = false;
 #pragma unroll
@@ -44,6 +53,7 @@ __device__ __forceinline__ void okp_smallest_right_singular_vector(double (&R)[4
                     gamma += R[r][p] * R[r][q];
                 }
                 if (fabs(gamma) <= 1e-300 || fabs(gamma) <= 2.3e-16 * sqrt(alpha * beta)) continue;
+                if (alpha <= negligible || beta <= negligible) continue;
                 rotated = true;
                 const double zeta = (beta - alpha) / (2.0 * gamma);
                 const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

@@ -411,6 +411,13 @@ int okp_oracle_max_threads(void) {
  * ------------------------------------------------------------------------------------- */
 static void smallest_right_singular_vector(double* A, int rows, double* h) {
     double Vm[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    /* a column whose norm has fallen below 1e-15 of the matrix norm is rounding noise (exactly consistent
+     * observations: the smallest singular value is 0); rotating against it changes nothing representable and the
+     * relative test below would never be met, so such pairs count as converged */
+    double negligible = 0;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < 4; ++c) negligible += A[r * 4 + c] * A[r * 4 + c];
+    negligible *= 1e-30;
     for (int sweep = 0; sweep < 60; ++sweep) {
         int rotated = 0;
         for (int p = 0; p < 3; ++p)
@@ -422,6 +429,7 @@ static void smallest_right_singular_vector(double* A, int rows, double* h) {
                     gamma += A[r * 4 + p] * A[r * 4 + q];
                 }
                 if (fabs(gamma) <= 1e-300 || fabs(gamma) <= 2.3e-16 * sqrt(alpha * beta)) continue;
+                if (alpha <= negligible || beta <= negligible) continue;
                 rotated = 1;
                 const double zeta = (beta - alpha) / (2.0 * gamma);
                 const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
