@@ -91,6 +91,42 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def workload_config(workload, world, exchange='gather'):
+    """The `config` object of the JSON line -- the SAME dict for both arms (ours / reference), so that the driver's
+    same_config check holds: it names the workload, not how an arm samples it (that is in `cpu_baseline.sample` / `e2e`)."""
+    w = WORKLOADS[workload]
+    H, W = w['size']
+    C = 1 + len(w['cfg'])
+    heat_bytes = w['frames'] * C * H * W * 4
+    return {'workload': workload, 'keypoint_config': w['config'], 'frames_per_gpu': w['frames'],
+            'prediction_size': [H, W], 'objects_per_frame': w['grid'][0] * w['grid'][1],
+            'l2': f"inputs {heat_bytes / 1e6:.0f} MB heatmaps per step exceed the 126 MB L2; no flush needed",
+            'parallelism': f"frames sharded over {world} GPU(s); per step one "
+                           f"{'gather to rank 0' if exchange == 'gather' else 'all_gather'} of the 3D keypoint records"}
+
+
+PARITY_INT = ('peak_count', 'peak_yx', 'peak_object', 'n_objects', 'flags', 'kp_assigned', 'kp_count', 'kp_peak', 'n_votes')
+PARITY_F32 = ('peak_score', 'peak_xy', 'peak_conf', 'kp_xy')
+
+
+def parity_mismatches(got, want):
+    """Frames of `got` (GPU tables, NumPy) that differ from the oracle's `want` under the parity rules: integer tables and
+    flags equal, float32 tables bitwise, votes equal, 3D points <= 1e-4 relative. -> (frames compared, frames differing)."""
+    import numpy as np
+    n = want['n_objects'].shape[0]
+    bad = np.zeros(n, bool)
+    for key in PARITY_INT:
+        bad |= (got[key][:n].reshape(n, -1) != want[key].reshape(n, -1)).any(axis=1)
+    for key in PARITY_F32:
+        bad |= (got[key][:n].view(np.uint32).reshape(n, -1) != want[key].view(np.uint32).reshape(n, -1)).any(axis=1)
+    for key in ('peak_vote', 'votes'):
+        bad |= (got[key][:n].reshape(n, -1) != want[key].reshape(n, -1)).any(axis=1)
+    scale = np.maximum(np.linalg.norm(want['kp_point'], axis=-1), 1e-9)
+    err = np.linalg.norm(got['kp_point'][:n] - want['kp_point'], axis=-1)
+    bad |= (err > 1e-4 * scale + 1e-12).reshape(n, -1).any(axis=1)
+    return n, int(bad.sum())
+
+
 def make_inputs(workload, device, seed):
     import torch
     from object_keypoints_b200 import synthetic
@@ -120,10 +156,10 @@ def cpu_baseline(workload, heat, depth, centers, budget_s=12.0):
     sample = int(max(probe, min(heat.shape[0], rate * budget_s)))
     h, d, c = heat[:sample].cpu().numpy(), depth[:sample].cpu().numpy(), centers[:sample].cpu().numpy()
     t0 = time.perf_counter()
-    c_oracle.decode(h, d, c, w['cfg'], camera, threads=cores)
+    want = c_oracle.decode(h, d, c, w['cfg'], camera, threads=cores)
     elapsed = time.perf_counter() - t0
     return {'value': sample / elapsed, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f"first {sample} frames of {workload} (C/OpenMP restatement oracle/okp_oracle.c, {elapsed:.2f} s)"}
+            'sample': f"first {sample} frames of {workload} (C/OpenMP restatement oracle/okp_oracle.c, {elapsed:.2f} s)"}, want
 
 
 def run_reference(args):
@@ -161,8 +197,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'keypoint_config': w['config'], 'frames_per_step': sample,
-                   'prediction_size': list(w['size'])},
+        'config': workload_config(args.workload, args.gpus, args.exchange),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f"{sample} frames of {args.workload} per step, C/OpenMP port of perception/pipeline.py"},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -171,11 +206,81 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def time_decode(decoder, inputs, tables, steps, warmup=3):
+    """ms per decode_batch over `steps` back-to-back calls (CUDA events on the launching stream, after warm-up)."""
+    import torch
+    for _ in range(warmup):
+        decoder.decode_batch(*inputs, tables=tables)
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        decoder.decode_batch(*inputs, tables=tables)
+    stop.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(stop) / steps
+
+
+def secondary_64x64(device, peaks, steps):
+    """The network's real output resolution (KeypointNet emits 64x64): 32768 valve frames of 64x64 (1.61 GB of
+    float32 heatmaps, far above the 126 MB L2), float32 and bfloat16, whole step = the fused decode kernel + its two no-op
+    fix-up launches, lean tables (only valid slots are written: at this size clearing the tables would be a quarter of the
+    DRAM traffic). Parity of this workload: tests/test_gpu_decode.py::test_headline_bench_workload_is_bitwise_the_oracle."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    w = WORKLOADS['config4_64x64']
+    frames = 32768
+    heat, depth, centers, n_obj = synthetic.torch_grid_batch(frames, w['cfg'], w['size'], seed=1004, grid=w['grid'], device=device)
+    camera = synthetic.default_camera(w['size'])
+    out = []
+    for dtype, esize, lean in (('f32', 4, True), ('f32', 4, False), ('bf16', 2, True)):
+        decoder = KeypointDecoder(w['cfg'], w['size'], camera=camera, device=device, lean_tables=lean)
+        inputs = (heat, depth, centers) if dtype == 'f32' else tuple(t.to(torch.bfloat16) for t in (heat, depth, centers))
+        tables = decoder.tables(frames)
+        ms = time_decode(decoder, inputs, tables, steps)
+        found = float((tables['n_objects'] == n_obj).float().mean())
+        assert found > 0.99, f"64x64 {dtype}: only {found:.3f} of the frames decoded to {n_obj} objects"
+        nbytes = frames * 3 * 64 * 64 * esize
+        out.append({'workload': 'config4_64x64', 'dtype': dtype, 'frames': frames, 'lean_tables': lean, 'ms': ms, 'kernel_ms': ms,
+                    'frames_per_s': frames / (ms / 1e3), 'algorithmic_bytes': nbytes,
+                    'achieved_gbs': nbytes / (ms / 1e3) / 1e9, 'frac': nbytes / (ms / 1e3) / 1e9 / peaks['hbm_gbs']})
+        del decoder, tables, inputs
+    del heat, depth, centers
+    torch.cuda.empty_cache()
+    return out
+
+
+def host_read_ceiling(device, nbytes=1 << 30):
+    """Measured ceilings of the e2e path on this box: (a) the DMA engine reading pinned host memory into HBM, (b) every
+    host core of this rank reading the same pinned buffer (the host pass's access pattern). GB/s."""
+    import numpy as np
+    import torch
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    host.fill_(1)
+    dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    for _ in range(2):
+        dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(3):
+        dev.copy_(host, non_blocking=True)
+    stop.record()
+    torch.cuda.synchronize()
+    h2d = 3 * nbytes / (start.elapsed_time(stop) / 1e3) / 1e9
+    view = host.numpy().view(np.float32)
+    threads = torch.get_num_threads()
+    t0 = time.perf_counter()
+    total = float(torch.from_numpy(view).sum())            # a streaming read by torch's intra-op threads
+    read = nbytes / (time.perf_counter() - t0) / 1e9
+    del host, dev
+    return {'h2d_pinned_gbs': h2d, 'host_read_gbs': read, 'host_read_threads': threads, 'checksum': total != 0.0}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from object_keypoints_b200 import KeypointDecoder, synthetic
-    from object_keypoints_b200.pipeline import DecodeTables
+    from object_keypoints_b200 import KeypointDecoder, synthetic, sharding
     from object_keypoints_b200.sharding import RecordExchange
 
     rank = int(os.environ.get('RANK', '0'))
@@ -187,36 +292,23 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
     w = WORKLOADS[args.workload]
-    frames = args.frames or w['frames']
-    w = dict(w, frames=frames)
-    WORKLOADS[args.workload] = w
+    frames = w['frames']
     H, W = w['size']
     C = 1 + len(w['cfg'])
     camera = synthetic.default_camera(w['size'])
     heat, depth, centers = make_inputs(args.workload, device, seed=rank)
     decoder = KeypointDecoder(w['cfg'], w['size'], camera=camera, device=device)
-    # two table sets: the gather of step k (own stream) overlaps the decode of step k + 1
-    table_sets = [decoder.tables(frames), DecodeTables(frames, decoder.C, decoder.cfg, decoder.params, device)]
-    tables = table_sets[0]
+    tables = decoder.tables(frames)
     root = 0 if args.exchange == 'gather' else None
-    exchange = RecordExchange(tables, world=world, rank=rank, transport=args.transport, root=root) if world > 1 else None
+    exchange = RecordExchange(decoder, frames, world=world, rank=rank, transport=args.transport, root=root) if world > 1 else None
     gathered = None
-    table_free = [None, None]
-    steps_done = [0]
 
     def step():
-        index = steps_done[0] % 2
-        steps_done[0] += 1
-        current = table_sets[index]
-        if table_free[index] is not None:
-            torch.cuda.current_stream().wait_event(table_free[index])     # its previous gather has read it
-        decoder.extract_peaks(heat, current)
-        decoder.group_objects(depth, centers, current)
-        if world > 1:
-            result, done = exchange.exchange(current)
-            table_free[index] = done
-            return result
-        return None
+        """One pass of the hot path: ONE call = the fused streaming kernel (peaks, grouping, 3D lift and, for N > 1, the
+        frame's record stored straight into the gathering rank's buffer over NVLink) + its two no-op fix-up launches."""
+        sink = exchange.begin() if world > 1 else None
+        decoder.decode_batch(heat, depth, centers, tables=tables, records=sink)
+        return exchange.end()[0] if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -227,7 +319,7 @@ def run_ours(args):
         gathered = step()
     barrier()
 
-    # ---- timed region: exactly K steps, device time, K1 bracketed by its own events ----
+    # ---- timed region: exactly K steps, device time, the decode bracketed by its own events ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -237,54 +329,79 @@ def run_ours(args):
     barrier()
     start.record()
     for i in range(args.steps):
-        index = steps_done[0] % 2
-        steps_done[0] += 1
-        current = table_sets[index]
-        if table_free[index] is not None:
-            torch.cuda.current_stream().wait_event(table_free[index])
+        sink = exchange.begin() if world > 1 else None
         k1_events[i][0].record()
-        decoder.extract_peaks(heat, current)
+        decoder.decode_batch(heat, depth, centers, tables=tables, records=sink)
         k1_events[i][1].record()
-        decoder.group_objects(depth, centers, current)
         if world > 1:
-            gathered, table_free[index] = exchange.exchange(current)
+            gathered, _ = exchange.end()
     if world > 1:
-        exchange.finish()                               # every gather of the K steps is inside the timed region
+        exchange.finish()                               # every completion of the K steps is inside the timed region
     stop.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = start.elapsed_time(stop)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / args.steps
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
-    e2e_frames = min(frames, args.e2e_frames)
-    host = [t[:e2e_frames].cpu().pin_memory() for t in (heat, depth, centers)]
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    result_host = None
-    for _ in range(2):
-        result_host = decoder.decode_host_batch(*host)
-    barrier()
-    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(e2e_steps):
-        result_host = decoder.decode_host_batch(*host)
-    t_stop.record()
-    barrier()
-    e2e_ms = t_start.elapsed_time(t_stop) / e2e_steps
-    d2h = sum(v.numel() * v.element_size() for v in result_host.values())
-    h2d = decoder.host_bytes_copied                     # bytes the copy engine moved; depth / centre maps are gathered in place
+    # ---- parity, outside the timed region ----
+    # N > 1: the gathered rows of EVERY rank against a re-pack of that rank's own tables (plain torch + NCCL all_gather)
+    gathered_check = None
+    if world > 1:
+        mine = sharding.unpack_compact_records(sharding.pack_compact_records(tables, w['cfg']), decoder.params.max_objects, w['cfg'])
+        want = {}
+        for key, value in mine.items():
+            parts = [torch.empty_like(value) for _ in range(world)]
+            dist.all_gather(parts, value.contiguous())
+            want[key] = torch.cat(parts)
+        if rank == 0 or args.exchange == 'allgather':
+            back = sharding.unpack_compact_records(gathered, decoder.params.max_objects, w['cfg'])
+            bad = torch.zeros(world * frames, dtype=torch.bool, device=device)
+            for key in want:
+                bad |= (back[key] != want[key]).reshape(world * frames, -1).any(dim=1)
+            gathered_check = {'rows': world * frames, 'mismatches': int(bad.sum()),
+                              'objects': int(back['n_objects'].sum())}
+            assert gathered_check['mismatches'] == 0, f"gathered records differ from the ranks' tables: {gathered_check}"
+            assert gathered_check['objects'] > 0.99 * world * frames * w['grid'][0] * w['grid'][1]
+    # every rank: a sample of its own frames against the C oracle
+    parity = None
+    if not args.no_cpu_baseline:
+        from oracle import c_oracle
+        sample = frames if world == 1 else min(frames, 128)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else 1
+        if world == 1:
+            baseline, want_tables = cpu_baseline(args.workload, heat, depth, centers)
+        else:
+            baseline = None
+            want_tables = c_oracle.decode(heat[:sample].cpu().numpy(), depth[:sample].cpu().numpy(), centers[:sample].cpu().numpy(),
+                                          w['cfg'], camera, threads=max(1, cores // world))
+        compared, differing = parity_mismatches(tables.numpy(), want_tables)
+        counts = torch.tensor([compared, differing], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(counts)
+        parity = {'frames': int(counts[0]), 'mismatches': int(counts[1]), 'against': 'oracle/okp_oracle.c on the same frames',
+                  'rules': 'integer + float32 tables bitwise, 3D points <= 1e-4 relative'}
+        if gathered_check is not None:
+            parity['gathered'] = gathered_check
+        assert parity['mismatches'] == 0, f"{parity['mismatches']} of {parity['frames']} frames differ from the oracle"
 
-    times = torch.tensor([elapsed_ms, k1_ms, e2e_ms], dtype=torch.float64, device=device)
+    # ---- strong scaling (N > 1): BASELINE config 4 as worded -- 4096 frames TOTAL sharded over the N GPUs, one CUDA graph
+    # replay = `depth` steps (decode + record stores + completion barrier on a forked stream), so that a 512-frame step is not
+    # bound by launch overhead. Rank 0 then decodes all 4096 frames alone for the single-GPU reference of the same run. ----
+    strong = None
+    if world > 1 and frames % world == 0:
+        strong = strong_scaling(args, decoder, exchange.transport, heat, depth, centers, frames, world, rank, device, root, barrier)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = end_to_end(args, decoder, heat, depth, centers, frames, world, rank, device, barrier)
+
+    times = torch.tensor([elapsed_ms, k1_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, k1_ms, e2e_ms = [float(v) for v in times.cpu()]
+    elapsed_ms, k1_ms = [float(v) for v in times.cpu()]
 
     # sanity: the decode found the objects that were drawn (guards against timing an empty kernel)
     found = float((tables['n_objects'] > 0).float().mean())
     assert found > 0.99, f"only {found:.3f} of the frames produced objects"
-    if world > 1 and (rank == 0 or args.exchange == 'allgather'):   # the gathered records hold every rank's frames
-        objects = gathered[:, 0].reshape(world, frames)
-        assert bool((objects > 0).float().mean(dim=1).gt(0.99).all()), "gathered records are incomplete"
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -293,43 +410,158 @@ def run_ours(args):
         algorithmic_bytes = frames * C * H * W * 4                 # every heatmap byte exactly once
         achieved = algorithmic_bytes / (k1_ms / 1e3) / 1e9
         traffic = None
-        ncu_summary = os.path.join(ROOT, 'profiles', 'r01_k1_traffic.json')
-        if os.path.exists(ncu_summary):
-            with open(ncu_summary) as f:
-                traffic = json.load(f).get(args.workload)
+        for name in ('r02_k1_traffic.json', 'r01_k1_traffic.json'):
+            ncu_summary = os.path.join(ROOT, 'profiles', name)
+            if os.path.exists(ncu_summary):
+                with open(ncu_summary) as f:
+                    traffic = json.load(f).get(args.workload)
+                break
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'keypoint_config': w['config'], 'frames_per_gpu': frames,
-                       'prediction_size': [H, W], 'objects_per_frame': w['grid'][0] * w['grid'][1],
-                       'l2': f"inputs {algorithmic_bytes / 1e6:.0f} MB heatmaps per step exceed the 126 MB L2; no flush needed",
-                       'parallelism': f"frames sharded over {world} GPU(s); per step one {'gather to rank 0' if args.exchange == 'gather' else 'all_gather'} of the 3D keypoint records"
-                                      + (f" ({exchange.transport}: "
-                                         + ('pack kernel stores straight into every peer over NVLink' if exchange.transport == 'peer'
-                                            else 'pack kernel + NCCL all_gather') + ", overlapped with the next step's decode)"
-                                         if world > 1 else "")},
+            'config': workload_config(args.workload, world, args.exchange),
+            'exchange': (f"{exchange.transport}: " + ('the decode kernel stores every frame\'s compact record straight into the '
+                                                     'gathering rank over NVLink (no pack kernel); completion = a device-side barrier'
+                                                     if exchange.transport == 'peer' else 'compact records + NCCL')
+                         + ", overlapped with the next step's decode") if world > 1 else None,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                          'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peak_kind,
-                         'kernel': 'K1 peaks (box sum + NMS + centroid) + merge', 'kernel_ms': k1_ms,
-                         'algorithmic_bytes': algorithmic_bytes},
-            'e2e': {'value': world * e2e_frames / (e2e_ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h, 'frames_per_step': e2e_frames, 'steps': e2e_steps,
-                    'host_input_bytes_per_step': sum(t.numel() * t.element_size() for t in host),
-                    'sparse_chunks': decoder.host_chunks_sparse,
-                    'note': 'pinned host tensors in, pinned host tables out, chunks of 128 frames pipelined (host pass / PCIe / '
-                            'decode). Heatmaps: a host pass (OpenMP + AVX2, inside the timed region) marks the 4x16-pixel tiles '
-                            'within reach of a value above threshold / 25 and only those cross PCIe (bit-identical tables, '
-                            'csrc/okp_sparse.cuh; dense copy when more than half of a chunk is marked). Depth and centre maps '
-                            '(gather-only) are read in place from pinned host memory over PCIe'},
-            'gpu_launches': args.steps * (3 + (1 if world > 1 else 0)),
+                         'kernel': 'okp_peaks_stream_kernel<float, FUSED>: box sum + NMS + centroid + grouping + 3D lift (+ records) in '
+                                   'one streaming pass; kernel_ms brackets the call, i.e. includes its two no-op fix-up launches',
+                         'kernel_ms': k1_ms, 'algorithmic_bytes': algorithmic_bytes},
+            'e2e': e2e,
+            'gpu_launches': args.steps * 3,
             'clocks': clocks,
         }
+        if parity is not None:
+            line['parity'] = parity
+        if strong is not None:
+            line['strong'] = strong
         if not args.no_cpu_baseline and world == 1:
-            line['cpu_baseline'] = cpu_baseline(args.workload, heat, depth, centers)
+            line['cpu_baseline'] = baseline
+        if world == 1 and not args.no_secondary:
+            line['secondary'] = secondary_64x64(device, peaks, max(5, min(args.steps, 20)))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling(args, decoder, transport, heat, depth, centers, frames, world, rank, device, root, barrier):
+    import torch
+    import torch.distributed as dist
+    from object_keypoints_b200.sharding import RecordExchange
+    share = frames // world
+    inputs = (heat[:share], depth[:share], centers[:share])
+    tables = decoder.tables(share)
+    exchange = RecordExchange(decoder, share, world=world, rank=rank, transport=transport, root=root)
+    steps_per_graph = exchange.depth
+
+    def eager_steps(count):
+        for _ in range(count):
+            sink = exchange.begin()
+            decoder.decode_batch(*inputs, tables=tables, records=sink)
+            exchange.end()
+
+    eager_steps(exchange.depth)                                # warm-up (allocations, module loads) before the capture
+    exchange.finish()
+    barrier()
+    graph, how = None, 'eager launches'
+    try:
+        exchange.calls = 0
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                eager_steps(steps_per_graph)                   # LAG < depth: every event waited on is recorded inside the capture
+                exchange.finish()
+        torch.cuda.current_stream().wait_stream(side)
+        how = f"one CUDA graph replay = {steps_per_graph} steps"
+    except Exception as error:                                 # e.g. a collective that cannot be captured on this build
+        graph, how = None, f"eager launches (graph capture failed: {type(error).__name__})"
+        torch.cuda.synchronize()
+        exchange.calls = 0
+    replays = max(1, (args.steps * 4 + steps_per_graph - 1) // steps_per_graph)
+
+    def run(count):
+        for _ in range(count):
+            if graph is not None:
+                graph.replay()
+            else:
+                eager_steps(steps_per_graph)
+                exchange.finish()
+
+    run(2)
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    run(replays)
+    stop.record()
+    barrier()
+    ms = torch.tensor([start.elapsed_time(stop) / (replays * steps_per_graph)], dtype=torch.float64, device=device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    single_ms = None
+    if rank == 0:                                              # the single-GPU time of the same 4096 frames, same run, same GPU
+        single_ms = time_decode(decoder, (heat, depth, centers), decoder.tables(frames), max(5, args.steps))
+    barrier()
+    if rank != 0:
+        return None
+    return {'frames_total': frames, 'frames_per_gpu': share, 'ms_per_step': ms, 'frames_per_s': frames / (ms / 1e3),
+            'single_gpu_ms_per_step': single_ms, 'efficiency_vs_n1': (single_ms / ms) / world,
+            'launch': how, 'steps_timed': replays * steps_per_graph}
+
+
+def end_to_end(args, decoder, heat, depth, centers, frames, world, rank, device, barrier):
+    import torch
+    import torch.distributed as dist
+    e2e_frames = min(frames, args.e2e_frames)
+    host = [t[:e2e_frames].cpu().pin_memory() for t in (heat, depth, centers)]
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def timed(**options):
+        out = None
+        for _ in range(2):
+            out = decoder.decode_host_batch(*host, out=out, **options)
+        barrier()
+        t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for _ in range(e2e_steps):
+            out = decoder.decode_host_batch(*host, out=out, **options)
+        t_stop.record()
+        barrier()
+        ms = torch.tensor([t_start.elapsed_time(t_stop) / e2e_steps], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), out, decoder.host_bytes_copied, decoder.host_chunks_sparse, getattr(decoder, 'host_marked_fraction', None)
+
+    e2e_ms, result_host, h2d, sparse_chunks, marked = timed()
+    dense_ms, _, dense_h2d, _, _ = timed(sparse=False)
+    d2h = sum(v.numel() * v.element_size() for v in result_host.values())
+    out = {'value': world * e2e_frames / (e2e_ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+           'd2h_bytes_per_step': d2h, 'frames_per_step': e2e_frames, 'steps': e2e_steps,
+           'host_input_bytes_per_step': sum(t.numel() * t.element_size() for t in host),
+           'sparse_chunks': sparse_chunks, 'marked_tile_fraction': marked,
+           'e2e_dense': {'value': world * e2e_frames / (dense_ms / 1e3), 'h2d_bytes_per_step': dense_h2d,
+                         'note': 'sparse=False: every heatmap byte crosses PCIe (what a caller gets on dense maps)'},
+           'host_threads_per_rank': getattr(decoder, 'host_pack_threads', None),
+           'note': 'pinned host tensors in, pinned host tables out, chunks of 128 frames pipelined (host pass / PCIe / '
+                   'decode). Heatmaps: a host pass (OpenMP, inside the timed region) marks the 4x16-pixel tiles '
+                   'within reach of a value above threshold / 25 and only those cross PCIe (bit-identical tables, '
+                   'csrc/okp_sparse.cuh; dense copy when more than half of a chunk is marked). Depth and centre maps '
+                   '(gather-only) are read in place from pinned host memory over PCIe'}
+    if rank == 0 and not args.no_cpu_baseline:
+        pageable = [t.clone() for t in (h.cpu() for h in (heat[:e2e_frames], depth[:e2e_frames], centers[:e2e_frames]))]
+        decoder.decode_host_batch(*pageable)
+        t0 = time.perf_counter()
+        decoder.decode_host_batch(*pageable)
+        out['pageable_inputs'] = {'value': e2e_frames / (time.perf_counter() - t0),
+                                  'note': 'one rank, pageable CPU tensors (what InferenceComponent.cpu() hands over in the reference): '
+                                          'every map is copied, nothing is gathered in place'}
+        out['ceilings'] = host_read_ceiling(device)
+    barrier()
+    return out
 
 
 def main():
@@ -343,11 +575,14 @@ def main():
     ap.add_argument('--e2e-frames', type=int, default=2048)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help="skip the 64x64 lines (N = 1)")
     ap.add_argument('--exchange', default='gather', choices=['gather', 'allgather'],
                     help="N > 1: gather the records to rank 0 (north_star) or to every rank")
     ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
                     help="N > 1: how the keypoint records are gathered (sharding.RecordExchange)")
     args = ap.parse_args()
+    if args.frames:
+        WORKLOADS[args.workload] = dict(WORKLOADS[args.workload], frames=args.frames)
     if args.impl == 'reference':
         run_reference(args)
     else:

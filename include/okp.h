@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define OKP_VERSION_MAJOR 0
-#define OKP_VERSION_MINOR 1
+#define OKP_VERSION_MINOR 2
 
 enum {
     OKP_OK = 0,
@@ -49,6 +49,9 @@ enum {
 #define OKP_FLAG_VOTE_OVERFLOW 16u    /* more votes for one object than max_votes */
 #define OKP_FLAG_NO_CENTERS 32u       /* empty centre map: frame has no objects (pipeline.py:105-106) */
 #define OKP_FLAG_ARGMAX_RESOLVED 64u  /* > cfg[t] detections, cfg[t] == 1: most confident kept (pipeline.py:139-142) */
+#define OKP_FLAG_GENERIC_PATH 128u    /* not a property of the data: this call's shape / mode is outside the tuned TMA kernel
+                                         (W % 4 != 0, W > 500, bfloat16 with W % 8 != 0, nms_size 3, box_sum 0) and ran
+                                         on the exact generic tile kernels, about 3x slower per pixel -- same results */
 
 #define OKP_MAX_MAPS 16               /* C = 1 + number of keypoint types */
 #define OKP_MAX_PEAKS 256             /* upper bound for OkpDecodeParams.max_peaks */
@@ -80,11 +83,17 @@ typedef struct OkpDecodeParams {
                                  score-descending (ties: raster order) -- CornerNet's _topk (py_utils/utils.py:27-38)
                                  per keypoint type; exact when the map has <= max_peaks peaks above the threshold,
                                  otherwise OKP_FLAG_PEAK_OVERFLOW is raised as usual */
+    int32_t lean_tables;      /* 0 (default): unused slots of every table are reset (zero / -1) as documented below.
+                                 1: only valid slots are written -- peak rows k < min(peak_count, K); kp_assigned / kp_count
+                                 rows o < n_objects; kp_peak / kp_xy / kp_point slots s < kp_count; votes v < n_votes --
+                                 everything else keeps whatever the buffer held. For callers that read by the counts (the
+                                 tables of a 64x64 frame are a quarter of its heatmap bytes: clearing them is the decode's
+                                 largest DRAM write). */
 } OkpDecodeParams;
 
 /* Fixed-capacity structure-of-arrays output. N frames, C maps, K = max_peaks, O = max_objects,
  * S = max(1, max(keypoint_config)), V = max_votes. Map 0 is the object-centre map. All arrays are
- * dense row-major with the shapes given; unused slots are zero / -1. */
+ * dense row-major with the shapes given; unused slots are zero / -1 (unless OkpDecodeParams.lean_tables). */
 typedef struct OkpDecodeTables {
     /* peaks of every map, raster (row-major y, x) order -- pipeline.py:69-79 */
     int32_t* peak_count;    /* [N,C]      true number of peaks (may exceed K) */
@@ -141,8 +150,12 @@ int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int 
  * *dev_ptr_out; OKP_E_UNSUPPORTED if the buffer is pageable or not mapped into the current device. */
 int okp_host_alias(const void* host_ptr, void** dev_ptr_out);
 
-/* Replaces ObjectKeypointPipeline.__call__ (pipeline.py:182-200) for a batch of N frames:
- * okp_extract_peaks_f32 followed by okp_group_objects_f32 on the same stream. */
+/* Replaces ObjectKeypointPipeline.__call__ (pipeline.py:182-200) for a batch of N frames. For the reference's
+ * configuration (nms_size 5, box_sum 1, top_k 0) on shapes the TMA kernel covers this is ONE streaming pass: the
+ * grouping and the 3D lift of a frame run in the epilogue warps of the peak kernel, from the frame's peak list in
+ * shared memory, while the next frames stream (plus two fix-up launches that are no-ops unless a map overflowed
+ * max_peaks). Otherwise: okp_extract_peaks_f32 followed by okp_group_objects_f32 on the same stream. Same tables
+ * either way. heat_dev must be 16-byte aligned (OKP_E_UNSUPPORTED otherwise). */
 int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev,
                    int N, int C, int H, int W, const int32_t* keypoint_config,
                    const OkpCamera* camera, const OkpDecodeParams* params,
@@ -166,6 +179,34 @@ int okp_decode_bf16(const void* heat_dev, const void* depth_dev, const void* cen
                     const OkpCamera* camera, const OkpDecodeParams* params,
                     const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
                     void* stream);
+
+/* okp_decode_* that also EMITS one compact record per frame -- what ObjectKeypointPipeline.__call__ returns per
+ * frame (pipeline.py:195-199): object count, kept-keypoint counts, camera-frame 3D points -- into every sink buffer
+ * while it decodes. This is the multi-GPU exchange of SURVEY section 8e (the reference is single-GPU, batch 1:
+ * pipeline.py:183): frames shard independently, the only cross-GPU step is the gather of these records. With the
+ * peer-mapped (symmetric-memory) buffer of the gathering rank as sink the stores travel over NVLink / NVSwitch from
+ * inside the decode kernel -- there is no exchange kernel; the caller provides the cross-rank barrier before the
+ * buffer is read. Record layout (little endian, `record_bytes` apart, row first_row + n for frame n):
+ *     int32 n_objects; uint32 flags; int32 kp_count[O][C]; (pad to 8); double point[O][P][3]
+ * with O = max_objects, P = 1 + sum(keypoint_config): object o's points in (map, slot) order. Only rows o < n_objects
+ * and slots s < kp_count[o][c] are written. okp_record_bytes() is the minimum record_bytes. */
+typedef struct OkpRecordSink {
+    void* const* buffers_dev;   /* HOST array of n_buffers <= 16 DEVICE pointers to [rows, record_bytes] byte buffers */
+    int32_t n_buffers;          /* 0: no records (the call is okp_decode_*) */
+    int32_t record_bytes;
+    long long first_row;
+} OkpRecordSink;
+int okp_record_bytes(int O, int C, const int32_t* keypoint_config);
+int okp_decode_emit_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev,
+                        int N, int C, int H, int W, const int32_t* keypoint_config,
+                        const OkpCamera* camera, const OkpDecodeParams* params,
+                        const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
+                        const OkpRecordSink* sink, void* stream);
+int okp_decode_emit_bf16(const void* heat_dev, const void* depth_dev, const void* centers_dev,
+                         int N, int C, int H, int W, const int32_t* keypoint_config,
+                         const OkpCamera* camera, const OkpDecodeParams* params,
+                         const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
+                         const OkpRecordSink* sink, void* stream);
 
 /* Replaces FisheyeCamera.undistort (camera_utils.py:75-81, cv2.fisheye.undistortPoints with
  * P = K). xy_dev/out_dev: [n,2] float64. round_to_f32 != 0 reproduces OpenCV's float32 output

@@ -20,6 +20,7 @@ FLAG_CLUSTERED = 8
 FLAG_VOTE_OVERFLOW = 16
 FLAG_NO_CENTERS = 32
 FLAG_ARGMAX_RESOLVED = 64
+FLAG_GENERIC_PATH = 128      # property of the call, not of the data: the shape / mode ran on the exact generic kernels
 
 ERRORS = {0: 'OKP_OK', -1: 'OKP_E_NULL', -2: 'OKP_E_SHAPE', -3: 'OKP_E_CAPACITY',
           -4: 'OKP_E_UNSUPPORTED', -5: 'OKP_E_CUDA', -6: 'OKP_E_WORKSPACE'}
@@ -35,7 +36,12 @@ class OkpDecodeParams(ctypes.Structure):
     _fields_ = [('threshold', ctypes.c_float), ('nms_size', ctypes.c_int32), ('box_sum', ctypes.c_int32),
                 ('compat_clip_bug', ctypes.c_int32), ('outlier_distance', ctypes.c_double),
                 ('max_peaks', ctypes.c_int32), ('max_objects', ctypes.c_int32), ('max_votes', ctypes.c_int32),
-                ('kmeans_iterations', ctypes.c_int32), ('top_k', ctypes.c_int32)]
+                ('kmeans_iterations', ctypes.c_int32), ('top_k', ctypes.c_int32), ('lean_tables', ctypes.c_int32)]
+
+
+class OkpRecordSink(ctypes.Structure):
+    _fields_ = [('buffers_dev', ctypes.POINTER(ctypes.c_void_p)), ('n_buffers', ctypes.c_int32),
+                ('record_bytes', ctypes.c_int32), ('first_row', ctypes.c_longlong)]
 
 
 # name, numpy dtype, shape as a function of the dimension dict -- order = field order in okp.h
@@ -74,7 +80,7 @@ def table_shapes(N, C, keypoint_config, params):
 
 
 def make_params(threshold=0.5, outlier_distance=20.0, max_peaks=32, max_objects=16, max_votes=16,
-                compat_clip_bug=True, kmeans_iterations=16, nms_size=5, box_sum=True, top_k=0):
+                compat_clip_bug=True, kmeans_iterations=16, nms_size=5, box_sum=True, top_k=0, lean_tables=False):
     if not (1 <= max_peaks <= OKP_MAX_PEAKS):
         raise ValueError(f"max_peaks must be in [1, {OKP_MAX_PEAKS}]")
     if not (1 <= max_objects <= OKP_MAX_OBJECTS):
@@ -86,7 +92,7 @@ def make_params(threshold=0.5, outlier_distance=20.0, max_peaks=32, max_objects=
     return OkpDecodeParams(threshold=threshold, nms_size=int(nms_size), box_sum=int(bool(box_sum)), top_k=int(top_k),
                            compat_clip_bug=int(bool(compat_clip_bug)),
                            outlier_distance=outlier_distance, max_peaks=max_peaks, max_objects=max_objects,
-                           max_votes=max_votes, kmeans_iterations=kmeans_iterations)
+                           max_votes=max_votes, kmeans_iterations=kmeans_iterations, lean_tables=int(bool(lean_tables)))
 
 
 def pack_camera(camera):
@@ -119,3 +125,26 @@ def check_keypoint_config(keypoint_config):
     if any(v < 1 or v > OKP_MAX_SLOTS for v in cfg):
         raise ValueError(f"keypoint_config entries must be in [1, {OKP_MAX_SLOTS}]")
     return cfg
+
+
+def mask_unspecified(tables):
+    """Copies of NumPy decode tables with every slot that ``lean_tables`` leaves unspecified (include/okp.h) reset to the
+    value the default mode writes there (zero / -1), so that lean tables compare one to one with cleared ones."""
+    t = {k: np.array(v, copy=True) for k, v in tables.items()}
+    N, C, K = t['peak_yx'].shape[:3]
+    O, S, V = t['kp_peak'].shape[1], t['kp_peak'].shape[3], t['votes'].shape[2]
+    valid_peak = np.arange(K)[None, None, :] < np.minimum(t['peak_count'], K)[:, :, None]
+    for name, fill in (('peak_yx', -1), ('peak_score', 0), ('peak_xy', 0), ('peak_conf', 0), ('peak_object', -1), ('peak_vote', 0)):
+        mask = valid_peak if t[name].ndim == 3 else valid_peak[..., None]
+        t[name] = np.where(mask, t[name], np.asarray(fill, t[name].dtype))
+    valid_obj = np.arange(O)[None, :] < t['n_objects'][:, None]
+    t['kp_assigned'] = np.where(valid_obj[:, :, None], t['kp_assigned'], 0)
+    t['kp_count'] = np.where(valid_obj[:, :, None], t['kp_count'], 0)
+    valid_slot = np.arange(S)[None, None, None, :] < t['kp_count'][..., None]
+    t['kp_peak'] = np.where(valid_slot, t['kp_peak'], -1)
+    t['kp_xy'] = np.where(valid_slot[..., None], t['kp_xy'], np.float32(0))
+    t['kp_point'] = np.where(valid_slot[..., None], t['kp_point'], 0.0)
+    t['n_votes'] = np.where(valid_obj, t['n_votes'], 0)
+    valid_vote = np.arange(V)[None, None, :] < t['n_votes'][..., None]
+    t['votes'] = np.where(valid_vote[..., None], t['votes'], 0.0)
+    return t

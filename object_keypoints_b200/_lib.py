@@ -20,6 +20,7 @@ EXPORTS = [
     'okp_extract_peaks_bf16', 'okp_group_objects_bf16', 'okp_decode_bf16',
     'okp_eval_match_f64', 'okp_eval_summary_f64', 'okp_record_doubles', 'okp_pack_records_f64',
     'okp_rasterise_targets_f32', 'okp_host_pack_scratch_bytes', 'okp_host_pack_tiles_f32', 'okp_scatter_tiles_f32',
+    'okp_record_bytes', 'okp_decode_emit_f32', 'okp_decode_emit_bf16',
 ]
 
 
@@ -29,35 +30,57 @@ class OkpError(RuntimeError):
         super().__init__(f"{where}: {_abi.ERRORS.get(code, code)} ({strerror(code)})")
 
 
-def build(verbose=False):
-    """Compile csrc/okp_api.cu for sm_100a into libokp.so (nvcc cross-compiles without a GPU)."""
+def build(verbose=False, tuning=False):
+    """Compile csrc/okp_api.cu for sm_100a into libokp.so (nvcc cross-compiles without a GPU).
+    tuning=True adds -DOKP_TUNING_KNOBS: the OKP_* environment variables of tools/sweep_k1.py override the launch-plan
+    constants (the shipped library reads no environment)."""
     import subprocess
     src = os.path.join(_HERE, 'csrc', 'okp_api.cu')
-    # the host side of the sparse transfer is plain C++ (OpenMP + AVX2): g++ compiles it, nvcc links it in
+    # the host side of the sparse transfer is plain C++ (OpenMP; its AVX2 loop is a run-time-dispatched target function,
+    # so no -mavx2 here and the file also builds on aarch64 hosts): g++ compiles it, nvcc links it in
     host_src = os.path.join(_HERE, 'csrc', 'okp_host_pack.cpp')
     host_obj = os.path.join(_HERE, 'csrc', 'okp_host_pack.o')
-    host = subprocess.run(['g++', '-O3', '-mavx2', '-fopenmp', '-fPIC', '-std=c++17', '-c', host_src, '-o', host_obj],
+    host = subprocess.run(['g++', '-O3', '-fopenmp', '-fPIC', '-std=c++17', '-c', host_src, '-o', host_obj],
                           capture_output=True, text=True)
     if host.returncode != 0:
         raise RuntimeError("g++ failed:\n" + host.stdout + host.stderr)
     cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
            '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static', '-o', LIBRARY_PATH, src, host_obj, '-lgomp']
+    if tuning:
+        cmd.insert(1, '-DOKP_TUNING_KNOBS')
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')
     result = subprocess.run(cmd, capture_output=True, text=True)
     if result.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + result.stdout + result.stderr)
+    with open(STAMP_PATH, 'w') as handle:
+        handle.write(_source_digest() + ('\ntuning' if tuning else '') + '\n')
     return result.stdout + result.stderr
 
 
+STAMP_PATH = LIBRARY_PATH + '.stamp'
+
+
+def _source_digest():
+    """sha256 over the contents of everything libokp.so is built from (robust against mtime changes when the tree is
+    copied to another box)."""
+    import hashlib
+    digest = hashlib.sha256()
+    csrc = os.path.join(_HERE, 'csrc')
+    names = sorted(f for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh', '.cpp', '.h')))
+    for path in [os.path.join(csrc, f) for f in names] + [os.path.join(os.path.dirname(_HERE), 'include', 'okp.h')]:
+        with open(path, 'rb') as handle:
+            digest.update(handle.read())
+    return digest.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIBRARY_PATH):
+    """True when libokp.so is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIBRARY_PATH) or not os.path.exists(STAMP_PATH):
         return True
-    built = os.path.getmtime(LIBRARY_PATH)
-    sources = [os.path.join(_HERE, 'csrc', f) for f in os.listdir(os.path.join(_HERE, 'csrc'))]
-    sources.append(os.path.join(os.path.dirname(_HERE), 'include', 'okp.h'))
-    return any(os.path.getmtime(s) > built for s in sources)
+    with open(STAMP_PATH) as handle:
+        return handle.read().split('\n')[0].strip() != _source_digest()
 
 
 def lib():
@@ -67,6 +90,10 @@ def lib():
     if not os.path.exists(LIBRARY_PATH):
         raise ImportError(f"{LIBRARY_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU fallback for the decode path)")
+    if needs_build():
+        import warnings
+        warnings.warn(f"{LIBRARY_PATH} is older than its sources (csrc/, include/okp.h): rebuild it with "
+                      "`python -c 'import __graft_entry__ as g; g.build()'`", RuntimeWarning, stacklevel=2)
     L = ctypes.CDLL(LIBRARY_PATH)
     vp, i32, sz, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_double
     P = ctypes.POINTER
@@ -91,6 +118,12 @@ def lib():
         extract.argtypes = L.okp_extract_peaks_f32.argtypes
         group.argtypes = L.okp_group_objects_f32.argtypes
         decode.argtypes = L.okp_decode_f32.argtypes
+    L.okp_record_bytes.restype = i32
+    L.okp_record_bytes.argtypes = [i32, i32, P(ctypes.c_int32)]
+    for suffix in ('f32', 'bf16'):
+        emit = getattr(L, f'okp_decode_emit_{suffix}')
+        emit.restype = i32
+        emit.argtypes = L.okp_decode_f32.argtypes[:-1] + [P(_abi.OkpRecordSink), vp]
     L.okp_host_alias.restype = i32
     L.okp_host_alias.argtypes = [vp, P(vp)]
     L.okp_fisheye_undistort_f64.restype = i32

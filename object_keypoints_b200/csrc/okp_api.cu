@@ -63,6 +63,7 @@ int check_params(const OkpDecodeParams* prm) {
     if (prm->max_votes < 1 || prm->max_votes > 4096) return OKP_E_CAPACITY;
     if ((prm->nms_size != 5 && prm->nms_size != 3) || (prm->box_sum != 0 && prm->box_sum != 1)) return OKP_E_UNSUPPORTED;
     if (prm->top_k < 0 || prm->top_k > prm->max_peaks) return OKP_E_CAPACITY;
+    if (prm->lean_tables != 0 && prm->lean_tables != 1) return OKP_E_UNSUPPORTED;
     return OKP_OK;
 }
 
@@ -116,6 +117,51 @@ size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodePar
 
 namespace {
 
+// Everything the peak entry checks before it launches; fills the plan and the workspace carving.
+struct PeakCall {
+    PeakPlan plan;
+    bool strip;
+    int32_t* tile_count;
+    OkpPeakRecord* tile_peaks;
+};
+
+template <typename T>
+int prepare_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
+                  const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, PeakCall* call) {
+    if (!heat_dev || !tables || !workspace_dev) return OKP_E_NULL;
+    if (!tables->peak_count || !tables->peak_yx || !tables->peak_score || !tables->peak_xy || !tables->peak_conf ||
+        !tables->peak_object || !tables->peak_vote)
+        return OKP_E_NULL;
+    // the table writers use 8- and 16-byte vector stores (int2 / float2 / double2 rows)
+    if (((uintptr_t)tables->peak_yx & 7u) || ((uintptr_t)tables->peak_xy & 7u) || ((uintptr_t)tables->peak_vote & 15u))
+        return OKP_E_UNSUPPORTED;
+    const int K = params->max_peaks;
+    const int maps = N * C;
+    call->plan = plan_peaks(maps, H, W, K, (int)sizeof(T), params);
+    call->strip = call->plan.strip;
+    // TMA needs a 16-byte aligned base. The generic kernels would take the map, but with a workspace orders of magnitude
+    // larger than okp_decode_workspace_bytes() advertises for this shape: refuse instead of failing later
+    if (call->strip && ((uintptr_t)heat_dev & 15u) != 0) return OKP_E_UNSUPPORTED;
+    if (workspace_bytes < workspace_for(call->plan, maps, K, call->strip)) return OKP_E_WORKSPACE;
+    const size_t tiles = call->strip ? (size_t)overflow_grid(maps) * call->plan.tiles_per_map : (size_t)maps * call->plan.tiles_per_map;
+    uintptr_t base = align_up((uintptr_t)workspace_dev, 256);
+    call->tile_count = (int32_t*)base;
+    call->tile_peaks = (OkpPeakRecord*)(base + align_up(tiles * sizeof(int32_t), 256));
+    return OKP_OK;
+}
+
+// maps with more than K peaks ("first K in raster order"), negative / NaN values ... are redone here; a no-op otherwise
+template <typename T>
+int launch_overflow(const T* heat_dev, const PeakCall& call, int maps, const OkpDecodeParams* params,
+                    const OkpDecodeTables* tables, cudaStream_t s) {
+    auto kernel = okp_peaks_overflow_kernel<256, T>;
+    OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)call.plan.smem_bytes));
+    kernel<<<overflow_grid(maps), 256, call.plan.smem_bytes, s>>>(heat_dev, call.plan.geo, params->threshold, params->max_peaks,
+                                                                   call.tile_count, call.tile_peaks, *tables);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
 template <typename T>
 int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
                   const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
@@ -124,39 +170,21 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     rc = check_shape(N, C, H, W);
     if (rc != OKP_OK) return rc;
     if (N == 0) return OKP_OK;
-    if (!heat_dev || !tables || !workspace_dev) return OKP_E_NULL;
-    if (!tables->peak_count || !tables->peak_yx || !tables->peak_score || !tables->peak_xy || !tables->peak_conf ||
-        !tables->peak_object || !tables->peak_vote)
-        return OKP_E_NULL;
-    // the table writers use 8- and 16-byte vector stores (int2 / float2 / double2 rows)
-    if (((uintptr_t)tables->peak_yx & 7u) || ((uintptr_t)tables->peak_xy & 7u) || ((uintptr_t)tables->peak_vote & 15u))
-        return OKP_E_UNSUPPORTED;
+    PeakCall call;
+    rc = prepare_peaks<T>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, &call);
+    if (rc != OKP_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int K = params->max_peaks;
     const int maps = N * C;
-    const PeakPlan p = plan_peaks(maps, H, W, K, (int)sizeof(T), params);
-    const bool strip = p.strip && ((uintptr_t)heat_dev & 15u) == 0;      // TMA needs a 16-byte aligned base
-    if (workspace_bytes < workspace_for(p, maps, K, strip)) return OKP_E_WORKSPACE;
-    const size_t tiles = strip ? (size_t)overflow_grid(maps) * p.tiles_per_map : (size_t)maps * p.tiles_per_map;
-    uintptr_t base = align_up((uintptr_t)workspace_dev, 256);
-    int32_t* tile_count = (int32_t*)base;
-    OkpPeakRecord* tile_peaks = (OkpPeakRecord*)(base + align_up(tiles * sizeof(int32_t), 256));
+    const PeakPlan& p = call.plan;
 
-    if (strip) {
-        // persistent warp-specialised form by default; OKP_PEAKS_KERNEL=strip selects the one-shot kernel (A/B, tuning)
+    if (call.strip) {
         OkpStreamPlan stream_plan;
-        const char* which = getenv("OKP_PEAKS_KERNEL");
-        const bool one_shot = which && strcmp(which, "strip") == 0;
-        if (!one_shot && okp_stream_plan(maps, H, W, K, (int)sizeof(T), &stream_plan))
-            rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, s);
-        else
-            rc = okp_strip_launch<T>(heat_dev, p.sp, params->threshold, *tables, s);
+        if (!okp_stream_plan(maps, C, H, W, K, (int)sizeof(T), 0, params->lean_tables, &stream_plan)) return OKP_E_UNSUPPORTED;
+        rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, s);
         if (rc != OKP_OK) return rc;
-        // maps with more than K peaks ("first K in raster order") are redone here; a no-op otherwise
-        auto kernel = okp_peaks_overflow_kernel<256, T>;
-        OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        kernel<<<overflow_grid(maps), 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks, *tables);
-        OKP_CUDA_CHECK(cudaGetLastError());
+        rc = launch_overflow<T>(heat_dev, call, maps, params, tables, s);
+        if (rc != OKP_OK) return rc;
         if (params->top_k > 0) {
             okp_topk_kernel<<<(maps + 3) / 4, 128, 0, s>>>(maps, K, params->top_k, *tables);
             OKP_CUDA_CHECK(cudaGetLastError());
@@ -166,12 +194,12 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     {
         auto kernel = okp_peaks_generic_kernel<256, T>;
         OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        kernel<<<p.grid, 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, tile_count, tile_peaks);
+        kernel<<<p.grid, 256, p.smem_bytes, s>>>(heat_dev, p.geo, params->threshold, K, call.tile_count, call.tile_peaks);
         OKP_CUDA_CHECK(cudaGetLastError());
     }
     const int warps_per_block = 4;
     okp_merge_peaks_kernel<<<(maps + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
-        tile_count, tile_peaks, maps, p.tiles_per_map, W, K, *tables);
+        call.tile_count, call.tile_peaks, maps, p.tiles_per_map, W, K, C, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     if (params->top_k > 0) {
         okp_topk_kernel<<<(maps + 3) / 4, 128, 0, s>>>(maps, K, params->top_k, *tables);
@@ -180,46 +208,122 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     return OKP_OK;
 }
 
-template <typename T>
-int group_objects(const T* depth_dev, const T* centers_dev, int N, int C, int H, int W,
-                  const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
-                  const OkpDecodeTables* tables, void* stream) {
-    int rc = check_params(params);
-    if (rc != OKP_OK) return rc;
-    rc = check_shape(N, C, H, W);
-    if (rc != OKP_OK) return rc;
-    if (N == 0) return OKP_OK;
+int convert_sink(const OkpRecordSink* sink, int O, int C, int P, OkpRecordSinks* out) {
+    memset(out, 0, sizeof(*out));
+    if (!sink || sink->n_buffers == 0) return OKP_OK;
+    if (sink->n_buffers < 0 || sink->n_buffers > OKP_MAX_PEERS || sink->first_row < 0) return OKP_E_SHAPE;
+    if (sink->record_bytes < okp_compact_record_bytes(O, C, P) || (sink->record_bytes & 7)) return OKP_E_SHAPE;
+    if (!sink->buffers_dev) return OKP_E_NULL;
+    for (int d = 0; d < sink->n_buffers; ++d) {
+        if (!sink->buffers_dev[d]) return OKP_E_NULL;
+        if ((uintptr_t)sink->buffers_dev[d] & 7u) return OKP_E_UNSUPPORTED;
+        out->base[d] = (unsigned char*)sink->buffers_dev[d];
+    }
+    out->n = sink->n_buffers;
+    out->stride = sink->record_bytes;
+    out->first_row = sink->first_row;
+    out->points_offset = okp_compact_points_offset(O, C);
+    return OKP_OK;
+}
+
+// Checks and packs what the grouping needs (okp_group.cuh); *warps = frames per CTA of the stand-alone kernel.
+int make_group_args(const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
+                    const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                    const OkpDecodeTables* tables, const OkpRecordSink* sink, OkpGroupArgs* a) {
     if (!tables || (C > 1 && (!centers_dev || !keypoint_config))) return OKP_E_NULL;
     if (camera && !depth_dev) return OKP_E_NULL;
     const void* const* fields = (const void* const*)tables;
     for (size_t i = 0; i < sizeof(OkpDecodeTables) / sizeof(void*); ++i)
         if (!fields[i]) return OKP_E_NULL;
-    OkpConfig config;
-    memset(&config, 0, sizeof(config));
-    config.cfg[0] = 1;                                  // pipeline.py:36: centre map first
-    int S = 1;
+    // vector stores: double2 rows of peak_vote / votes, float2 rows of kp_xy
+    if (((uintptr_t)tables->peak_vote & 15u) || ((uintptr_t)tables->votes & 15u) || ((uintptr_t)tables->kp_xy & 7u) ||
+        ((uintptr_t)tables->peak_xy & 7u))
+        return OKP_E_UNSUPPORTED;
+    memset(a, 0, sizeof(*a));
+    a->config.cfg[0] = 1;                               // pipeline.py:36: centre map first
+    int S = 1, P = 1;
     for (int i = 0; i < C - 1; ++i) {
         if (keypoint_config[i] < 1 || keypoint_config[i] > OKP_MAX_SLOTS) return OKP_E_CAPACITY;
-        config.cfg[1 + i] = keypoint_config[i];
+        a->config.cfg[1 + i] = keypoint_config[i];
         if (keypoint_config[i] > S) S = keypoint_config[i];
+        P += keypoint_config[i];
     }
-    OkpCamera cam;
-    memset(&cam, 0, sizeof(cam));
-    if (camera) cam = *camera;
+    if (camera) a->cam = *camera;
+    a->prm = *params;
+    a->depth = depth_dev; a->centers = centers_dev;
+    a->N = N; a->C = C; a->H = H; a->W = W; a->S = S; a->P = P;
+    a->have_camera = camera != nullptr;
     const int K = params->max_peaks, O = params->max_objects;
-    bool stash = true;
+    a->stash = 1;
     size_t per_frame = okp_group_smem_bytes(C, K, O, S, true);
-    if (per_frame > 160 * 1024) { stash = false; per_frame = okp_group_smem_bytes(C, K, O, S, false); }
-    int warps = (int)((size_t)(48 * 1024) / per_frame);          // frames per CTA: one warp each
+    if (per_frame > 160 * 1024) { a->stash = 0; per_frame = okp_group_smem_bytes(C, K, O, S, false); }
+    a->frame_smem_bytes = (int)per_frame;
+    return convert_sink(sink, O, C, P, &a->sinks);
+}
+
+template <typename T>
+int launch_group(const OkpGroupArgs& a, int only_pending, const OkpDecodeTables* tables, cudaStream_t s) {
+    int warps = (int)((size_t)(48 * 1024) / a.frame_smem_bytes);          // frames per CTA: one warp each
     if (warps > 4) warps = 4;
     if (warps < 1) warps = 1;
-    const size_t smem = per_frame * warps;
+    const size_t smem = (size_t)a.frame_smem_bytes * warps;
     auto kernel = okp_group_kernel<T>;
     if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(N + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
-        depth_dev, centers_dev, N, C, H, W, config, cam, camera != nullptr, *params, S, stash ? 1 : 0, (int)per_frame, *tables);
+    kernel<<<(a.N + warps - 1) / warps, warps * 32, smem, s>>>(a, only_pending, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
+}
+
+template <typename T>
+int group_objects(const T* depth_dev, const T* centers_dev, int N, int C, int H, int W,
+                  const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                  const OkpDecodeTables* tables, const OkpRecordSink* sink, void* stream) {
+    int rc = check_params(params);
+    if (rc != OKP_OK) return rc;
+    rc = check_shape(N, C, H, W);
+    if (rc != OKP_OK) return rc;
+    if (N == 0) return OKP_OK;
+    OkpGroupArgs a;
+    rc = make_group_args(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, sink, &a);
+    if (rc != OKP_OK) return rc;
+    return launch_group<T>(a, 0, tables, (cudaStream_t)stream);
+}
+
+// ObjectKeypointPipeline.__call__ for a batch (perception/pipeline.py:182-200): the fused streaming pass where the
+// shape and the mode allow it, else peak extraction followed by grouping.
+template <typename T>
+int decode(const T* heat_dev, const T* depth_dev, const T* centers_dev, int N, int C, int H, int W,
+           const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+           const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, const OkpRecordSink* sink,
+           void* stream) {
+    int rc = check_params(params);
+    if (rc != OKP_OK) return rc;
+    rc = check_shape(N, C, H, W);
+    if (rc != OKP_OK) return rc;
+    if (N == 0) return OKP_OK;
+    OkpGroupArgs a;
+    rc = make_group_args(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, sink, &a);
+    if (rc != OKP_OK) return rc;
+    PeakCall call;
+    rc = prepare_peaks<T>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, &call);
+    if (rc != OKP_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    OkpStreamPlan stream_plan;
+    const bool fused = call.strip && params->top_k == 0 &&
+                       okp_stream_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), a.frame_smem_bytes,
+                                       params->lean_tables, &stream_plan) && stream_plan.F > 0;
+    if (!fused) {
+        rc = extract_peaks<T>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
+        if (rc != OKP_OK) return rc;
+        return launch_group<T>(a, 0, tables, s);
+    }
+    rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, &a, s);
+    if (rc != OKP_OK) return rc;
+    // fix-up launches: maps that overflowed the fast path are redone exactly, then their frames are grouped. With no such
+    // map each is one read of peak_count / n_objects
+    rc = launch_overflow<T>(heat_dev, call, N * C, params, tables, s);
+    if (rc != OKP_OK) return rc;
+    return launch_group<T>(a, 1, tables, s);
 }
 
 }  // namespace
@@ -240,14 +344,14 @@ int okp_extract_peaks_bf16(const void* heat_dev, int N, int C, int H, int W, con
 int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
                           const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
                           const OkpDecodeTables* tables, void* stream) {
-    return group_objects<float>(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, stream);
+    return group_objects<float>(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, nullptr, stream);
 }
 
 int okp_group_objects_bf16(const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
                            const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
                            const OkpDecodeTables* tables, void* stream) {
     return group_objects<__nv_bfloat16>((const __nv_bfloat16*)depth_dev, (const __nv_bfloat16*)centers_dev, N, C, H, W,
-                                        keypoint_config, camera, params, tables, stream);
+                                        keypoint_config, camera, params, tables, nullptr, stream);
 }
 
 int okp_host_alias(const void* host_ptr, void** dev_ptr_out) {
@@ -265,17 +369,41 @@ int okp_host_alias(const void* host_ptr, void** dev_ptr_out) {
 int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
                    const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
                    const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
-    int rc = okp_extract_peaks_f32(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
-    if (rc != OKP_OK) return rc;
-    return okp_group_objects_f32(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, stream);
+    return decode<float>(heat_dev, depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, workspace_dev,
+                         workspace_bytes, nullptr, stream);
 }
 
 int okp_decode_bf16(const void* heat_dev, const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
                     const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
                     const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
-    int rc = okp_extract_peaks_bf16(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
-    if (rc != OKP_OK) return rc;
-    return okp_group_objects_bf16(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, stream);
+    return decode<__nv_bfloat16>((const __nv_bfloat16*)heat_dev, (const __nv_bfloat16*)depth_dev, (const __nv_bfloat16*)centers_dev,
+                                 N, C, H, W, keypoint_config, camera, params, tables, workspace_dev, workspace_bytes, nullptr, stream);
+}
+
+int okp_record_bytes(int O, int C, const int32_t* keypoint_config) {
+    if (O < 1 || O > OKP_MAX_OBJECTS || C < 1 || C > OKP_MAX_MAPS || (C > 1 && !keypoint_config)) return 0;
+    int P = 1;
+    for (int i = 0; i < C - 1; ++i) {
+        if (keypoint_config[i] < 1 || keypoint_config[i] > OKP_MAX_SLOTS) return 0;
+        P += keypoint_config[i];
+    }
+    return okp_compact_record_bytes(O, C, P);
+}
+
+int okp_decode_emit_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
+                        const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                        const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
+                        const OkpRecordSink* sink, void* stream) {
+    return decode<float>(heat_dev, depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, workspace_dev,
+                         workspace_bytes, sink, stream);
+}
+
+int okp_decode_emit_bf16(const void* heat_dev, const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
+                         const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                         const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
+                         const OkpRecordSink* sink, void* stream) {
+    return decode<__nv_bfloat16>((const __nv_bfloat16*)heat_dev, (const __nv_bfloat16*)depth_dev, (const __nv_bfloat16*)centers_dev,
+                                 N, C, H, W, keypoint_config, camera, params, tables, workspace_dev, workspace_bytes, sink, stream);
 }
 
 int okp_fisheye_undistort_f64(const double* xy_dev, int n, const OkpCamera* camera, int round_to_f32,

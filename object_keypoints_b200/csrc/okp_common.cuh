@@ -26,6 +26,8 @@ struct OkpPeakRecord {
     int32_t pad[3];
 };
 
+struct OkpConfig { int32_t cfg[OKP_MAX_MAPS]; };    // cfg[0] = 1 (centre map), then keypoint_config
+
 __device__ __forceinline__ int okp_min(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int okp_max(int a, int b) { return a > b ? a : b; }
 __device__ __forceinline__ int okp_clamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -1,16 +1,23 @@
 // okp_group.cuh -- K3 + K4: centre-vector voting into object instances, over-detection
-// resolution and 3D points. One CTA per frame; everything it touches is a few hundred bytes of
+// resolution and 3D points. One WARP per frame; everything it touches is a few hundred bytes of
 // peak records plus 3 gathered floats per spoke peak (2 centre-vector components, 1 depth).
 //
 // Replaces ObjectExtraction.__call__ (perception/pipeline.py:104-153) and the DetectionToPoint
 // loop of ObjectKeypointPipeline.__call__ (pipeline.py:189-199).
+//
+// okp_group_frame() is the one statement of that arithmetic. It runs in two places:
+//   * in the epilogue warps of the fused decode kernel (okp_peaks_stream.cuh, FUSED = true), straight from the
+//     frame's sorted peak list in shared memory while the compute warps stream the next frames -- the normal path;
+//   * in okp_group_kernel below, which first pulls the frame's peak tables from HBM: the stand-alone entry
+//     (okp_group_objects_*), shapes the fused kernel does not cover, and the fix-up of frames one of whose maps
+//     took the overflow path (marked by n_objects = OKP_GROUP_PENDING).
 #pragma once
 #include "okp_common.cuh"
 #include "okp_geometry.cuh"
+#include "okp_records.cuh"
 
 #define OKP_KMEANS_MAX_INITS 256
 
-struct OkpConfig { int32_t cfg[OKP_MAX_MAPS]; };    // cfg[0] = 1 (centre map), then keypoint_config
 
 // Deterministic stand-in for the reference's unseeded KMeans(init='random') (pipeline.py:146-148):
 // Lloyd's algorithm from every k-subset of the detections (lexicographic, at most
@@ -78,7 +85,26 @@ __device__ __noinline__ void okp_cluster_detections(const float* __restrict__ xy
 #undef OKP_PT
 }
 
-// Shared-memory bytes ONE frame (= one warp) of okp_group_kernel needs; `stash` = the kept keypoints are also
+
+#define OKP_GROUP_PENDING (-1)      // n_objects marker: the frame's grouping is left to the fix-up launch
+
+// What the grouping needs besides the peak list (one kernel parameter, read from the constant bank).
+struct OkpGroupArgs {
+    const void* depth;              // [N,C,H,W]     element type E (device memory or a pinned-host alias: gather-only)
+    const void* centers;            // [N,C-1,2,H,W]
+    OkpConfig config;
+    OkpCamera cam;
+    OkpDecodeParams prm;
+    OkpRecordSinks sinks;           // optional compact records (okp_records.cuh); n = 0: none
+    int N, C, H, W;
+    int S;                          // max(1, max(keypoint_config))
+    int P;                          // points per object in a record: 1 + sum(keypoint_config)
+    int have_camera;
+    int stash;                      // kept keypoints are also held in shared memory for the 3D lift
+    int frame_smem_bytes;           // okp_group_smem_bytes()
+};
+
+// Shared-memory bytes ONE frame (= one warp) of the grouping needs; `stash` = the kept keypoints are also
 // held in shared memory for the 3D lift (dropped when the worst-case capacities would not fit).
 static inline size_t okp_group_smem_bytes(int C, int K, int O, int S, bool stash) {
     size_t bytes = (size_t)O * 2 * sizeof(double);                                                  // centres
@@ -89,46 +115,60 @@ static inline size_t okp_group_smem_bytes(int C, int K, int O, int S, bool stash
     return (bytes + 15) / 16 * 16;
 }
 
-// Latency is what this kernel is made of (a frame is ~40 peaks, and every 3D lift is a serial float64
-// Newton + tan chain of a few microseconds): ONE WARP PER FRAME, several frames per CTA, so that an SM holds
-// 64 frames whose chains overlap (the CTA-per-frame form held 16 and took 4x longer). The frame's peak
-// records are pulled into shared memory with one round trip, every later phase works on shared memory, and
-// results leave as fire-and-forget stores. Global round trips on the critical path: counts -> records ->
-// centre-vector gather -> depth gather. No block-level barrier anywhere: warps are independent.
-template <typename E>
-__global__ void __launch_bounds__(128)
-okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int N, int C, int H, int W,
-                 OkpConfig config, OkpCamera cam, int have_camera, OkpDecodeParams prm, int S, int stash,
-                 int frame_smem_bytes, OkpDecodeTables t) {
-    constexpr int THREADS = 32;                            // a frame's team: the strides below
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (n >= N) return;
-    const int K = prm.max_peaks, O = prm.max_objects, V = prm.max_votes, T = C - 1;
-    const size_t HW = (size_t)H * W;
-    extern __shared__ __align__(16) unsigned char group_smem[];
-    unsigned char* mine = group_smem + (size_t)(threadIdx.x >> 5) * frame_smem_bytes;
-    double (*s_center)[2] = reinterpret_cast<double (*)[2]>(mine);          // [O][2]
-    double* s_vote = reinterpret_cast<double*>(mine) + (size_t)O * 2;       // [C][K][2] predicted centre of a spoke peak
-    float* s_xy = reinterpret_cast<float*>(s_vote + (size_t)C * K * 2);     // [C][K][2] centroid (x, y)
-    float* s_conf = s_xy + (size_t)C * K * 2;                               // [C][K]
-    int* s_obj = reinterpret_cast<int*>(s_conf + (size_t)C * K);            // [C][K]    object of a peak, -1 = none
-    int* s_kept = s_obj + (size_t)C * K;                                    // [O][C]    keypoints kept per (object, map)
-    int* s_counts = s_kept + (size_t)O * C;                                 // [OKP_MAX_MAPS]
-    unsigned int* s_flags_ptr = reinterpret_cast<unsigned int*>(s_counts + OKP_MAX_MAPS);
-    float* s_kept_xy = reinterpret_cast<float*>(s_flags_ptr + 1);           // [O][C][S][2] (only with stash)
-#define s_flags (*s_flags_ptr)
+// The frame's scratch, carved out of `mine` (okp_group_smem_bytes() bytes, 16-byte aligned).
+struct OkpGroupScratch {
+    double (*center)[2];            // [O][2]
+    double* vote;                   // [C][K][2] predicted centre of a spoke peak
+    float* xy;                      // [C][K][2] centroid (x, y)        -- filled by the caller
+    float* conf;                    // [C][K]                           -- filled by the caller
+    int* obj;                       // [C][K]    object of a peak, -1 = none
+    int* kept;                      // [O][C]    keypoints kept per (object, map)
+    int* counts;                    // [OKP_MAX_MAPS] min(peaks of the map, K) -- filled by the caller
+    unsigned int* flags;            // [1]       OKP_FLAG_* seen so far     -- initialised by the caller
+    float* kept_xy;                 // [O][C][S][2] (only with stash)
+};
 
+__device__ __forceinline__ OkpGroupScratch okp_group_scratch(unsigned char* mine, int C, int K, int O) {
+    OkpGroupScratch g;
+    g.center = reinterpret_cast<double (*)[2]>(mine);
+    g.vote = reinterpret_cast<double*>(mine) + (size_t)O * 2;
+    g.xy = reinterpret_cast<float*>(g.vote + (size_t)C * K * 2);
+    g.conf = g.xy + (size_t)C * K * 2;
+    g.obj = reinterpret_cast<int*>(g.conf + (size_t)C * K);
+    g.kept = g.obj + (size_t)C * K;
+    g.counts = g.kept + (size_t)O * C;
+    g.flags = reinterpret_cast<unsigned int*>(g.counts + OKP_MAX_MAPS);
+    g.kept_xy = reinterpret_cast<float*>(g.flags + 1);
+    return g;
+}
+
+// Latency is what the grouping is made of (a frame is ~40 peaks, and every 3D lift is a serial float64
+// Newton + tan chain of a few microseconds): ONE WARP PER FRAME. Expects g.xy / g.conf / g.counts / g.flags to
+// hold the frame's peaks (raster order per map); every later phase works on shared memory, results leave as
+// fire-and-forget stores. Global round trips on the critical path: centre-vector gather -> depth gather.
+// No block-level barrier: warps are independent.
+//   OkpDecodeParams.lean_tables == 0: every slot of the frame's object tables that is not written is reset (zero / -1),
+//                  as include/okp.h promises by default;
+//   lean_tables == 1: only the valid slots are written (the tables of a 64x64 frame are a quarter of its heatmap
+//                  bytes; clearing them costs more DRAM traffic than the frame's peaks).
+template <typename E>
+__device__ __forceinline__ void okp_group_frame(const int n, const int lane, const OkpGroupScratch& g, const OkpGroupArgs& a,
+                                                const OkpDecodeTables& t) {
+    const bool CLEAR = a.prm.lean_tables == 0;
+    constexpr int THREADS = 32;
+    const int C = a.C, H = a.H, W = a.W, S = a.S;
+    const int K = a.prm.max_peaks, O = a.prm.max_objects, V = a.prm.max_votes, T = C - 1;
+    const size_t HW = (size_t)H * W;
     const size_t m0 = (size_t)n * C;
-    if (lane == 0) s_flags = 0;
-    __syncwarp();
-    if (lane < C) {
-        const int c = t.peak_count[m0 + lane];
-        s_counts[lane] = c < K ? c : K;
-        if (c > K) atomicOr(&s_flags, OKP_FLAG_PEAK_OVERFLOW);
-    }
-    // reset this frame's object tables (flat, coalesced; every region is contiguous per frame)
-    {
+    const E* depth = reinterpret_cast<const E*>(a.depth);
+    const E* centers = reinterpret_cast<const E*>(a.centers);
+    unsigned int& s_flags = *g.flags;
+    const int* s_counts = g.counts;
+
+    const int n_center = s_counts[0];
+    const int n_obj = n_center < O ? n_center : O;
+    if (CLEAR) {
+        // reset this frame's object tables (flat, coalesced; every region is contiguous per frame)
         const int oc = O * C, ocs = oc * S;
         int32_t* assigned = t.kp_assigned + (size_t)n * oc;
         int32_t* count = t.kp_count + (size_t)n * oc;
@@ -144,38 +184,35 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
         double* votes = t.votes + (size_t)n * O * V * 2;
         for (int i = lane; i < O * V * 2; i += THREADS) votes[i] = 0.0;
     }
-    __syncwarp();
-
-    const int n_center = s_counts[0];
     if (n_center == 0) {                                   // pipeline.py:105-106
-        if (lane == 0) { t.n_objects[n] = 0; t.flags[n] = s_flags | OKP_FLAG_NO_CENTERS; }
+        if (lane == 0) {
+            const unsigned int f = s_flags | OKP_FLAG_NO_CENTERS;
+            t.n_objects[n] = 0; t.flags[n] = f;
+            okp_record_header(a.sinks, n, 0, f);
+        }
         return;
     }
-    const int n_obj = n_center < O ? n_center : O;
     if (lane == 0 && n_center > O) atomicOr(&s_flags, OKP_FLAG_OBJECT_OVERFLOW);
 
-    // ---- the frame's peak records into shared memory (one round trip); spoke peaks fetch their centre vector
-    // in the same pass and vote as soon as the centres are known ----
+    // ---- centre peaks become objects (pipeline.py:109-114); spoke peaks fetch their centre vector ----
     for (int i = lane; i < C * K; i += THREADS) {
         const int c = i / K, k = i - c * K;
         if (k >= s_counts[c]) continue;
         const size_t s = (m0 + c) * K + k;
-        const float2 p = *reinterpret_cast<const float2*>(t.peak_xy + 2 * s);
-        s_xy[2 * i] = p.x; s_xy[2 * i + 1] = p.y;
-        s_conf[i] = t.peak_conf[s];
-        if (c == 0) {                                      // pipeline.py:109-114: one object per centre peak
+        const float px = g.xy[2 * i], py = g.xy[2 * i + 1];
+        if (c == 0) {
             const int o = k < n_obj ? k : -1;
-            s_obj[i] = o;
-            if (o >= 0) { s_center[o][0] = (double)p.x; s_center[o][1] = (double)p.y; t.peak_object[s] = o; }
+            g.obj[i] = o;
+            if (o >= 0) { g.center[o][0] = (double)px; g.center[o][1] = (double)py; }
+            t.peak_object[s] = o;
         } else {
-            const int xi = okp_clamp(__float2int_rn(p.x), 0, W - 1);      // np.round = half to even
-            const int yi = okp_clamp(__float2int_rn(p.y), 0, H - 1);
+            const int xi = okp_clamp(__float2int_rn(px), 0, W - 1);       // np.round = half to even
+            const int yi = okp_clamp(__float2int_rn(py), 0, H - 1);
             const E* cmap = centers + ((size_t)n * T + (c - 1)) * 2 * HW;
             const double vx = ((double)xi + 0.5) + (double)okp_ld<E>(cmap + (size_t)yi * W + xi);
             const double vy = ((double)yi + 0.5) + (double)okp_ld<E>(cmap + HW + (size_t)yi * W + xi);
-            s_vote[2 * i] = vx; s_vote[2 * i + 1] = vy;
-            t.peak_vote[2 * s] = vx;
-            t.peak_vote[2 * s + 1] = vy;
+            g.vote[2 * i] = vx; g.vote[2 * i + 1] = vy;
+            reinterpret_cast<double2*>(t.peak_vote)[s] = make_double2(vx, vy);
         }
     }
     __syncwarp();
@@ -184,19 +221,19 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
     for (int i = K + lane; i < C * K; i += THREADS) {
         const int c = i / K, k = i - c * K;
         if (k >= s_counts[c]) continue;
-        const double vx = s_vote[2 * i], vy = s_vote[2 * i + 1];
+        const double vx = g.vote[2 * i], vy = g.vote[2 * i + 1];
         int arg = 0;
         double dmin = 0.0;
         for (int o = 0; o < n_obj; ++o) {
-            const double dx = s_center[o][0] - vx, dy = s_center[o][1] - vy;
+            const double dx = g.center[o][0] - vx, dy = g.center[o][1] - vy;
             const double d = sqrt(dx * dx + dy * dy);
             if (o == 0 || d < dmin) { dmin = d; arg = o; }             // first minimum, like np.argmin
         }
-        if (dmin > prm.outlier_distance) {
+        if (dmin > a.prm.outlier_distance) {
             atomicOr(&s_flags, OKP_FLAG_OUTLIER_SKIPPED);              // the reference prints and skips
             arg = -1;
         }
-        s_obj[i] = arg;
+        g.obj[i] = arg;
         t.peak_object[(m0 + c) * K + k] = arg;
     }
     __syncwarp();
@@ -207,10 +244,9 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
         int nv = 0;
         for (int c = 1; c < C; ++c) {
             for (int k = 0; k < s_counts[c]; ++k) {
-                if (s_obj[c * K + k] != o) continue;
+                if (g.obj[c * K + k] != o) continue;
                 if (nv < V) {
-                    t.votes[(ob * V + nv) * 2] = s_vote[(c * K + k) * 2];
-                    t.votes[(ob * V + nv) * 2 + 1] = s_vote[(c * K + k) * 2 + 1];
+                    reinterpret_cast<double2*>(t.votes)[ob * V + nv] = make_double2(g.vote[(c * K + k) * 2], g.vote[(c * K + k) * 2 + 1]);
                 } else {
                     atomicOr(&s_flags, OKP_FLAG_VOTE_OVERFLOW);
                 }
@@ -221,18 +257,22 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
     }
 
     // ---- per (object, map): resolve over-detection ----
-    float* kept_xy = stash ? s_kept_xy : t.kp_xy + (size_t)n * O * C * S * 2;
+    float* kept_xy = a.stash ? g.kept_xy : t.kp_xy + (size_t)n * O * C * S * 2;
     for (int i = lane; i < n_obj * C; i += THREADS) {
         const int o = i / C, c = i - o * C;
         const size_t oc = ((size_t)n * O + o) * C + c;
-        const int limit = config.cfg[c];
-        const int* obj = s_obj + c * K;
-        const float* xy = s_xy + (size_t)c * K * 2;
+        const int limit = a.config.cfg[c];
+        const int* obj = g.obj + c * K;
+        const float* xy = g.xy + (size_t)c * K * 2;
         int cnt = 0;
         for (int k = 0; k < s_counts[c]; ++k) cnt += (obj[k] == o);
         t.kp_assigned[oc] = cnt;
-        s_kept[i] = 0;
-        if (cnt == 0) continue;                            // pipeline.py:150-152: empty array
+        g.kept[i] = 0;
+        if (cnt == 0) {                                    // pipeline.py:150-152: empty array
+            if (!CLEAR) t.kp_count[oc] = 0;
+            okp_record_count(a.sinks, n, O, C, o, c, 0);
+            continue;
+        }
         float pts[OKP_MAX_SLOTS][2];
         int ids[OKP_MAX_SLOTS];
         int kept = 0;
@@ -249,7 +289,7 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
             float best = 0.0f;
             for (int k = 0; k < s_counts[c]; ++k)
                 if (obj[k] == o) {
-                    const float conf = s_conf[c * K + k];
+                    const float conf = g.conf[c * K + k];
                     if (arg < 0 || conf > best) { best = conf; arg = k; }   // first maximum, like np.argmax
                 }
             ids[0] = arg;
@@ -259,39 +299,80 @@ okp_group_kernel(const E* __restrict__ depth, const E* __restrict__ centers, int
             atomicOr(&s_flags, OKP_FLAG_ARGMAX_RESOLVED);
         } else {                                           // pipeline.py:143-148: cluster
             unsigned char members[OKP_MAX_PEAKS];
-            int g = 0;
+            int m = 0;
             for (int k = 0; k < s_counts[c]; ++k)
-                if (obj[k] == o) members[g++] = (unsigned char)k;
+                if (obj[k] == o) members[m++] = (unsigned char)k;
             kept = limit;
-            okp_cluster_detections(xy, members, g, kept, prm.kmeans_iterations, &pts[0][0]);
+            okp_cluster_detections(xy, members, m, kept, a.prm.kmeans_iterations, &pts[0][0]);
             for (int s = 0; s < kept; ++s) ids[s] = -1;
             atomicOr(&s_flags, OKP_FLAG_CLUSTERED);
         }
         t.kp_count[oc] = kept;
-        s_kept[i] = kept;
+        okp_record_count(a.sinks, n, O, C, o, c, kept);
+        g.kept[i] = kept;
         for (int s = 0; s < kept; ++s) {
             t.kp_peak[oc * S + s] = ids[s];
-            t.kp_xy[(oc * S + s) * 2] = pts[s][0];
-            t.kp_xy[(oc * S + s) * 2 + 1] = pts[s][1];
-            if (stash) { s_kept_xy[((size_t)i * S + s) * 2] = pts[s][0]; s_kept_xy[((size_t)i * S + s) * 2 + 1] = pts[s][1]; }
+            reinterpret_cast<float2*>(t.kp_xy)[oc * S + s] = make_float2(pts[s][0], pts[s][1]);
+            if (a.stash) { g.kept_xy[((size_t)i * S + s) * 2] = pts[s][0]; g.kept_xy[((size_t)i * S + s) * 2 + 1] = pts[s][1]; }
         }
     }
-    __syncwarp();                                       // also makes the kp_xy stores visible to the block (no stash)
+    __syncwarp();                                       // also makes the kp_xy stores visible to the warp (no stash)
 
-    // ---- lift every kept keypoint to 3D, one thread each (pipeline.py:164-171, 189-199) ----
-    if (have_camera) {
-        for (int i = lane; i < n_obj * C * S; i += THREADS) {
-            const int ocl = i / S, s = i - ocl * S;        // ocl = o * C + c inside the frame
-            if (s >= s_kept[ocl]) continue;
-            const int c = ocl % C;
-            double p3[3];
+    // ---- lift every kept keypoint to 3D, one thread each (pipeline.py:164-171, 189-199); the point goes to the
+    // table and, when the caller asked for them, into the compact record of every sink (okp_records.cuh) ----
+    for (int i = lane; i < n_obj * C * S; i += THREADS) {
+        const int ocl = i / S, s = i - ocl * S;        // ocl = o * C + c inside the frame
+        if (s >= g.kept[ocl]) continue;
+        const int o = ocl / C, c = ocl - o * C;
+        double p3[3] = {0.0, 0.0, 0.0};
+        if (a.have_camera) {
             okp_detection_to_point(kept_xy[((size_t)ocl * S + s) * 2], kept_xy[((size_t)ocl * S + s) * 2 + 1],
-                                   depth + (m0 + c) * HW, H, W, cam, prm.compat_clip_bug, p3);
+                                   depth + (m0 + c) * HW, H, W, a.cam, a.prm.compat_clip_bug, p3);
             double* out = t.kp_point + (((size_t)n * O * C + ocl) * S + s) * 3;
             out[0] = p3[0]; out[1] = p3[1]; out[2] = p3[2];
         }
+        okp_record_point(a.sinks, n, O, C, a.P, a.config, o, c, s, p3);
     }
     __syncwarp();
-    if (lane == 0) { t.n_objects[n] = n_obj; t.flags[n] = s_flags; }
-#undef s_flags
+    if (lane == 0) {
+        const unsigned int f = s_flags;
+        t.n_objects[n] = n_obj; t.flags[n] = f;
+        okp_record_header(a.sinks, n, n_obj, f);
+    }
+}
+
+// Stand-alone form: one warp per frame, four frames per CTA (an SM holds 64 frames whose latency chains overlap).
+// The frame's peak records are pulled from the tables into shared memory with one round trip. only_pending != 0: only
+// frames marked OKP_GROUP_PENDING by the fused decode kernel are processed (the fix-up launch: with no overflowing map
+// it is one read of n_objects per frame).
+template <typename E>
+__global__ void __launch_bounds__(128)
+okp_group_kernel(const __grid_constant__ OkpGroupArgs a, const int only_pending, const OkpDecodeTables t) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    if (only_pending && t.n_objects[n] != OKP_GROUP_PENDING) return;
+    const int C = a.C, K = a.prm.max_peaks, O = a.prm.max_objects;
+    extern __shared__ __align__(16) unsigned char group_smem[];
+    const OkpGroupScratch g = okp_group_scratch(group_smem + (size_t)(threadIdx.x >> 5) * a.frame_smem_bytes, C, K, O);
+    const size_t m0 = (size_t)n * C;
+    // OKP_FLAG_GENERIC_PATH is a property of the call, written by the peak extraction: keep it
+    if (lane == 0) *g.flags = t.flags[n] & OKP_FLAG_GENERIC_PATH;
+    __syncwarp();
+    if (lane < C) {
+        const int c = t.peak_count[m0 + lane];
+        g.counts[lane] = c < K ? c : K;
+        if (c > K) atomicOr(g.flags, OKP_FLAG_PEAK_OVERFLOW);
+    }
+    __syncwarp();
+    for (int i = lane; i < C * K; i += 32) {
+        const int c = i / K, k = i - c * K;
+        if (k >= g.counts[c]) continue;
+        const size_t s = (m0 + c) * K + k;
+        const float2 p = *reinterpret_cast<const float2*>(t.peak_xy + 2 * s);
+        g.xy[2 * i] = p.x; g.xy[2 * i + 1] = p.y;
+        g.conf[i] = t.peak_conf[s];
+    }
+    __syncwarp();
+    okp_group_frame<E>(n, lane, g, a, t);
 }

@@ -1,8 +1,15 @@
 // okp_host_pack.cpp -- HOST side of the sparse heatmap transfer (see csrc/okp_sparse.cuh for the argument why
-// dropping empty regions leaves every table bit-identical). Plain C++ with OpenMP and AVX2, compiled by g++ and linked
-// into libokp.so: the pass has to run at memory speed (it reads every heatmap byte once), otherwise it would be slower
-// than the PCIe copy it replaces.
+// dropping empty regions leaves every table bit-identical). Plain C++ with OpenMP, compiled by g++ and linked into
+// libokp.so: the pass has to run at memory speed (it reads every heatmap byte once), otherwise it would be slower than
+// the PCIe copy it replaces. On x86-64 the marking loop has an AVX2 form that is selected at RUN time
+// (__builtin_cpu_supports); every other host (aarch64 Grace, x86 without AVX2) runs the portable loop, which g++
+// vectorises for the build target. The file is compiled without -mavx2 so nothing outside the guarded function uses it.
+#if defined(__x86_64__) || defined(_M_X64)
+#define OKP_HOST_X86 1
 #include <immintrin.h>
+#else
+#define OKP_HOST_X86 0
+#endif
 #include <math.h>
 #include <omp.h>
 #include <stdint.h>
@@ -17,30 +24,58 @@
 static inline int tiles_y(int H) { return (H + OKP_TILE_H - 1) / OKP_TILE_H; }
 static inline int tiles_x(int W) { return (W + OKP_TILE_W - 1) / OKP_TILE_W; }
 
-// marks[ty * TX + tx] |= 1 if the tile holds a value that is NOT <= tau (so NaN counts as active: it must reach the
-// device unchanged). Row-wise: one pass over the map in memory order.
-static void mark_active_tiles(const float* map, int H, int W, float tau, unsigned char* marks, int TX) {
+// One full-height (4-row) band of 16-wide tiles: marks[tx] = 1 if the tile holds a value that is NOT <= tau (so NaN
+// counts as active: it must reach the device unchanged).
+static void mark_band_portable(const float* base, int W, int full, float tau, unsigned char* mrow) {
+    for (int tx = 0; tx < full; ++tx) {
+        unsigned char any = 0;
+        for (int r = 0; r < OKP_TILE_H; ++r) {
+            const float* row = base + (size_t)r * W + tx * OKP_TILE_W;
+            for (int c = 0; c < OKP_TILE_W; ++c) any |= (unsigned char)!(row[c] <= tau);
+        }
+        mrow[tx] = any;
+    }
+}
+
+#if OKP_HOST_X86
+__attribute__((target("avx2")))
+static void mark_band_avx2(const float* base, int W, int full, float tau, unsigned char* mrow) {
     const __m256 vtau = _mm256_set1_ps(tau);
+    const float *r0 = base, *r1 = base + W, *r2 = base + 2 * (size_t)W, *r3 = base + 3 * (size_t)W;
+    for (int tx = 0; tx < full; ++tx) {                    // four row streams, one mark store per tile
+        const int x = tx * OKP_TILE_W;
+        __m256 hit = _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r0 + x), vtau, _CMP_NLE_UQ),
+                                  _mm256_cmp_ps(_mm256_loadu_ps(r0 + x + 8), vtau, _CMP_NLE_UQ));
+        hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r1 + x), vtau, _CMP_NLE_UQ),
+                                             _mm256_cmp_ps(_mm256_loadu_ps(r1 + x + 8), vtau, _CMP_NLE_UQ)));
+        hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r2 + x), vtau, _CMP_NLE_UQ),
+                                             _mm256_cmp_ps(_mm256_loadu_ps(r2 + x + 8), vtau, _CMP_NLE_UQ)));
+        hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r3 + x), vtau, _CMP_NLE_UQ),
+                                             _mm256_cmp_ps(_mm256_loadu_ps(r3 + x + 8), vtau, _CMP_NLE_UQ)));
+        mrow[tx] = (unsigned char)(_mm256_movemask_ps(hit) != 0);
+    }
+}
+#endif
+
+typedef void (*MarkBandFn)(const float*, int, int, float, unsigned char*);
+
+static MarkBandFn pick_mark_band() {
+#if OKP_HOST_X86
+    if (__builtin_cpu_supports("avx2")) return mark_band_avx2;
+#endif
+    return mark_band_portable;
+}
+
+// Row-wise: one pass over the map in memory order.
+static void mark_active_tiles(const float* map, int H, int W, float tau, unsigned char* marks, int TX, MarkBandFn band) {
     const int full = W / OKP_TILE_W;                       // tile columns that are 16 wide
     const int TY = tiles_y(H);
     for (int ty = 0; ty < TY; ++ty) {
         const int y0 = ty * OKP_TILE_H, rows = y0 + OKP_TILE_H <= H ? OKP_TILE_H : H - y0;
         const float* base = map + (size_t)y0 * W;
         unsigned char* mrow = marks + (size_t)ty * TX;
-        if (rows == OKP_TILE_H) {                          // four row streams, one mark store per tile
-            const float *r0 = base, *r1 = base + W, *r2 = base + 2 * (size_t)W, *r3 = base + 3 * (size_t)W;
-            for (int tx = 0; tx < full; ++tx) {
-                const int x = tx * OKP_TILE_W;
-                __m256 hit = _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r0 + x), vtau, _CMP_NLE_UQ),
-                                          _mm256_cmp_ps(_mm256_loadu_ps(r0 + x + 8), vtau, _CMP_NLE_UQ));
-                hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r1 + x), vtau, _CMP_NLE_UQ),
-                                                     _mm256_cmp_ps(_mm256_loadu_ps(r1 + x + 8), vtau, _CMP_NLE_UQ)));
-                hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r2 + x), vtau, _CMP_NLE_UQ),
-                                                     _mm256_cmp_ps(_mm256_loadu_ps(r2 + x + 8), vtau, _CMP_NLE_UQ)));
-                hit = _mm256_or_ps(hit, _mm256_or_ps(_mm256_cmp_ps(_mm256_loadu_ps(r3 + x), vtau, _CMP_NLE_UQ),
-                                                     _mm256_cmp_ps(_mm256_loadu_ps(r3 + x + 8), vtau, _CMP_NLE_UQ)));
-                mrow[tx] = (unsigned char)(_mm256_movemask_ps(hit) != 0);
-            }
+        if (rows == OKP_TILE_H) {
+            band(base, W, full, tau, mrow);
         } else {
             for (int tx = 0; tx < full; ++tx) {
                 unsigned char any = 0;
@@ -77,12 +112,13 @@ extern "C" int okp_host_pack_tiles_f32(const float* heat_host, int maps, int H, 
     // a box sum above the threshold needs a value above threshold / 25; the slack covers the 24 float32 roundings
     const float tau = threshold > 0.0f ? threshold / 25.0f * (1.0f - 1e-5f) : -INFINITY;
     if (threads <= 0) threads = omp_get_max_threads();
+    const MarkBandFn band = pick_mark_band();
     // pass 1: per map, activity marks -> marks widened by one tile in every direction, and their count
 #pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
     for (int m = 0; m < maps; ++m) {
         unsigned char* raw = scratch_host + (size_t)m * 2 * tiles;
         unsigned char* wide = raw + tiles;
-        mark_active_tiles(heat_host + (size_t)m * H * W, H, W, tau, raw, TX);
+        mark_active_tiles(heat_host + (size_t)m * H * W, H, W, tau, raw, TX, band);
         long long count = 0;
         for (int ty = 0; ty < TY; ++ty)
             for (int tx = 0; tx < TX; ++tx) {
@@ -111,11 +147,8 @@ extern "C" int okp_host_pack_tiles_f32(const float* heat_host, int maps, int H, 
             const int y0 = ty * OKP_TILE_H, x0 = tx * OKP_TILE_W;
             float* dst = packed_host + at * OKP_TILE_FLOATS;
             if (y0 + OKP_TILE_H <= H && x0 + OKP_TILE_W <= W) {
-                for (int r = 0; r < OKP_TILE_H; ++r) {
-                    const float* src = map + (size_t)(y0 + r) * W + x0;
-                    _mm256_storeu_ps(dst + r * OKP_TILE_W, _mm256_loadu_ps(src));
-                    _mm256_storeu_ps(dst + r * OKP_TILE_W + 8, _mm256_loadu_ps(src + 8));
-                }
+                for (int r = 0; r < OKP_TILE_H; ++r)                 // 64 bytes per row: the compiler emits vector moves
+                    memcpy(dst + r * OKP_TILE_W, map + (size_t)(y0 + r) * W + x0, OKP_TILE_W * sizeof(float));
             } else {
                 for (int r = 0; r < OKP_TILE_H; ++r)
                     for (int c = 0; c < OKP_TILE_W; ++c)

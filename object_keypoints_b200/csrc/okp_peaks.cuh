@@ -24,6 +24,10 @@ struct OkpTileGeometry {
     int box_sum;         // 1: the score is the 5x5 box sum (the reference); 0: the map value itself
 };
 
+// torch's max_pool2d update rule (`if (val > max || isnan(val)) max = val`): a NaN anywhere in the window makes the
+// maximum NaN, so `x == hmax` (perception/models.py:55-58) fails for every pixel within reach of a NaN box sum.
+__device__ __forceinline__ float okp_pool_max(float m, float v) { return (v > m || v != v) ? v : m; }
+
 __device__ __forceinline__ void okp_centroid_from_smem(const float* raw, int pitch, int ry, int rx, int gy, int gx,
                                                        float* cx, float* cy, float* conf) {
     // raw(ry, rx) is the peak pixel inside the staged tile; (gy, gx) its image coordinates.
@@ -105,7 +109,7 @@ __device__ __forceinline__ void okp_generic_tile(const T* __restrict__ heat, con
             if (!(v > threshold)) continue;
             float m = v;
             for (int dy = 2 - r; dy <= 2 + r; ++dy)
-                for (int dx = 2 - r; dx <= 2 + r; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
+                for (int dx = 2 - r; dx <= 2 + r; ++dx) m = okp_pool_max(m, score[(py + dy) * SP + px + dx]);
             if (v == m) {
                 const int slot = atomicAdd(&s_count, 1);
                 if (slot < K) keys[slot] = gy * g.W + gx;
@@ -131,7 +135,7 @@ __device__ __forceinline__ void okp_generic_tile(const T* __restrict__ heat, con
                             if (v > threshold) {
                                 float m = v;
                                 for (int dy = 2 - r; dy <= 2 + r; ++dy)
-                                    for (int dx = 2 - r; dx <= 2 + r; ++dx) m = fmaxf(m, score[(py + dy) * SP + px + dx]);
+                                    for (int dx = 2 - r; dx <= 2 + r; ++dx) m = okp_pool_max(m, score[(py + dy) * SP + px + dx]);
                                 is_peak = (v == m);
                                 key = gy * g.W + gx;
                             }
@@ -239,12 +243,14 @@ __device__ __forceinline__ void okp_merge_map(const int32_t* tile_count, const O
     if (lane == 0) t.peak_count[m] = total;
 }
 
+// C: maps per frame. The generic path announces itself per frame (OKP_FLAG_GENERIC_PATH; the grouping keeps the bit).
 __global__ void __launch_bounds__(128)
 okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakRecord* __restrict__ tile_peaks,
-                       int maps, int tiles_per_map, int W, int K, OkpDecodeTables t) {
+                       int maps, int tiles_per_map, int W, int K, int C, OkpDecodeTables t) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= maps) return;
     okp_merge_map(tile_count, tile_peaks, warp, (size_t)warp * tiles_per_map, threadIdx.x & 31, tiles_per_map, W, K, t);
+    if ((threadIdx.x & 31) == 0 && t.flags && warp % C == 0) t.flags[warp / C] = OKP_FLAG_GENERIC_PATH;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,8 +16,17 @@
 //     table writes) WHILE the compute warps stream the next group. Hand-over is one mbarrier arrive per
 //     warp per group (cand_full / cand_free), not per row batch, so it costs nothing (the r01b design paid
 //     42 % of its issue slots for per-batch hand-over spins).
+//
+// FUSED = true (round 2; okp_decode_*): a group is a whole number of frames (M = F * C maps) and the epilogue warps go
+// on from the frame's sorted peak list -- still in shared memory -- to the grouping and the 3D lift (okp_group_frame,
+// okp_group.cuh) and to the frame's compact record (okp_records.cuh), so that ObjectKeypointPipeline.__call__
+// (perception/pipeline.py:182-200) is ONE streaming pass over the heatmaps: no second kernel that re-reads the peak
+// tables, no pack kernel for the multi-GPU gather. A frame one of whose maps overflowed (more than K peaks, negative /
+// NaN values, more candidates than slots) is marked OKP_GROUP_PENDING and finished by the fix-up launches
+// (okp_peaks_overflow_kernel, okp_group_kernel with only_pending).
 #pragma once
 #include "okp_peaks_strip.cuh"
+#include "okp_group.cuh"
 
 struct OkpStreamPlan {
     OkpStripPlan s;               // geometry, M, NS, stage layout (smem offsets below replace s.off_*)
@@ -25,6 +34,10 @@ struct OkpStreamPlan {
     int EW;                       // epilogue warps
     int off_pending[2], off_count[2];   // candidate lists and [n_pending[M], redo[M]] per buffer
     int off_peaks, off_items, off_misc, off_mbar;
+    int off_group;                // fused: F frame scratches of okp_group_smem_bytes() (okp_group.cuh)
+    int C;                        // maps per frame
+    int F;                        // fused: frames per group (M = F * C); 0 = peaks only
+    int lean;                     // OkpDecodeParams.lean_tables
     int smem_bytes;
     int threads;                  // compute warps + producer warp + epilogue warps
 };
@@ -33,10 +46,13 @@ __device__ __forceinline__ void okp_named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__(OKP_STRIP_MAX_THREADS, 1)
-okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ heat, OkpStreamPlan sp,
-                        float threshold, float thr_lo, OkpDecodeTables t) {
+template <typename T, bool FUSED>
+// 96 registers: two CTAs of 320 threads per SM (__maxnreg__ and __launch_bounds__ exclude each other; the launch uses at
+// most OKP_STRIP_MAX_THREADS = 640 threads, which 96 registers also allow)
+__global__ void __maxnreg__(96)
+okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ heat, const __grid_constant__ OkpStreamPlan sp,
+                        float threshold, float thr_lo, const __grid_constant__ OkpDecodeTables t,
+                        const __grid_constant__ OkpGroupArgs ga) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int RB = OKP_STRIP_RB;
     const OkpStripPlan& p = sp.s;
@@ -46,6 +62,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
     int* n_peaks = reinterpret_cast<int*>(smem + sp.off_misc);                                 // [M]
     int* n_items = n_peaks + p.M;                                                              // [1]
     int* cand_start = n_items + 1;                                                             // [M + 1] prefix of candidate counts
+    int* pend = cand_start + p.M + 1;                                                          // [M] fused: frame f is left to the fix-up launches
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.off_mbar);       // [NS] TMA landed
     uint64_t* done = full + OKP_STRIP_MAX_NS;                               // [NS] compute warps finished the batch
     uint64_t* cand_full = done + OKP_STRIP_MAX_NS;                          // [2] candidate buffer complete
@@ -61,6 +78,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
         for (int i = tid; i < 2 * p.M; i += blockDim.x) count[i] = 0;
     }
     for (int i = tid; i < p.M + 1; i += blockDim.x) n_peaks[i] = 0;
+    for (int i = tid; i < p.M; i += blockDim.x) pend[i] = 0;
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { okp_mbar_init(full + i, 1); okp_mbar_init(done + i, compute_warps); }
         for (int i = 0; i < 2; ++i) { okp_mbar_init(cand_full + i, compute_warps); okp_mbar_init(cand_free + i, sp.EW); }
@@ -81,8 +99,8 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
             for (int it = 0; it < my_groups; ++it) {
                 const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
                 for (int b = 0; b < p.nb; ++b, ++q) {
-                    if (q >= NS) {
-                        while (!okp_mbar_try_wait(done + stage, parity)) __nanosleep(64);
+                    if (q >= NS) {                            // every compute warp has left the stage (sleeps in hardware)
+                        while (!okp_mbar_try_wait_suspend(done + stage, parity)) {}
                     }
                     uint64_t* bar = full + stage;
                     unsigned char* dst = smem + (size_t)stage * p.stage_bytes;
@@ -142,7 +160,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
                 if ((tid & 31) == 0) okp_mbar_arrive(done + stage);
                 if (++stage == NS) { stage = 0; full_parity ^= 1u; }
             }
-            if (active && (sign >> 31)) count[p.M + mm] = 1;          // redo: benign race, every writer stores 1
+            if (active && (sign >> 30)) count[p.M + mm] = 1;          // redo (negative, NaN, Inf, >= 2.0): benign race, every writer stores 1
             __syncwarp();
             if ((tid & 31) == 0) okp_mbar_arrive(cand_full + buf);
         }
@@ -273,14 +291,28 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
             }
             okp_named_barrier(1, ethreads);
 
-            // C: raster order (rank by key), final tables, unused slots cleared
+            // C: raster order (rank by key), final tables, unused slots cleared (not with lean tables). Fused: the sorted
+            // rows also go into the frame's grouping scratch, which is what phase D works from.
+            const int K = p.K;
             for (int mm = 0; mm < p.M && first_map + mm < p.maps; ++mm) {
                 const int map = first_map + mm;
-                const int total = (redo[mm] || n_pending[mm] > p.PK) ? p.K + 1 : n_peaks[mm];
-                if (et == 0) t.peak_count[map] = total;
-                if (total > p.K) continue;                       // tables of this map are written by the overflow path
-                for (int slot = et; slot < p.K; slot += ethreads) {
-                    const size_t dst = (size_t)map * p.K + slot;
+                const int total = (redo[mm] || n_pending[mm] > p.PK) ? K + 1 : n_peaks[mm];
+                if (et == 0) {
+                    t.peak_count[map] = total;
+                    if (FUSED) {
+                        const int f = mm / sp.C, c = mm - f * sp.C;
+                        const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
+                                                                    ga.prm.max_objects);
+                        g.counts[c] = total < K ? total : K;
+                        if (c == 0) *g.flags = 0;
+                        if (total > K) pend[f] = 1;
+                    } else if (t.flags && map % sp.C == 0) {
+                        t.flags[map / sp.C] = 0;                 // a stale OKP_FLAG_GENERIC_PATH must not survive (okp_group_kernel keeps the bit)
+                    }
+                }
+                if (total > K || sp.lean) continue;              // tables of an overflowing map are written by the overflow path
+                for (int slot = et; slot < K; slot += ethreads) {
+                    const size_t dst = (size_t)map * K + slot;
                     t.peak_object[dst] = -1;
                     reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
                     if (slot >= total) {
@@ -297,33 +329,78 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
                 const int mm = lo, i = mm * p.PK + (idx - cand_start[mm]);
                 const OkpStripPeak pk = peaks[i];
                 if (pk.key < 0) continue;
-                if (redo[mm] || n_pending[mm] > p.PK || n_peaks[mm] > p.K) continue;
+                if (redo[mm] || n_pending[mm] > p.PK || n_peaks[mm] > K) continue;
                 const OkpStripPeak* mine = peaks + (size_t)mm * p.PK;
                 const int np = n_pending[mm];
                 int rank = 0;
                 for (int j = 0; j < np; ++j) { const int kj = mine[j].key; rank += (kj >= 0 && kj < pk.key); }
-                const size_t dst = (size_t)(first_map + mm) * p.K + rank;
+                const size_t dst = (size_t)(first_map + mm) * K + rank;
                 const int y = pk.key / W;
                 reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(y, pk.key - y * W);
                 t.peak_score[dst] = pk.score;
                 reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(pk.cx, pk.cy);
                 t.peak_conf[dst] = pk.conf;
+                if (sp.lean) {                                   // the row's assignment columns, which the clearing loop did not reset
+                    t.peak_object[dst] = -1;
+                    reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
+                }
+                if (FUSED) {
+                    const int f = mm / sp.C, c = mm - f * sp.C;
+                    const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
+                                                                ga.prm.max_objects);
+                    g.xy[2 * (c * K + rank)] = pk.cx; g.xy[2 * (c * K + rank) + 1] = pk.cy;
+                    g.conf[c * K + rank] = pk.conf;
+                }
             }
             okp_named_barrier(1, ethreads);
-            // hand the buffer back, cleared
+            // hand the candidate buffer back, cleared: the compute warps never wait for the grouping below
             for (int i = et; i < 2 * p.M; i += ethreads) n_pending[i] = 0;
             for (int i = et; i < p.M + 1; i += ethreads) n_peaks[i] = 0;
             okp_named_barrier(1, ethreads);
             if ((et & 31) == 0) okp_mbar_arrive(cand_free + buf);
+
+            // D (fused): grouping + 3D lift + compact record, one warp per frame, from the sorted peak list in shared memory
+            if (FUSED) {
+                const int first_frame = first_map / sp.C;
+                for (int f = et >> 5; f < sp.F && first_frame + f < ga.N; f += sp.EW) {
+                    const int n = first_frame + f;
+                    if (pend[f]) {                               // okp_group_kernel keeps OKP_FLAG_GENERIC_PATH: not from this call
+                        if ((et & 31) == 0) { t.n_objects[n] = OKP_GROUP_PENDING; t.flags[n] = 0; }
+                    } else {
+                        const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
+                                                                    ga.prm.max_objects);
+                        okp_group_frame<T>(n, et & 31, g, ga, t);
+                    }
+                }
+                okp_named_barrier(1, ethreads);                  // phase C of the next group rewrites the scratches
+                for (int i = et; i < p.M; i += ethreads) pend[i] = 0;
+            }
         }
     }
 }
 
-static inline bool okp_stream_plan(int maps, int H, int W, int K, int esize, OkpStreamPlan* out) {
+// C: maps per frame. group_frame_bytes > 0 asks for the fused form: groups of whole frames plus one grouping scratch
+// (group_frame_bytes each) per frame of a group; returns with sp.F == 0 when not even one frame fits a group (the caller
+// then runs the peak kernel and okp_group_kernel separately).
+static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esize, int group_frame_bytes, int lean,
+                                   OkpStreamPlan* out) {
     OkpStreamPlan sp;
     memset(&sp, 0, sizeof(sp));
     if (!okp_strip_plan(maps, H, W, K, esize, &sp.s)) return false;
     OkpStripPlan& p = sp.s;
+    sp.C = C;
+    sp.lean = lean;
+    const bool fused = group_frame_bytes > 0;
+    if (fused && p.M < C) return false;
+    auto resize = [&](int M) {
+        p.M = M;
+        p.threads = p.M * p.strips;
+        p.IC = p.M * 64;
+        p.half_bytes = p.M * OKP_STRIP_RB * p.BW * esize;
+        p.half_stride = okp_round_up_int(p.half_bytes, 128);
+        p.stage_bytes = p.halves * p.half_stride;
+    };
+    if (fused) resize(p.M / C * C);
     sp.EW = okp_env_int("OKP_STREAM_EPILOGUE_WARPS", 0, 4, 0);    // 0: decided below, once M is known
     // the second candidate buffer costs PK * 8 bytes per map: give it back from the per-CTA budget by re-planning M
     const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;
@@ -334,18 +411,17 @@ static inline bool okp_stream_plan(int maps, int H, int W, int K, int esize, Okp
         sp.off_peaks = off; off += p.M * p.PK * (int)sizeof(OkpStripPeak);
         sp.off_items = off; off += p.IC * 4;
         for (int b = 0; b < 2; ++b) { sp.off_count[b] = off; off += 2 * p.M * 4; }
-        sp.off_misc = off; off += (2 * p.M + 2) * 4;
-        off = okp_round_up_int(off, 8);
+        sp.off_misc = off; off += (3 * p.M + 2) * 4;
+        off = okp_round_up_int(off, 16);
+        sp.off_group = off;
+        if (fused) off += (p.M / C) * group_frame_bytes;
         sp.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 4) * 8;
         sp.smem_bytes = off;
-        if ((off <= budget && p.threads <= compute_limit) || p.M == 1) break;
-        --p.M;                                             // shrink the group until it fits
-        p.threads = p.M * p.strips;
-        p.IC = p.M * 64;
-        p.half_bytes = p.M * OKP_STRIP_RB * p.BW * esize;
-        p.half_stride = okp_round_up_int(p.half_bytes, 128);
-        p.stage_bytes = p.halves * p.half_stride;
+        const int step = fused ? C : 1;
+        if ((off <= budget && p.threads <= compute_limit) || p.M == step) break;
+        resize(p.M - step);                                // shrink the group until it fits
     }
+    sp.F = fused ? p.M / C : 0;
     if (sp.smem_bytes > 224 * 1024 || p.threads > compute_limit) return false;
     // two epilogue warps where they fit beside the compute warps in 320 threads (two CTAs per SM at 96 registers), else
     // one: small maps (64x64: 14 row batches per group) finish a group every few microseconds and one warp cannot keep
@@ -357,9 +433,10 @@ static inline bool okp_stream_plan(int maps, int H, int W, int K, int esize, Okp
     return true;
 }
 
+// ga: grouping arguments (fused form, sp.F > 0) or NULL (peaks only).
 template <typename T>
 static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, float threshold,
-                                    const OkpDecodeTables& tables, cudaStream_t stream) {
+                                    const OkpDecodeTables& tables, const OkpGroupArgs* ga, cudaStream_t stream) {
     const OkpStripPlan& p = sp.s;
     OkpEncodeTiledFn encode = okp_encode_tiled_fn();
     if (!encode) return OKP_E_CUDA;
@@ -373,7 +450,10 @@ static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, floa
     const CUresult r = encode(&tmap, dtype, 3, (void*)heat, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return OKP_E_CUDA;
-    auto kernel = okp_peaks_stream_kernel<T>;
+    const bool fused = ga != nullptr && sp.F > 0;
+    auto kernel = fused ? okp_peaks_stream_kernel<T, true> : okp_peaks_stream_kernel<T, false>;
+    OkpGroupArgs none;
+    if (!fused) memset(&none, 0, sizeof(none));
     OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.smem_bytes));
     int per_sm = 0;
     OKP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, sp.threads, sp.smem_bytes));
@@ -384,7 +464,7 @@ static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, floa
     long long grid = (long long)per_sm * sms;               // persistent: every CTA resident, groups dealt round-robin
     if (grid > sp.groups) grid = sp.groups;
     const float thr_lo = threshold - OKP_STRIP_THRESHOLD_SLACK * fabsf(threshold);
-    kernel<<<(unsigned)grid, sp.threads, sp.smem_bytes, stream>>>(tmap, heat, sp, threshold, thr_lo, tables);
+    kernel<<<(unsigned)grid, sp.threads, sp.smem_bytes, stream>>>(tmap, heat, sp, threshold, thr_lo, tables, fused ? *ga : none);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

@@ -21,9 +21,11 @@
 //     loads from L2, raster-order __fadd_rn), compares it with the threshold, and with the exact S of
 //     every masked neighbour (normally none). The peak set, the scores and the raster order are
 //     therefore bit-identical to the exact kernel's; ties keep every tied pixel like `x == hmax`;
-//   * maps holding a negative value (sign bit seen by a 2-LOP3-per-row check) void the bound: they
-//     are handed to the exact generic kernels through the overflow path, like maps with more than K
-//     peaks ("the first K in raster order").
+//   * maps holding a negative value void the bound, and so do NaN / Inf (torch's max_pool2d propagates NaN:
+//     no pixel whose window holds a NaN box sum is a peak). The stream ORs the bits of every value
+//     (2 LOP3 per row); bit 31 = a negative value, bit 30 = a value >= 2.0, an Inf or a NaN (probabilities
+//     never set it). Such maps are handed to the exact generic kernels through the overflow path, like maps
+//     with more than K peaks ("the first K in raster order").
 //
 // Data movement: heatmap rows arrive in shared memory by TMA (cp.async.bulk.tensor, one elected
 // thread of a producer warp); the tensor map's out-of-bounds zero fill IS conv2d's zero padding.
@@ -95,12 +97,25 @@ __device__ __forceinline__ bool okp_mbar_try_wait(uint64_t* bar, uint32_t parity
         "}\n" : "=r"(ok) : "r"(okp_smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the hint (in ns-scale
+// ticks) runs out, instead of coming back after the short default time-out and spinning through the instruction issue
+// slots of the warps that do the work (the producer's wait loop was 15 % of K1's executed instructions, r01v).
+__device__ __forceinline__ bool okp_mbar_try_wait_suspend(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(okp_smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    return ok != 0;
+}
 // Waits for the phase with the given parity. A wait that lasts longer than ~2 s of SM clocks can only
 // be a protocol bug: trap (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void okp_mbar_wait(uint64_t* bar, uint32_t parity) {
     if (okp_mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!okp_mbar_try_wait(bar, parity)) {
+    while (!okp_mbar_try_wait_suspend(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
@@ -266,237 +281,24 @@ __device__ __forceinline__ void okp_strip_batch(const unsigned char* raw, int ro
     okp_strip_step<4, EDGE>(a0, a1, pr, hp, sv, sign, y0 + 4, L);
 }
 
-// Roles. Warps [0, CW) are compute warps (thread = one strip of one map, packed densely); the only thing
-// they ever wait for is TMA data (full[]); after RB rows they arrive on done[]. The last warp is the
-// producer: one lane keeps NS batches of rows in flight.
-template <typename T>
-__global__ void __launch_bounds__(OKP_STRIP_MAX_THREADS, 1)
-okp_peaks_strip_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ heat, OkpStripPlan p,
-                       float threshold, float thr_lo, OkpDecodeTables t) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int RB = OKP_STRIP_RB;
-    const int NS = p.NS;
-    OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + p.off_pending);   // [M][PK]
-    OkpStripPeak* peaks = reinterpret_cast<OkpStripPeak*>(smem + p.off_peaks);                 // [M][PK]
-    uint32_t* items = reinterpret_cast<uint32_t*>(smem + p.off_items);                         // [IC] (candidate << 5) | neighbour
-    int* n_pending = reinterpret_cast<int*>(smem + p.off_count);             // [M] candidates
-    int* n_peaks = n_pending + p.M;                                          // [M] confirmed peaks
-    int* redo = n_peaks + p.M;                                               // [M] map goes to the exact generic path
-    int* n_items = redo + p.M;                                               // [1]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_mbar);         // [NS] TMA landed
-    uint64_t* done = full + OKP_STRIP_MAX_NS;                                // [NS] compute warps finished the batch
-
-    const int tid = threadIdx.x;
-    const int H = p.H, W = p.W;
-    const int first_map = blockIdx.x * p.M;
-    const int compute_warps = (p.threads + 31) >> 5;
-
-    for (int i = tid; i < 3 * p.M + 1; i += blockDim.x) n_pending[i] = 0;
-    if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { okp_mbar_init(full + i, 1); okp_mbar_init(done + i, compute_warps); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
-    if ((tid >> 5) >= compute_warps) {
-        if ((tid & 31) == 0) {
-            const CUtensorMap* tmap_ptr = &tmap;              // address of the __grid_constant__ parameter itself
-            int stage = 0;
-            uint32_t parity = 0;
-            for (int b = 0; b < p.nb; ++b) {
-                if (b >= NS) {                                // every compute warp has left the stage
-                    while (!okp_mbar_try_wait(done + stage, parity)) __nanosleep(64);
-                }
-                uint64_t* bar = full + stage;
-                unsigned char* dst = smem + (size_t)stage * p.stage_bytes;
-                okp_mbar_expect_tx(bar, (uint32_t)(p.halves * p.half_bytes));
-                okp_tma_load_3d(dst, tmap_ptr, -4 - p.lead[0], b * RB - 2, first_map, bar);
-                if (p.halves == 2)
-                    okp_tma_load_3d(dst + p.half_stride, tmap_ptr, 4 * p.half_strips - 4 - p.lead[1], b * RB - 2, first_map, bar);
-                if (++stage == NS) { stage = 0; if (b >= NS) parity ^= 1u; }
-            }
-        }
-    } else {
-        const bool active = tid < p.threads;              // the last compute warp may be partly idle
-        const int ct = active ? tid : p.threads - 1;      // idle lanes shadow a real strip (they never emit)
-        const int mm = ct / p.strips;                     // map slot inside the CTA
-        const int s = ct - mm * p.strips;                 // strip inside the map
-        const int half = s >= p.half_strips ? 1 : 0;
-        OkpStripLane L;
-        L.H = H; L.W = W; L.thr_lo = thr_lo; L.PK = p.PK;
-        L.xs = 4 * s;
-        L.vmask = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) L.vmask |= (L.xs + c - 2 >= 0 && L.xs + c - 2 < W) ? (1u << c) : 0u;
-        if (!active) L.vmask = 0;
-        if (active && (tid & 31) > 0 && s > 0) L.vmask |= 16u;                                       // lane - 1 holds strip s - 1 of this map
-        if (active && (tid & 31) < 31 && s + 1 < p.strips && tid + 1 < p.threads) L.vmask |= 32u;   // lane + 1 holds strip s + 1
-        L.pending = pending + (size_t)mm * p.PK;
-        L.n_pending = n_pending + mm;
-        // this thread's window row inside a stage: box [M][RB][BW], first column lead + 4 * (s - half * half_strips)
-        const int thread_raw = half * p.half_stride +
-                               (mm * RB * p.BW + p.lead[half] + 4 * (s - half * p.half_strips)) * (int)sizeof(T);
-        const int row_pitch = p.BW * (int)sizeof(T);
-
-        float pr[5][4], hp[4], sv[5][4];
-        uint32_t sign = 0;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { pr[i][j] = 0.0f; sv[i][j] = -INFINITY; }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hp[j] = 0.0f;
-
-        int stage = 0;
-        uint32_t full_parity = 0;
-        for (int b = 0; b < p.nb; ++b) {
-            okp_mbar_wait(full + stage, full_parity);
-            const unsigned char* raw = smem + (size_t)stage * p.stage_bytes + thread_raw;
-            const int y0 = b * RB - 4;                    // new row of step i is y0 + i + 2, tested row y0 + i - 2
-            if (b >= 2 && y0 + 4 < H)                     // rows y0 - 4 .. y0 + 4 all exist
-                okp_strip_batch<false, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
-            else
-                okp_strip_batch<true, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
-            __syncwarp();
-            if ((tid & 31) == 0) okp_mbar_arrive(done + stage);
-            if (++stage == NS) { stage = 0; full_parity ^= 1u; }
-        }
-        if (active && (sign >> 31)) redo[mm] = 1;         // benign race: every writer stores 1
-    }
-    __syncthreads();
-
-    // ---- epilogue A: every candidate's exact box sum (the reference's raster-order adds), one thread each so
-    // that all loads of the CTA are in flight together; a candidate above the threshold gets its centroid
-    // (pipeline.py:46-62) from the same 25 values and queues its undecided neighbours ----
-    const int slots = p.M * p.PK;
-    for (int i = tid; i < slots; i += blockDim.x) {
-        const int mm = i / p.PK, j = i - mm * p.PK;
-        OkpStripPeak pk;
-        pk.key = -1; pk.score = 0.0f; pk.cx = 0.0f; pk.cy = 0.0f; pk.conf = 0.0f;
-        if (first_map + mm < p.maps && j < n_pending[mm]) {
-            const OkpStripCandidate cd = pending[i];
-            const int y = cd.key / W, x = cd.key - y * W;
-            const T* src = heat + (size_t)(first_map + mm) * H * W;
-            float q[25];
-#pragma unroll
-            for (int k = 0; k < 25; ++k) {
-                const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;   // +0 outside: conv2d's zero padding
-            }
-            float sum = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 25; ++k) sum = __fadd_rn(sum, q[k]);
-            if (sum > threshold) {
-                float sy = 0.0f, sx = 0.0f, sp = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 25; ++k) {
-                    const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                    const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                    if (in) {                                     // border-clipped window, raster order
-                        sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
-                        sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
-                        sp = __fadd_rn(sp, q[k]);
-                    }
-                }
-                pk.key = cd.key;
-                pk.score = sum;
-                pk.cx = __fdiv_rn(sx, sp);
-                pk.cy = __fdiv_rn(sy, sp);
-                pk.conf = sp;
-                uint32_t ties = cd.ties;                          // keep the neighbours that exist
-                ties &= (y >= 2 ? 0x1Fu : 0u) | (y >= 1 ? 0x3E0u : 0u) | 0x6C00u | (y + 1 < H ? 0xF8000u : 0u) | (y + 2 < H ? 0x1F00000u : 0u);
-                ties &= (x >= 2 ? 0x108421u : 0u) | (x >= 1 ? 0x210842u : 0u) | 0x421084u | (x + 1 < W ? 0x842108u : 0u) | (x + 2 < W ? 0x1084210u : 0u);
-                if (ties) {
-                    const int at = atomicAdd(n_items, __popc(ties));
-                    if (at + __popc(ties) > p.IC) {
-                        redo[mm] = 1;                             // more undecided neighbours than item slots (plateaus)
-                        for (int n = at; n < p.IC; ++n) items[n] = 0xFFFFFFFFu;
-                    } else {
-                        int n = at;
-                        while (ties) {
-                            const int k = __ffs(ties) - 1;
-                            ties &= ties - 1;
-                            items[n++] = ((uint32_t)i << 5) | (uint32_t)k;
-                        }
-                    }
-                }
-            }
-        }
-        peaks[i] = pk;
-    }
-    __syncthreads();
-
-    // ---- epilogue B: one thread per undecided neighbour: its exact box sum against the candidate's.
-    // A candidate with a strictly larger neighbour is not a peak (`x == hmax` keeps exact ties). ----
-    {
-        const int total_items = okp_min(*n_items, p.IC);
-        for (int it = tid; it < total_items; it += blockDim.x) {
-            const uint32_t item = items[it];
-            if (item == 0xFFFFFFFFu) continue;                   // slot of a map that is redone anyway
-            const int i = (int)(item >> 5), k = (int)(item & 31u);
-            const int mm = i / p.PK;
-            const int key = pending[i].key;
-            const int y = key / W, x = key - y * W;
-            const T* src = heat + (size_t)(first_map + mm) * H * W;
-            if (okp_exact_box_sum<T>(src, H, W, y + k / 5 - 2, x + k % 5 - 2) > peaks[i].score) peaks[i].key = -1;
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < slots; i += blockDim.x)
-        if (peaks[i].key >= 0) atomicAdd(n_peaks + i / p.PK, 1);
-    __syncthreads();
-
-    // ---- epilogue C: raster order (rank by key), final tables, unused slots cleared ----
-    for (int i = tid; i < p.M * p.K; i += blockDim.x) {
-        const int mm = i / p.K, slot = i - mm * p.K;
-        const int map = first_map + mm;
-        if (map >= p.maps) continue;
-        // a map with negative values, or with more candidates / undecided neighbours than slots, is reported
-        // as overflowing, which hands it to the exact generic path (so is a map with more than K peaks)
-        const int total = (redo[mm] || n_pending[mm] > p.PK) ? p.K + 1 : n_peaks[mm];
-        if (slot == 0) t.peak_count[map] = total;
-        if (total > p.K) continue;                           // tables of this map are written by the overflow path
-        const size_t dst = (size_t)map * p.K + slot;
-        t.peak_object[dst] = -1;
-        t.peak_vote[2 * dst] = 0.0; t.peak_vote[2 * dst + 1] = 0.0;
-        if (slot >= total) {
-            t.peak_yx[2 * dst] = -1; t.peak_yx[2 * dst + 1] = -1;
-            t.peak_score[dst] = 0.0f;
-            t.peak_xy[2 * dst] = 0.0f; t.peak_xy[2 * dst + 1] = 0.0f;
-            t.peak_conf[dst] = 0.0f;
-        }
-    }
-    for (int i = tid; i < slots; i += blockDim.x) {
-        const OkpStripPeak pk = peaks[i];
-        if (pk.key < 0) continue;
-        const int mm = i / p.PK;
-        if (redo[mm] || n_pending[mm] > p.PK || n_peaks[mm] > p.K) continue;
-        const OkpStripPeak* mine = peaks + (size_t)mm * p.PK;
-        const int np = n_pending[mm];
-        int rank = 0;
-        for (int j = 0; j < np; ++j) { const int kj = mine[j].key; rank += (kj >= 0 && kj < pk.key); }
-        const size_t dst = (size_t)(first_map + mm) * p.K + rank;
-        const int y = pk.key / W;
-        t.peak_yx[2 * dst] = y; t.peak_yx[2 * dst + 1] = pk.key - y * W;
-        t.peak_score[dst] = pk.score;
-        t.peak_xy[2 * dst] = pk.cx; t.peak_xy[2 * dst + 1] = pk.cy;
-        t.peak_conf[dst] = pk.conf;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side: plan + tensor map + launch
 // ---------------------------------------------------------------------------------------------
 static inline int okp_round_up_int(int v, int m) { return (v + m - 1) / m * m; }
 
-static inline int okp_env_int(const char* name, int lo, int hi, int fallback) {   // tuning aids (tools/sweep_k1.py)
+// Launch-plan constants. The library keeps no global state and reads no environment: the values below are the shipped
+// ones. A build with -DOKP_TUNING_KNOBS (python -c "from object_keypoints_b200 import _lib; _lib.build(tuning=True)";
+// tools/sweep_k1.py) lets OKP_* environment variables override them for parameter sweeps.
+static inline int okp_env_int(const char* name, int lo, int hi, int fallback) {
+#ifdef OKP_TUNING_KNOBS
     const char* e = getenv(name);
     if (!e) return fallback;
     const int v = atoi(e);
     return v >= lo && v <= hi ? v : fallback;
+#else
+    (void)name; (void)lo; (void)hi;
+    return fallback;
+#endif
 }
 
 static inline bool okp_strip_plan(int maps, int H, int W, int K, int esize, OkpStripPlan* out) {
@@ -566,28 +368,4 @@ static inline OkpEncodeTiledFn okp_encode_tiled_fn() {
         fn = (OkpEncodeTiledFn)ptr;
     }
     return fn;
-}
-
-template <typename T>
-static inline int okp_strip_launch(const T* heat, const OkpStripPlan& p, float threshold,
-                                   const OkpDecodeTables& tables, cudaStream_t stream) {
-    OkpEncodeTiledFn encode = okp_encode_tiled_fn();
-    if (!encode) return OKP_E_CUDA;
-    if (((uintptr_t)heat & 15u) != 0) return OKP_E_UNSUPPORTED;
-    CUtensorMap tmap;
-    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.maps};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(T), (cuuint64_t)p.W * p.H * sizeof(T)};
-    const cuuint32_t box[3] = {(cuuint32_t)p.BW, (cuuint32_t)OKP_STRIP_RB, (cuuint32_t)p.M};
-    const cuuint32_t elem[3] = {1, 1, 1};
-    const CUtensorMapDataType dtype = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    const CUresult r = encode(&tmap, dtype, 3, (void*)heat, dims, strides, box, elem,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return OKP_E_CUDA;
-    OKP_CUDA_CHECK(cudaFuncSetAttribute(okp_peaks_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    const int block = (p.threads + 31) / 32 * 32 + 32;     // compute warps + the producer warp
-    const float thr_lo = threshold - OKP_STRIP_THRESHOLD_SLACK * fabsf(threshold);
-    okp_peaks_strip_kernel<T><<<p.grid, block, p.smem_bytes, stream>>>(tmap, heat, p, threshold, thr_lo, tables);
-    OKP_CUDA_CHECK(cudaGetLastError());
-    return OKP_OK;
 }

@@ -53,7 +53,13 @@ def _as_device_f32(x, device):
         x = x.float()
     if x.device != device:
         x = x.to(device, non_blocking=True)
-    return x.contiguous()
+    return _aligned(x.contiguous())
+
+
+def _aligned(x):
+    """The TMA kernel needs a 16-byte aligned base (okp.h: OKP_E_UNSUPPORTED otherwise): a view that starts in the
+    middle of an allocation (``batch[1:]`` of a map with an odd element count) is re-materialised."""
+    return x.clone() if x.data_ptr() % 16 else x
 
 
 def _as_device_map(x, device):
@@ -62,7 +68,7 @@ def _as_device_map(x, device):
     if isinstance(x, torch.Tensor) and x.dtype == torch.bfloat16:
         if x.device != device:
             x = x.to(device, non_blocking=True)
-        return x.contiguous(), 'bf16'
+        return _aligned(x.contiguous()), 'bf16'
     return _as_device_f32(x, device), 'f32'
 
 
@@ -105,13 +111,13 @@ class KeypointDecoder:
 
     def __init__(self, keypoint_config, prediction_size, camera=None, device=None, max_peaks=32, max_objects=16,
                  max_votes=16, threshold=0.5, outlier_distance=20.0, compat_clip_bug=True, nms_size=5, box_sum=True,
-                 top_k=0):
+                 top_k=0, lean_tables=False):
         self.cfg = _abi.check_keypoint_config(keypoint_config)
         self.C = 1 + len(self.cfg)
         self.H, self.W = int(prediction_size[0]), int(prediction_size[1])
         self.params = _abi.make_params(threshold=threshold, outlier_distance=outlier_distance, max_peaks=max_peaks,
                                        max_objects=max_objects, max_votes=max_votes, compat_clip_bug=compat_clip_bug,
-                                       nms_size=nms_size, box_sum=box_sum, top_k=top_k)
+                                       nms_size=nms_size, box_sum=box_sum, top_k=top_k, lean_tables=lean_tables)
         self.device = _device(device)
         self._cfg_array = (ctypes.c_int32 * max(len(self.cfg), 1))(*self.cfg)
         self._camera = None
@@ -156,9 +162,15 @@ class KeypointDecoder:
         _lib.check(rc, f'okp_extract_peaks_{kind}')
         return tables
 
-    def decode_batch(self, heat, depth, centers, tables=None, stream=None):
+    def record_bytes(self):
+        """Bytes of one compact per-frame record (okp_decode_emit_*, include/okp.h)."""
+        return int(self._lib.okp_record_bytes(self.params.max_objects, self.C, self._cfg_array))
+
+    def decode_batch(self, heat, depth, centers, tables=None, stream=None, records=None):
         """heat [N,C,H,W], depth [N,C,H,W], centers [N,C-1,2,H,W] (float32 or bfloat16; CUDA tensors
-        are used in place, host arrays are copied) -> DecodeTables on the device. No synchronisation."""
+        are used in place, host arrays are copied) -> DecodeTables on the device. No synchronisation.
+        records: an ``_abi.OkpRecordSink`` (sharding.RecordExchange.begin()): the kernel also writes every frame's
+        compact record into the sink's buffers while it decodes (the multi-GPU gather)."""
         heat, heat_kind = _as_device_map(heat, self.device)
         self._check(heat)
         depth, depth_kind = _as_device_map(depth, self.device)
@@ -173,11 +185,14 @@ class KeypointDecoder:
         tables = self.tables(N) if tables is None else tables
         ws = self._workspace_for(N)
         cam = ctypes.byref(self._camera) if self._camera is not None else None
+        if heat_kind != depth_kind and records is not None:
+            raise ValueError("records need heatmaps and depth / centre maps of one element type")
         if heat_kind == depth_kind:
-            rc = getattr(self._lib, f'okp_decode_{heat_kind}')(
+            rc = getattr(self._lib, f'okp_decode_emit_{heat_kind}')(
                 heat.data_ptr(), depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array, cam,
-                ctypes.byref(self.params), ctypes.byref(tables.struct), ws.data_ptr(), ws.numel(), _stream_handle(stream))
-            _lib.check(rc, f'okp_decode_{heat_kind}')
+                ctypes.byref(self.params), ctypes.byref(tables.struct), ws.data_ptr(), ws.numel(),
+                ctypes.byref(records) if records is not None else None, _stream_handle(stream))
+            _lib.check(rc, f'okp_decode_emit_{heat_kind}')
         else:                                                # e.g. bf16 heatmaps with float32 depth / centre maps
             rc = getattr(self._lib, f'okp_extract_peaks_{heat_kind}')(
                 heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params), ctypes.byref(tables.struct),
@@ -201,21 +216,44 @@ class KeypointDecoder:
         return alias.value
 
     SPARSE_CAPACITY = 0.5          # fall back to the dense copy when more than this share of a chunk's tiles is marked
-    SPARSE_MIN_THREADS = 8         # sparse='auto' needs this many host threads per rank to beat the plain copy
+    SPARSE_MIN_THREADS = 2         # sparse='auto' runs the host pass from this many host threads per rank on: the scheduler
+                                   # below hands it a chunk only when it will finish before the copy engine could have moved
+                                   # the remaining chunks densely, so a slow pass (few threads) just takes fewer chunks
 
     def _sparse_ok(self, heat, sparse):
         """The sparse transfer holds for the reference's configuration only (csrc/okp_sparse.cuh)."""
         if sparse in (False, 'off', None):
             return False
-        # the pass reads every heatmap byte from host memory: it only pays while PCIe, not host DRAM, is the limit, i.e.
-        # with enough host threads for this rank (8 threads pack at about the rate of one Gen5 x16 link; with 4 or 8
-        # ranks per node the DMA engines alone saturate host memory, measured 262 k frames/s on 8 GPUs)
+        # the pass reads every heatmap byte from host memory: it pays while PCIe, not host DRAM, is the limit (8 threads pack
+        # at about the rate of one Gen5 x16 link). Round 1 switched it off below 8 threads per rank, which left 4- and 8-rank
+        # runs on the dense copy alone; now the chunk scheduler decides (see SPARSE_MIN_THREADS)
         if sparse == 'auto' and _host_threads() < self.SPARSE_MIN_THREADS:
             return False
         return (self.params.nms_size == 5 and self.params.box_sum == 1 and self.params.threshold > 0.0 and
                 heat.device.type == 'cpu' and heat.dtype == torch.float32 and heat.is_contiguous())
 
-    def decode_host_batch(self, heat, depth, centers, chunk_frames=128, sparse='auto'):
+    HOST_STAGING_SETS = 2          # staging sets (device chunk buffers + pinned packing buffers) kept, least recently used out
+
+    def _check_host_inputs(self, heat, depth, centers):
+        """Shapes / dtypes of decode_host_batch's inputs: the host pass and the in-place gathers work on raw pointers, so a
+        wrong shape would be an out-of-bounds read, not an exception."""
+        for name, tensor in (('heat', heat), ('depth', depth), ('centers', centers)):
+            if not isinstance(tensor, torch.Tensor) or tensor.device.type != 'cpu' or tensor.dtype != torch.float32:
+                raise ValueError(f"{name} must be a float32 CPU tensor")
+        self._check(heat)
+        N = int(heat.shape[0])
+        if tuple(depth.shape) != tuple(heat.shape):
+            raise ValueError(f"depth must have the heatmap's shape {tuple(heat.shape)}, got {tuple(depth.shape)}")
+        if tuple(centers.shape) != (N, self.C - 1, 2, self.H, self.W):
+            raise ValueError(f"centers must be [{N},{self.C - 1},2,{self.H},{self.W}], got {tuple(centers.shape)}")
+
+    def host_result(self, N, like=None):
+        """Pinned CPU tensors for decode_host_batch's result (pass them back as ``out=`` to reuse them)."""
+        like = like if like is not None else DecodeTables(1, self.C, self.cfg, self.params, self.device)
+        return {name: torch.empty((N,) + tuple(like[name].shape[1:]), dtype=like[name].dtype).pin_memory()
+                for name in self.HOST_RESULT_TABLES}
+
+    def decode_host_batch(self, heat, depth, centers, chunk_frames=128, sparse='auto', out=None):
         """End-to-end form for HOST inputs, the shape the reference's caller has (CPU tensors out of
         InferenceComponent, pipeline.py:24-28). The batch is cut into chunks that are pipelined: while chunk i is
         decoded, chunk i+1 crosses PCIe and chunk i+2 is prepared on the host.
@@ -231,14 +269,17 @@ class KeypointDecoder:
         dense copies. Depth and centre maps are only gathered from (3 values per spoke peak): when they live in
         pinned host memory the kernels read them in place over PCIe; pageable tensors are copied like dense
         heatmaps. The object tables of every chunk are copied back into pinned host tensors.
-        Returns a dict of CPU tensors (synchronised)."""
+        Returns a dict of CPU tensors (synchronised): freshly allocated for every call, or ``out`` (a dict from an earlier
+        call or from ``host_result``) filled in place."""
+        self._check_host_inputs(heat, depth, centers)
+        heat, depth, centers = heat.contiguous(), depth.contiguous(), centers.contiguous()
         N = int(heat.shape[0])
         chunk = max(1, min(chunk_frames, N))
         depth_alias = self._host_alias(depth)
         centers_alias = self._host_alias(centers)
         in_place = depth_alias is not None and centers_alias is not None
         use_sparse = self._sparse_ok(heat, sparse)
-        key = ('host', N, chunk, in_place, use_sparse)
+        key = ('host', chunk, in_place, use_sparse)
         tiles_per_map = ((self.H + 3) // 4) * ((self.W + 15) // 16)
         capacity = max(1, int(self.SPARSE_CAPACITY * chunk * self.C * tiles_per_map))
         if key not in self._tables:
@@ -261,11 +302,20 @@ class KeypointDecoder:
                     slot['scratch'] = np.zeros(self._lib.okp_host_pack_scratch_bytes(maps, self.H, self.W), np.uint8)
                     slot['offsets'] = np.zeros(maps + 1, np.int64)
                 staging.append(slot)
-            like = staging[0]['tables']
-            result = {name: torch.empty((N,) + tuple(like[name].shape[1:]), dtype=like[name].dtype).pin_memory()
-                      for name in self.HOST_RESULT_TABLES}
-            self._tables[key] = (staging, result, torch.cuda.Stream(device=self.device))
-        staging, result, copy_stream = self._tables[key]
+            held = [k for k in self._tables if isinstance(k, tuple) and k[0] == 'host']
+            while len(held) >= self.HOST_STAGING_SETS:            # bounded: callers with varying chunk sizes do not pile up HBM
+                del self._tables[held.pop(0)]
+            self._tables[key] = (staging, torch.cuda.Stream(device=self.device))
+        else:
+            self._tables[key] = self._tables.pop(key)              # most recently used last
+        staging, copy_stream = self._tables[key]
+        if out is None:
+            result = self.host_result(N, staging[0]['tables'])
+        else:
+            result = out
+            for name in self.HOST_RESULT_TABLES:
+                if name not in result or result[name].shape[0] != N or not result[name].is_pinned():
+                    raise ValueError(f"out['{name}'] must be a pinned CPU tensor with {N} rows (see host_result)")
         compute = torch.cuda.current_stream()
         self._workspace_for(chunk)
         depth_frame = self.C * self.H * self.W * 4
@@ -273,6 +323,8 @@ class KeypointDecoder:
         cam = ctypes.byref(self._camera) if self._camera is not None else None
         self.host_bytes_copied = 0
         self.host_chunks_sparse = 0
+        self.host_pack_threads = _host_threads() if use_sparse else 0
+        marked_tiles = [0, 0]                              # tiles marked / tiles looked at by the host pass
         starts = list(range(0, N, chunk))
 
         def pack(index, slot):
@@ -289,6 +341,8 @@ class KeypointDecoder:
                 ctypes.c_void_p(slot['packed_host'].data_ptr()), capacity, ctypes.byref(count), _host_threads())
             _lib.check(rc, 'okp_host_pack_tiles_f32')
             self._pack_seconds = time.perf_counter() - began
+            marked_tiles[0] += int(count.value)
+            marked_tiles[1] += n * self.C * tiles_per_map
             return int(count.value)
 
         def enqueue(index, slot, n_tiles):
@@ -384,6 +438,7 @@ class KeypointDecoder:
             if packing is not None:                                # an exception above: do not leave a pass running
                 packing[0].cancel() or packing[0].exception()
         compute.synchronize()
+        self.host_marked_fraction = marked_tiles[0] / marked_tiles[1] if marked_tiles[1] else None
         return result
 
     def group_objects(self, depth, centers, tables, stream=None):

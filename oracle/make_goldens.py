@@ -238,6 +238,39 @@ def adversarial_frames(size=(64, 64)):
     return names, cfg, heat, depth, centers
 
 
+def nan_frames():
+    """Valve frames of the clean generator with NaN pixels planted around a blob: torch's max_pool2d propagates NaN, so a
+    NaN pixel up to 4 px from a peak (its box sum reaches the peak's 5x5 NMS window) suppresses that peak although the
+    peak's own box sum is finite; a NaN pixel far from every blob changes nothing."""
+    cfg = [1, 3]
+    batch = synthetic.make_batch(6, cfg, (64, 64), seed=1010, objects=(1, 2))
+    heat, depth, centers = batch.heat.copy(), batch.depth.copy(), batch.centers.copy()
+    names = []
+    for f, (offset, where) in enumerate([((4, 0), 'centre'), ((0, 3), 'spoke'), ((1, 1), 'spoke'), ((0, 5), 'centre'),
+                                         (None, 'far'), ((-3, -3), 'centre')]):
+        scene = batch.scenes[f]
+        if where == 'centre':
+            x, y = scene.centers[0]
+            c = 0
+        elif where == 'spoke':
+            x, y = scene.spokes[1][0, 0]
+            c = 2
+        else:
+            c, best = 0, None
+            for yy in range(4, 60, 4):                     # the pixel farthest from every centre
+                for xx in range(4, 60, 4):
+                    d = min(np.hypot(xx - cx, yy - cy) for cx, cy in scene.centers)
+                    if best is None or d > best[0]:
+                        best = (d, xx, yy)
+            x, y, offset = best[1], best[2], (0, 0)
+            assert best[0] > 9.0
+        px, py = int(round(x)) + offset[0], int(round(y)) + offset[1]
+        px, py = min(max(px, 0), 63), min(max(py, 0), 63)
+        heat[f, c, py, px] = np.nan
+        names.append(f"{where}{offset}")
+    return names, cfg, heat, depth, centers
+
+
 def test_pipeline_frames(ref, camera_utils, video):
     """The synthetic-heatmap recipe of test/test_pipeline.py:39-57,97-102 (valve, 180x320)."""
     import cv2
@@ -599,6 +632,13 @@ def main():
     if '--only-producer' in sys.argv:
         save('producer_valve.npz', **producer_case())
         return
+    if '--only-nan' in sys.argv:
+        names, cfg, heat, depth, centers = nan_frames()
+        camera = reference_camera(camera_utils, (64, 64))
+        tables = reference_tables(ref, camera, heat, depth, centers, cfg, seed=16)
+        save('nan_64.npz', heat=heat, depth=depth, centers=centers, names=np.array(names),
+             keypoint_config=np.array(cfg, np.int32), **camera_arrays(camera), **{'ref_' + k: v for k, v in tables.items()})
+        return
     if '--only-topk' in sys.argv:
         save('cornernet_topk.npz', **cornernet_topk_case())
         return
@@ -626,6 +666,12 @@ def main():
     save('adversarial_64.npz', heat=heat, depth=depth, centers=centers, names=np.array(names),
          keypoint_config=np.array(cfg, np.int32), **camera_arrays(camera),
          **{'ref_' + k: v for k, v in tables.items()})
+
+    # 4b: NaN pixels around peaks (max_pool2d propagates NaN)
+    names, cfg, heat, depth, centers = nan_frames()
+    tables = reference_tables(ref, camera, heat, depth, centers, cfg, seed=16)
+    save('nan_64.npz', heat=heat, depth=depth, centers=centers, names=np.array(names),
+         keypoint_config=np.array(cfg, np.int32), **camera_arrays(camera), **{'ref_' + k: v for k, v in tables.items()})
 
     # 5: the reference's own test recipe (test_pipeline.py)
     cfg, heat, depth, centers, truth, keypoints, left, right, T_RL = test_pipeline_frames(ref, camera_utils, video)

@@ -109,7 +109,9 @@ void okp_oracle_detection_to_point_f32(const float* xy, int n, const float* dept
 /* ---------------------------------------------------------------------------------------
  * A2-A5: box sum, NMS, threshold, centroid -- pipeline.py:46-79, models.py:55-58
  * ------------------------------------------------------------------------------------- */
-#define MAXF(a, b) ((a) > (b) ? (a) : (b))   /* inputs are never NaN; vectorises, unlike fmaxf */
+/* torch's max_pool2d update rule, `if (val > max || isnan(val)) max = val` (ATen MaxPoolKernel): NaN propagates, so no
+ * pixel within reach of a NaN box sum passes `x == hmax` (perception/models.py:55-58). Still vectorises. */
+#define MAXF(a, b) (((b) > (a) || (b) != (b)) ? (b) : (a))
 
 typedef struct {
     float* padded;   /* (H+4) x (W+4), zero border */

@@ -63,7 +63,7 @@ def test_ctypes_signatures_agree_with_the_header(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.okp_version() == 1
+    assert lib.okp_version() == 2
     assert lib.okp_strerror(0) == b"ok"
     assert b"NULL" in lib.okp_strerror(-1)
 

@@ -8,9 +8,10 @@ import pytest
 from helpers import (load_golden, golden_camera, reference_tables, assert_tables_match, TOL_PIXELS, TOL_METRES_REL)
 
 pytestmark = pytest.mark.gpu
+GENERIC_PATH = 128          # OKP_FLAG_GENERIC_PATH
 
 DECODE_FIXTURES = ['valve_64.npz', 'cups_64.npz', 'valve_grid_180x320.npz', 'test_pipeline_180x320.npz',
-                   'adversarial_64.npz']
+                   'adversarial_64.npz', 'nan_64.npz']
 
 
 def gpu_decode(heat, depth, centers, cfg, camera, **options):
@@ -23,9 +24,10 @@ def assert_matches_oracle(got, want):
     """GPU vs C oracle on the same input: integer tables and flags identical; the oracle and the
     kernels share one arithmetic contract, so float32 tables are compared bitwise too; float64
     3D points within 1e-4 relative (CUDA's tan/atan are not the host libm's)."""
-    for key in ['peak_count', 'peak_yx', 'peak_object', 'n_objects', 'flags', 'kp_assigned', 'kp_count', 'kp_peak',
-                'n_votes']:
+    for key in ['peak_count', 'peak_yx', 'peak_object', 'n_objects', 'kp_assigned', 'kp_count', 'kp_peak', 'n_votes']:
         np.testing.assert_array_equal(got[key], want[key], err_msg=key)
+    # OKP_FLAG_GENERIC_PATH says which kernels ran, not what the data held: the oracle has no such bit
+    np.testing.assert_array_equal(got['flags'] & ~np.uint32(GENERIC_PATH), want['flags'], err_msg='flags')
     for key in ['peak_score', 'peak_xy', 'peak_conf', 'kp_xy']:
         np.testing.assert_array_equal(got[key].view(np.uint32), want[key].view(np.uint32), err_msg=key + " (bitwise)")
     np.testing.assert_array_equal(got['peak_vote'], want['peak_vote'])
@@ -387,23 +389,165 @@ def test_bf16_peak_extraction_shapes_noise_and_overflow(H, W, N, C, K):
 
 
 def test_record_pack_kernel_equals_the_torch_packing():
-    """okp_pack_records_f64 (the pack / peer-store step of sharding.RecordExchange) against
-    sharding.record_tensor, on the tables of a real decode; several exchanges through the slot ring."""
+    """okp_pack_records_f64 (the dense float64 record of the tables) against sharding.record_tensor, on the tables of a
+    real decode."""
+    import ctypes
     import torch
-    from object_keypoints_b200 import KeypointDecoder, synthetic, sharding
+    from object_keypoints_b200 import KeypointDecoder, synthetic, sharding, _lib
     cfg = [1, 3]
     batch = synthetic.make_batch(21, cfg, (64, 64), seed=17, objects=(1, 3))
     decoder = KeypointDecoder(cfg, (64, 64), camera=synthetic.default_camera((64, 64)))
     tables = decoder.decode_batch(batch.heat, batch.depth, batch.centers)
-    exchange = sharding.RecordExchange(tables, world=1, rank=0)
-    assert exchange.transport == 'local' and exchange.R == 2 + 16 * 3 + 16 * 3 * 3 * 3
+    R = _lib.lib().okp_record_doubles(16, 3, 3)
+    assert R == 2 + 16 * 3 + 16 * 3 * 3 * 3
     want = sharding.record_tensor(tables)
-    for _ in range(4):
-        got, done = exchange.exchange(tables)
-        done.synchronize()
-        assert torch.equal(got, want)
-    back = sharding.unpack_records(got, tables)
+    got = torch.zeros((21 + 4, R), dtype=torch.float64, device='cuda')
+    destinations = (ctypes.c_void_p * 1)(got.data_ptr())
+    rc = _lib.lib().okp_pack_records_f64(ctypes.byref(tables.struct), 21, 16, 3, 3, 4, destinations, 1, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(got[4:], want) and not got[:4].any()
+    back = sharding.unpack_records(got[4:], tables)
     assert torch.equal(back['kp_point'], tables['kp_point']) and torch.equal(back['n_objects'], tables['n_objects'])
+
+
+@pytest.mark.parametrize('cfg,size,lean', [([1, 3], (64, 64), False), ([1, 3], (64, 64), True), ([1, 1, 1], (64, 64), False),
+                                           ([1, 3], (37, 93), False)])
+def test_compact_records_emitted_by_the_decode_kernel(cfg, size, lean):
+    """okp_decode_emit_*: the record every frame's grouping writes into the sink (the multi-GPU gather's payload) equals
+    the torch packing of the tables -- fused kernel (64x64), generic path + stand-alone grouping (37x93), frames that
+    take the overflow fix-up, several steps through the slot ring of sharding.RecordExchange (world 1: 'local')."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic, sharding
+    layout = dict(center_separation=18.0, spoke_radius=(4.0, 6.0), peak_separation=5.0, border=3.0) if size[0] < 64 else {}
+    batch = synthetic.make_batch(23, cfg, size, seed=19, objects=(1, 3), **layout)
+    heat = batch.heat.copy()
+    heat[3, 1] = 0.5                                                   # a map with more than K peaks: overflow fix-up
+    heat[5, 0, 10, 10] = -0.25                                         # a negative value: exact path for that map
+    heat[7, 0] = 0.0                                                   # no centres
+    camera = synthetic.default_camera((64, 64))
+    decoder = KeypointDecoder(cfg, size, camera=camera, lean_tables=lean)
+    exchange = sharding.RecordExchange(decoder, 23, world=1, rank=0)
+    assert exchange.transport == 'local' and exchange.record_bytes == sharding.compact_layout(16, cfg)['record_bytes']
+    tables = decoder.tables(23)
+    for step in range(6):
+        sink = exchange.begin()
+        decoder.decode_batch(heat, batch.depth, batch.centers, tables=tables, records=sink)
+        got, done = exchange.end()
+        done.synchronize()
+        back = sharding.unpack_compact_records(got, 16, cfg)
+        for key in ('n_objects', 'kp_count', 'kp_point'):
+            want = tables[key]
+            if key == 'kp_count':
+                want = torch.where(torch.arange(16, device='cuda')[None, :, None] < tables['n_objects'][:, None, None], want, 0)
+            if key == 'kp_point':
+                slot = torch.arange(want.shape[3], device='cuda')[None, None, None, :] < back['kp_count'][..., None]
+                want = torch.where(slot[..., None], want, 0.0)
+            assert torch.equal(back[key], want.to(back[key].dtype)), (step, key)
+        assert torch.equal(back['flags'], tables['flags'].to(torch.int32))
+        if step == 0:
+            assert (tables['flags'][3] & 1) and int(tables['n_objects'][7]) == 0
+            want_bytes = sharding.pack_compact_records(tables, cfg)
+            fresh = torch.equal(got, want_bytes)                      # the buffers start zeroed: byte-identical the first time
+            assert fresh, "record bytes differ from the torch packing"
+
+
+def test_lean_tables_write_only_the_valid_slots():
+    """OkpDecodeParams.lean_tables: the valid slots are bitwise those of the default mode; everything else keeps what
+    the buffer held (here: the poison written before the call)."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic, _abi
+    from oracle import c_oracle
+    cfg = [1, 3]
+    camera = synthetic.default_camera((64, 64))
+    for size, frames in (((64, 64), 40), ((180, 320), 6), ((37, 93), 5)):
+        layout = dict(center_separation=18.0, spoke_radius=(4.0, 6.0), peak_separation=5.0, border=3.0) if size[0] < 64 else {}
+        batch = synthetic.make_batch(frames, cfg, size, seed=23, objects=(1, 3), **layout)
+        heat = batch.heat.copy()
+        heat[1, 2] = 0.5                                               # overflow map
+        heat[2, 0] = 0.0                                               # no centres
+        cam = synthetic.default_camera(size) if size != (37, 93) else camera
+        want = c_oracle.decode(heat, batch.depth, batch.centers, cfg, cam)
+        lean = KeypointDecoder(cfg, size, camera=cam, lean_tables=True)
+        tables = lean.tables(frames)
+        tables.flat.fill_(0x5A)                                        # poison
+        got = lean.decode_batch(heat, batch.depth, batch.centers, tables=tables).numpy()
+        assert_matches_oracle(_abi.mask_unspecified(got), want)
+        if size == (64, 64):                                           # and the poison is still there where nothing is valid
+            assert (got['votes'][2].view(np.uint8) == 0x5A).all() and (got['kp_point'][2].view(np.uint8) == 0x5A).all()
+            assert (got['peak_xy'][0, 0, 8:].view(np.uint8) == 0x5A).all()
+
+
+def test_generic_path_flag_tells_the_caller_the_shape_fell_off_the_tma_kernel():
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    camera = synthetic.default_camera((64, 64))
+    layout = dict(center_separation=18.0, spoke_radius=(4.0, 6.0), peak_separation=5.0, border=3.0)
+    for size, options, generic in (((64, 64), {}, False), ((37, 93), {}, True), ((40, 56), {}, False),
+                                   ((64, 64), dict(nms_size=3), True), ((64, 64), dict(box_sum=False), True),
+                                   ((64, 64), dict(top_k=4), False)):
+        batch = synthetic.make_batch(5, [1, 3], size, seed=29, objects=(1, 2), **(layout if size[0] < 64 else {}))
+        decoder = KeypointDecoder([1, 3], size, camera=camera, **options)
+        tables = decoder.tables(5)
+        tables['flags'].fill_(GENERIC_PATH if not generic else 0)      # a stale bit must not survive, a missing one must appear
+        flags = decoder.decode_batch(batch.heat, batch.depth, batch.centers, tables=tables).numpy()['flags']
+        assert bool((flags & GENERIC_PATH).all()) == generic and bool((flags & GENERIC_PATH).any()) == generic, (size, options)
+
+
+def test_nan_maps_follow_torch_max_pool():
+    """torch's max_pool2d propagates NaN: no pixel whose 5x5 window holds a NaN box sum is a peak (fixture made with the
+    unmodified reference). The stream kernel sees the NaN in its bit test and hands the map to the exact kernels."""
+    from oracle import c_oracle
+    g = load_golden('nan_64.npz')
+    cfg, camera = list(g['keypoint_config']), golden_camera(g)
+    got = gpu_decode(g['heat'], g['depth'], g['centers'], cfg, camera)
+    ref = reference_tables(g)
+    np.testing.assert_array_equal(got['peak_count'], ref['peak_count'])
+    np.testing.assert_array_equal(got['peak_yx'], ref['peak_yx'])
+    np.testing.assert_array_equal(got['n_objects'], ref['n_objects'])
+    assert_matches_oracle(got, c_oracle.decode(g['heat'], g['depth'], g['centers'], cfg, camera))
+
+
+def test_unaligned_views_and_wrong_host_shapes():
+    """A heatmap view whose base is not 16-byte aligned is re-materialised (the C entry refuses it); decode_host_batch
+    validates shapes instead of reading out of bounds; every call returns its own result tensors."""
+    import ctypes
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, synthetic, _lib
+    cfg = [1]
+    size = (5, 12)                                                     # 2 maps x 60 floats per frame: frame 1 starts at byte 480, frame stride 480
+    camera = synthetic.default_camera((64, 64))
+    rng = np.random.default_rng(3)
+    heat = torch.from_numpy(rng.uniform(0, 0.2, (6, 2, 5, 12)).astype(np.float32)).cuda()
+    flat = torch.zeros(heat.numel() + 1, device='cuda')
+    flat[1:] = heat.reshape(-1)
+    view = flat[1:].reshape(heat.shape)                                # base + 4 bytes
+    assert view.data_ptr() % 16 == 4
+    decoder = KeypointDecoder(cfg, size, camera=camera)
+    a = decoder.extract_peaks(view).numpy()
+    b = decoder.extract_peaks(heat).numpy()
+    for key in ('peak_count', 'peak_yx', 'peak_score'):
+        np.testing.assert_array_equal(a[key], b[key])
+    ws = decoder._workspace_for(6)
+    rc = _lib.lib().okp_extract_peaks_f32(view.data_ptr(), 6, 2, 5, 12, ctypes.byref(decoder.params),
+                                          ctypes.byref(decoder.tables(6).struct), ws.data_ptr(), ws.numel(), None)
+    assert rc == -4                                                    # OKP_E_UNSUPPORTED, not a silent slow path
+    batch = synthetic.make_batch(9, [1, 3], (64, 64), seed=31, objects=(1, 2))
+    dec = KeypointDecoder([1, 3], (64, 64), camera=camera)
+    host = [torch.from_numpy(x).pin_memory() for x in (batch.heat, batch.depth, batch.centers)]
+    with pytest.raises(ValueError):
+        dec.decode_host_batch(host[0], host[1][:, :2], host[2])
+    with pytest.raises(ValueError):
+        dec.decode_host_batch(host[0], host[1], host[2][:4])
+    with pytest.raises(ValueError):
+        dec.decode_host_batch(host[0][:, :2], host[1], host[2])
+    r1 = dec.decode_host_batch(*host, chunk_frames=4, sparse=False)
+    r2 = dec.decode_host_batch(host[0] * 0, host[1], host[2], chunk_frames=4, sparse=False)
+    assert r1 is not r2 and int(r1['n_objects'].sum()) > 0 and int(r2['n_objects'].sum()) == 0
+    r3 = dec.decode_host_batch(*host, chunk_frames=4, sparse=False, out=r2)
+    assert r3 is r2 and torch.equal(r3['kp_point'], r1['kp_point'])
+    for chunk in (1, 2, 3, 5):                                         # staging sets are bounded
+        dec.decode_host_batch(*host, chunk_frames=chunk, sparse=False)
+    assert len([k for k in dec._tables if isinstance(k, tuple)]) <= dec.HOST_STAGING_SETS
 
 
 def test_sparse_host_transfer_gives_the_tables_of_the_dense_copy():
@@ -451,3 +595,79 @@ def test_sparse_host_transfer_gives_the_tables_of_the_dense_copy():
         assert dec.host_chunks_sparse == 2
         for name in KeypointDecoder.HOST_RESULT_TABLES:
             np.testing.assert_array_equal(got[name].numpy().view(np.uint8), want[name].numpy().view(np.uint8), err_msg=name)
+
+
+@pytest.mark.parametrize('workload,frames', [('config4_180x320', 256), ('config4_64x64', 1024)])
+def test_headline_bench_workload_is_bitwise_the_oracle(workload, frames):
+    """The very frames bench.py times (synthetic.torch_grid_batch with bench.py's seed 1004 and grid) decoded on the GPU
+    against the C oracle: bitwise integer and float32 tables, 3D points <= 1e-4 relative. The oracle was checked against the
+    unmodified reference on frames of this generator; this closes the remaining GPU-vs-oracle comparison."""
+    import bench
+    from oracle import c_oracle
+    from object_keypoints_b200 import KeypointDecoder, synthetic
+    w = bench.WORKLOADS[workload]
+    heat, depth, centers, n_obj = synthetic.torch_grid_batch(frames, w['cfg'], w['size'], seed=1004, grid=w['grid'], device='cuda')
+    camera = synthetic.default_camera(w['size'])
+    decoder = KeypointDecoder(w['cfg'], w['size'], camera=camera)
+    got = decoder.decode_batch(heat, depth, centers).numpy()
+    want = c_oracle.decode(heat.cpu().numpy(), depth.cpu().numpy(), centers.cpu().numpy(), w['cfg'], camera)
+    assert_matches_oracle(got, want)
+    assert (got['n_objects'] == n_obj).mean() > 0.99
+    # bf16 form of the same frames (config 5's element type): bitwise the oracle on the up-cast maps
+    import torch
+    heat16, depth16, centers16 = (t.to(torch.bfloat16) for t in (heat, depth, centers))
+    got16 = decoder.decode_batch(heat16, depth16, centers16).numpy()
+    want16 = c_oracle.decode(heat16.float().cpu().numpy(), depth16.float().cpu().numpy(), centers16.float().cpu().numpy(),
+                             w['cfg'], camera)
+    assert_matches_oracle(got16, want16)
+
+
+def _tiny_scripted_model(path, heat, depth, centers):
+    """A TorchScript module with the deployed model's contract (scripts/package_model.py:22-28): frames [N,3,h,w] ->
+    (heat [N,C,H,W], depth, centers [N,C-1,2,H,W]); it replays fixed maps scaled by a function of the frame so that the
+    input matters."""
+    import torch
+
+    class Replay(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.register_buffer('heat', torch.from_numpy(heat))
+            self.register_buffer('depth', torch.from_numpy(depth))
+            self.register_buffer('centers', torch.from_numpy(centers))
+
+        def forward(self, frames):
+            gain = 1.0 + 0.0 * frames.mean()
+            return self.heat * gain, self.depth * gain, self.centers * gain
+
+    torch.jit.script(Replay()).save(path)
+
+
+def test_inference_component_and_learned_pipeline(tmp_path):
+    """A9: InferenceComponent loads a TorchScript file, runs it on the device and leaves the outputs there;
+    LearnedKeypointTrackingPipeline(model, cuda, prediction_size, points_3d, keypoint_config)(frame) returns
+    (objects, heatmap) like perception/pipeline.py:13-28,202-209."""
+    import torch
+    from object_keypoints_b200 import InferenceComponent, LearnedKeypointTrackingPipeline, ObjectKeypointPipeline
+    g = load_golden('valve_64.npz')
+    ref = reference_tables(g)
+    path = str(tmp_path / 'model.pt')
+    _tiny_scripted_model(path, g['heat'][:1], g['depth'][:1], g['centers'][:1])
+    inference = InferenceComponent(path, cuda=True)
+    assert inference.name == 'inference'
+    outputs = inference(torch.zeros(1, 3, 32, 32))
+    assert len(outputs) == 3 and all(o.is_cuda for o in outputs), "outputs stay on the device (no .cpu() round trip)"
+    assert outputs[0].shape == (1, 3, 64, 64) and outputs[2].shape == (1, 2, 2, 64, 64)
+    pipeline = LearnedKeypointTrackingPipeline(path, True, [64, 64], None, {'keypoint_config': [1, 3]})
+    pipeline.reset(golden_camera(g))
+    objects, heatmap = pipeline(torch.zeros(1, 3, 32, 32))
+    assert torch.equal(heatmap.cpu(), torch.from_numpy(g['heat'][:1]))
+    plain = ObjectKeypointPipeline([64, 64], None, {'keypoint_config': [1, 3]})
+    plain.reset(golden_camera(g))
+    want = plain(torch.from_numpy(g['heat'][:1]), torch.from_numpy(g['depth'][:1]), torch.from_numpy(g['centers'][:1]))
+    assert len(objects) == len(want) == ref['n_objects'][0]
+    for a, b in zip(objects, want):
+        for c in range(3):
+            np.testing.assert_array_equal(a['keypoints'][c], b['keypoints'][c])
+            np.testing.assert_array_equal(a['p_C'][c], b['p_C'][c])
+            cnt = ref['kp_count'][0, objects.index(a), c]
+            assert np.abs(a['keypoints'][c] - ref['kp_xy'][0, objects.index(a), c, :cnt]).max(initial=0) <= TOL_PIXELS

@@ -8,7 +8,7 @@ from helpers import (load_golden, golden_camera, reference_tables, assert_tables
 from oracle import np_oracle, c_oracle
 
 DECODE_FIXTURES = ['valve_64.npz', 'cups_64.npz', 'valve_grid_180x320.npz', 'test_pipeline_180x320.npz',
-                   'adversarial_64.npz']
+                   'adversarial_64.npz', 'nan_64.npz']
 
 
 def bits(a):

@@ -61,3 +61,39 @@ def test_config5_bf16_producer_feeds_the_decode_kernels_in_place():
     for key in ['peak_score', 'peak_xy', 'peak_conf', 'kp_xy']:
         np.testing.assert_array_equal(got[key].view(np.uint32), want[key].view(np.uint32), err_msg=key)
     assert got['peak_count'].sum() > 0
+
+
+@pytest.mark.gpu
+def test_learned_pipeline_runs_a_traced_keypoint_net(tmp_path):
+    """A9 end to end, the way scripts/package_model.py:21-42 + scripts/eval_model.py:278-293 use it: the network is traced
+    to TorchScript, LearnedKeypointTrackingPipeline loads the file, runs it on the device and decodes its outputs in place.
+    The objects must be those of the decoder called directly on the network's outputs, and (objects, heatmap) the return."""
+    from object_keypoints_b200 import KeypointDecoder, LearnedKeypointTrackingPipeline, producer, synthetic
+    from object_keypoints_b200.pipeline import tables_to_objects
+    cfg = {'keypoint_config': [1, 3]}
+    net = producer.build_producer(cfg, device='cuda', dtype=torch.float32, seed=0)
+    frame = torch.randn(1, 3, 511, 511, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        traced = torch.jit.trace(net, frame.cuda().contiguous(memory_format=torch.channels_last))
+    path = str(tmp_path / 'keypoint_net.pt')
+    traced.save(path)
+    options = dict(max_peaks=128, max_objects=128, max_votes=64)          # random-init maps: ~100 noise peaks per map
+    pipeline = LearnedKeypointTrackingPipeline(path, True, [64, 64], None, cfg, **options)
+    camera = synthetic.default_camera((64, 64))
+    pipeline.reset(camera)
+    objects, heatmap = pipeline(frame)
+    assert heatmap.is_cuda and heatmap.shape == (1, 3, 64, 64)
+    with torch.no_grad():
+        heat, depth, centers = torch.jit.load(path).cuda()(frame.cuda())
+    assert torch.equal(heat, heatmap)
+    decoder = KeypointDecoder(cfg, (64, 64), camera=camera, **options)
+    want = tables_to_objects(decoder.decode_batch(heat, depth, centers).numpy(), 0)
+    assert len(objects) == len(want) > 0
+    for a, b in zip(objects, want):
+        assert set(a) == {'p_centers', 'keypoints', 'p_C'}
+        for c in range(3):
+            np.testing.assert_array_equal(a['keypoints'][c], b['keypoints'][c])
+            if b['p_C'][c] is None:
+                assert a['p_C'][c] is None
+            else:
+                np.testing.assert_array_equal(a['p_C'][c], b['p_C'][c])

@@ -49,6 +49,61 @@ def test_record_roundtrip():
         assert torch.equal(back[key], t[key]), key
 
 
+def consistent_tables(n, seed, cfg=(1, 3), O=4):
+    """Fake decode tables whose counts respect keypoint_config (what the kernel can actually produce)."""
+    g = torch.Generator().manual_seed(seed)
+    config = [1] + list(cfg)
+    C, S = len(config), max(config)
+    limit = torch.tensor(config, dtype=torch.int32)[None, None, :] + 1
+    count = (torch.randint(0, 9, (n, O, C), generator=g, dtype=torch.int32) % limit).to(torch.int32)
+    return {'n_objects': torch.randint(0, O + 1, (n,), generator=g, dtype=torch.int32),
+            'flags': torch.randint(0, 256, (n,), generator=g, dtype=torch.int32),
+            'kp_count': count, 'kp_point': torch.randn((n, O, C, S, 3), generator=g, dtype=torch.float64)}
+
+
+def _masked(t):
+    """What a compact record preserves: counts of existing objects, points of kept slots."""
+    O, S = t['kp_count'].shape[1], t['kp_point'].shape[3]
+    valid = torch.arange(O)[None, :] < t['n_objects'][:, None]
+    count = torch.where(valid[:, :, None], t['kp_count'], torch.zeros((), dtype=torch.int32))
+    slot = torch.arange(S)[None, None, None, :] < count[..., None]
+    return {'n_objects': t['n_objects'], 'flags': t['flags'], 'kp_count': count,
+            'kp_point': torch.where(slot[..., None], t['kp_point'], torch.zeros((), dtype=torch.float64))}
+
+
+def test_compact_record_layout_and_roundtrip():
+    lay = sharding.compact_layout(16, {'keypoint_config': [1, 3]})
+    assert (lay['C'], lay['P'], lay['slot_of']) == (3, 5, [0, 1, 2])
+    assert lay['points_offset'] == 8 + 192 and lay['record_bytes'] == 8 + 192 + 16 * 5 * 24      # 2120, not 3856
+    assert sharding.compact_layout(3, [1, 1, 1])['points_offset'] == 8 + 48                     # 4 * 3 * 4 = 48 is a multiple of 8
+    assert sharding.compact_layout(3, [2])['points_offset'] == 8 + 24
+    assert sharding.compact_layout(1, [])['points_offset'] == 16                                 # 4 bytes of counts, padded to 8
+    for cfg, O in (([1, 3], 4), ([1, 1, 1], 3), ([], 2), ([2, 4], 5)):
+        t = consistent_tables(9, 5, cfg, O)
+        records = sharding.pack_compact_records(t, cfg)
+        assert records.dtype == torch.uint8 and records.shape == (9, sharding.compact_layout(O, cfg)['record_bytes'])
+        back = sharding.unpack_compact_records(records, O, cfg)
+        want = _masked(t)
+        for key in want:
+            assert torch.equal(back[key], want[key]), (cfg, key)
+        # stale bytes where the kernel does not write must not leak through the reader
+        lay = sharding.compact_layout(O, cfg)
+        noisy = records.clone()
+        for n in range(9):
+            for o in range(O):
+                for c in range(lay['C']):
+                    kept = int(want['kp_count'][n, o, c])
+                    if o >= int(t['n_objects'][n]):
+                        noisy[n, 8 + 4 * (o * lay['C'] + c):8 + 4 * (o * lay['C'] + c) + 4] = 0x5A
+                    for s_ in range(kept, lay['cfg'][c]):
+                        at = lay['points_offset'] + 24 * (o * lay['P'] + lay['slot_of'][c] + s_)
+                        noisy[n, at:at + 24] = 0x5A
+        assert not torch.equal(noisy, records)
+        back = sharding.unpack_compact_records(noisy, O, cfg)
+        for key in want:
+            assert torch.equal(back[key], want[key]), (cfg, key, 'stale bytes leaked')
+
+
 def _worker(rank, world, port, frames_total, out_dir):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -60,6 +115,15 @@ def _worker(rank, world, port, frames_total, out_dir):
         gathered = sharding.gather_keypoint_records(mine, world)
         got = sharding.unpack_records(gathered, mine)
         ok = all(torch.equal(got[k], everything[k]) for k in everything)
+        # the compact records of the fused kernel travel the same way (NCCL transport: all_gather of the byte rows)
+        everything = consistent_tables(frames_total, 321)
+        mine = {k: v[f0:f1].clone() for k, v in everything.items()}
+        local = sharding.pack_compact_records(mine, [1, 3])
+        rows = torch.empty((world * local.shape[0], local.shape[1]), dtype=torch.uint8)
+        dist.all_gather_into_tensor(rows, local)
+        back = sharding.unpack_compact_records(rows, 4, [1, 3])
+        want = _masked(everything)
+        ok = ok and all(torch.equal(back[k], want[k]) for k in want)
         np.save(os.path.join(out_dir, f'ok_{rank}.npy'), np.array([ok, gathered.shape[0]]))
     finally:
         dist.destroy_process_group()

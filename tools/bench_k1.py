@@ -1,5 +1,5 @@
-"""Times okp_extract_peaks_* (K1) and okp_group_objects_* alone on synthetic batches.
-usage: python tools/bench_k1.py [180x320|64x64] [frames] [reps] [f32|bf16]"""
+"""Times okp_extract_peaks_* (K1) and okp_group_objects_* alone, and the fused okp_decode_* call, on synthetic batches.
+usage: python tools/bench_k1.py [180x320|64x64] [frames] [reps] [f32|bf16] [lean]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,7 +15,8 @@ heat, depth, centers, _ = synthetic.torch_grid_batch(frames, [1, 3], (H, W), see
 if dtype == 'bf16':
     heat, depth, centers = heat.bfloat16(), depth.bfloat16(), centers.bfloat16()
 camera = synthetic.default_camera((H, W))
-dec = KeypointDecoder([1, 3], (H, W), camera=camera)
+lean = len(sys.argv) > 5 and sys.argv[5] == 'lean'
+dec = KeypointDecoder([1, 3], (H, W), camera=camera, lean_tables=lean)
 tables = dec.tables(frames)
 for _ in range(3):
     dec.extract_peaks(heat, tables); dec.group_objects(depth, centers, tables)
@@ -27,7 +28,17 @@ for _ in range(reps):
     torch.cuda.synchronize()
     k1 += ev[0].elapsed_time(ev[1]); k3 += ev[1].elapsed_time(ev[2])
 k1 /= reps; k3 /= reps
+for _ in range(3):
+    dec.decode_batch(heat, depth, centers, tables=tables)
+torch.cuda.synchronize()
+ev[0].record()
+for _ in range(reps):
+    dec.decode_batch(heat, depth, centers, tables=tables)
+ev[1].record()
+torch.cuda.synchronize()
+fused = ev[0].elapsed_time(ev[1]) / reps
 gb = frames * 3 * H * W * heat.element_size() / 1e9
 print(f"{shape} {dtype} frames={frames} env={ {k: v for k, v in os.environ.items() if k.startswith('OKP_')} } "
-      f"K1 {k1 * 1e3:.1f} us = {gb / (k1 / 1e3):.0f} GB/s ({gb / (k1 / 1e3) / 6548.2:.3f} of measured HBM peak); group {k3 * 1e3:.1f} us; "
+      f"K1 {k1 * 1e3:.1f} us = {gb / (k1 / 1e3):.0f} GB/s ({gb / (k1 / 1e3) / 6547.2:.3f} of measured HBM peak); group {k3 * 1e3:.1f} us; "
+      f"FUSED decode{' (lean tables)' if lean else ''} {fused * 1e3:.1f} us = {gb / (fused / 1e3) / 6547.2:.3f}; "
       f"objects/frame {float(tables['n_objects'].float().mean()):.2f}")

@@ -18,17 +18,29 @@ report = {}
 for transport, root in (('nccl', None), ('peer', None), ('nccl', 0), ('peer', 0), ('peer', world - 1)):
     label = f"{transport}/{'allgather' if root is None else 'gather->' + str(root)}"
     try:
-        exchange = None
-        for step in range(5):
+        exchange = sharding.RecordExchange(decoder, frames, world=world, rank=rank, transport=transport, root=root)
+        tables = decoder.tables(frames)
+        for step in range(7):                                     # more steps than ring slots
             batch = synthetic.make_batch(frames, cfg, size, seed=100 * step + rank, objects=(1, 3))
-            tables = decoder.decode_batch(batch.heat, batch.depth, batch.centers)
-            if exchange is None:
-                exchange = sharding.RecordExchange(tables, world=world, rank=rank, transport=transport, root=root)
-            got, done = exchange.exchange(tables)
-            want = sharding.gather_keypoint_records(tables, world)
+            heat = batch.heat.copy()
+            heat[rank % frames, 1] = 0.5                          # an overflowing map: that frame's record comes from the fix-up launch
+            sink = exchange.begin()
+            decoder.decode_batch(heat, batch.depth, batch.centers, tables=tables, records=sink)
+            got, done = exchange.end()
+            # what every rank should have sent: the torch packing of its own tables, gathered with a plain all_gather
+            mine = sharding.unpack_compact_records(sharding.pack_compact_records(tables, cfg), 16, cfg)
+            want = {}
+            for key, value in mine.items():
+                parts = [torch.empty_like(value) for _ in range(world)]
+                dist.all_gather(parts, value.contiguous())
+                want[key] = torch.cat(parts)
             done.synchronize()
             if root is None or rank == root:
-                assert torch.equal(got, want), f"{label}: step {step} differs on rank {rank}"
+                back = sharding.unpack_compact_records(got, 16, cfg)
+                for key in want:
+                    assert torch.equal(back[key], want[key]), f"{label}: step {step} {key} differs on rank {rank}"
+                assert int(back['n_objects'].sum()) > 0
+            dist.barrier()
         report[label] = 'ok'
     except Exception as error:
         report[label] = f"FAILED {type(error).__name__}: {error}"
