@@ -250,6 +250,83 @@ def secondary_64x64(device, peaks, steps):
     return out
 
 
+def secondary_config3(device, reps=5):
+    """BASELINE config 3: valve sequence of ~900 frames (30 s at 30 fps), 8 objects, 16 viewpoints per point: decode ->
+    cross-view association -> robust multi-view triangulation (object_keypoints_b200/sequence.py), everything on the device.
+    Parity: tests/test_sequence.py (bit-equal matches / masks, points <= 1e-4 relative against oracle/sequence_oracle.py)."""
+    import numpy as np
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, sequence, synthetic, targets
+    camera = synthetic.default_camera((180, 320))
+    seq = sequence.synthetic_sequence(900)
+    keypoints, depths = sequence.project_sequence(seq, camera)
+    heat, depth, centers = targets.rasterise_targets(keypoints, depths, [1, 3], (180, 320), device=device)
+    decoder = KeypointDecoder([1, 3], (180, 320), camera=camera, device=device)
+    tables = decoder.tables(900)
+    chain = sequence.SequenceTriangulator(camera, views=16, device=device)
+    prepared = chain.prepare(seq['T_CW'])
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    decode_ms = chain_ms = 0.0
+    out = None
+    for rep in range(reps + 2):
+        events[0].record()
+        decoder.decode_batch(heat, depth, centers, tables=tables)
+        events[1].record()
+        out = chain(tables, prepared)
+        events[2].record()
+        torch.cuda.synchronize()
+        if rep >= 2:
+            decode_ms += events[0].elapsed_time(events[1]) / reps
+            chain_ms += events[1].elapsed_time(events[2]) / reps
+    points = out['points'].cpu().numpy()
+    ok = ~np.isnan(points[..., 0])
+    truth = seq['scene'].reshape(-1, 3)
+    error = np.linalg.norm(points[ok][:, None] - truth[None], axis=2).min(axis=1)
+    observed, valid = out['observed'].cpu().numpy()[ok], out['valid'].cpu().numpy()[ok]
+    return {'workload': 'config3_sequence: 900 valve frames 180x320, 8 objects, 16 views per point', 'frames': 900,
+            'tracks': int(ok.sum()), 'views': 16, 'decode_ms': decode_ms, 'association_triangulation_ms': chain_ms,
+            'frames_per_s': 900 / ((decode_ms + chain_ms) / 1e3), 'points_per_s': int(ok.sum()) / (chain_ms / 1e3),
+            'objects_per_frame': float(tables['n_objects'].float().mean()),
+            'views_observed_mean': float(observed.sum(axis=1).mean()), 'views_dropped_by_the_filter': int(observed.sum() - valid.sum()),
+            'median_error_m': float(np.median(error)), 'within_1cm': float((error < 1e-2).mean())}
+
+
+def secondary_config5(device, batch=256, reps=3):
+    """BASELINE config 5: random-init CornerNet-Squeeze forward in bf16 at batch 256 (plain PyTorch / cuDNN: the input
+    producer, not the product) whose three head outputs stay on the device and go straight into okp_decode_bf16.
+    Random-init heatmaps sit at ~0.5: about a hundred noise peaks per map, every map overflows the fast path."""
+    import torch
+    from object_keypoints_b200 import KeypointDecoder, producer, synthetic
+    cfg = [1, 3]
+    torch.backends.cudnn.benchmark = True
+    net = producer.build_producer(cfg, device=device, dtype=torch.bfloat16, seed=0)
+    generator = torch.Generator(device=device).manual_seed(0)
+    frames = torch.randn(batch, 3, 511, 511, device=device, dtype=torch.bfloat16, generator=generator).contiguous(memory_format=torch.channels_last)
+    decoder = KeypointDecoder(cfg, (64, 64), camera=synthetic.default_camera((64, 64)), device=device, max_peaks=128, max_objects=128,
+                              max_votes=64)
+    tables = decoder.tables(batch)
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    net_ms = dec_ms = 0.0
+    with torch.no_grad():
+        for rep in range(reps + 2):
+            events[0].record()
+            heat, depth, centers = net(frames)
+            events[1].record()
+            decoder.decode_batch(heat, depth, centers, tables=tables)
+            events[2].record()
+            torch.cuda.synchronize()
+            if rep >= 2:
+                net_ms += events[0].elapsed_time(events[1]) / reps
+                dec_ms += events[1].elapsed_time(events[2]) / reps
+    out = {'workload': 'config5: CornerNet-Squeeze bf16 forward (PyTorch) -> okp_decode_bf16, random-init weights', 'batch': batch,
+           'network_ms': net_ms, 'decode_ms': dec_ms, 'frames_per_s': batch / ((net_ms + dec_ms) / 1e3),
+           'decode_share': dec_ms / (net_ms + dec_ms), 'mean_peaks_per_map': float(tables['peak_count'].float().mean()),
+           'overflow_frames': int((tables['flags'] & 1).ne(0).sum()), 'dtype': 'bf16'}
+    del net, frames
+    torch.cuda.empty_cache()
+    return out
+
+
 def host_read_ceiling(device, nbytes=1 << 30):
     """Measured ceilings of the e2e path on this box: (a) the DMA engine reading pinned host memory into HBM, (b) every
     host core of this rank reading the same pinned buffer (the host pass's access pattern). GB/s."""
@@ -442,6 +519,8 @@ def run_ours(args):
             line['cpu_baseline'] = baseline
         if world == 1 and not args.no_secondary:
             line['secondary'] = secondary_64x64(device, peaks, max(5, min(args.steps, 20)))
+            line['secondary'].append(secondary_config3(device))
+            line['secondary'].append(secondary_config5(device))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

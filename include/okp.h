@@ -254,6 +254,14 @@ int okp_triangulate_robust_f64(const double* obs_dev, uint8_t* valid_dev, const 
                                const OkpCamera* camera, int P, int V, double max_error_px, int max_rounds,
                                double* out_dev, double* err_dev, int32_t* dropped_dev, void* stream);
 
+/* okp_triangulate_robust_f64 for TRACKS of a moving camera (BASELINE config 3: a 30 s sequence, 16 viewpoints per point):
+ * the points come in G groups of Pg, each group seen from its own V poses -- the generalisation of
+ * LabelingApp._triangulate (scripts/label.py:285-305: one pose pair per labelled point) to V views. obs_dev [G,Pg,V,2],
+ * valid_dev [G,Pg,V], poses_dev [G,V,4,4] world->camera, out_dev [G,Pg,3], err_dev [G,Pg,V], dropped_dev [G,Pg]. */
+int okp_triangulate_tracks_f64(const double* obs_dev, uint8_t* valid_dev, const double* poses_dev,
+                               const OkpCamera* camera, int G, int Pg, int V, double max_error_px, int max_rounds,
+                               double* out_dev, double* err_dev, int32_t* dropped_dev, void* stream);
+
 /* Replaces the cv2.correctMatches call of StereoCamera.triangulate (camera_utils.py:100-101): the
  * Hartley-Sturm optimal correction. F: 9 doubles row-major on the HOST with x_right^T F x_left = 0
  * (camera_utils.py:184-189). left_dev/right_dev: [n,2] float64 UNDISTORTED pixels; the outputs are the
@@ -274,6 +282,14 @@ int okp_stereo_associate_f64(const double* F, const double* left_dev, const int3
                              const double* right_dev, const int32_t* n_right_dev, int B, int max_left,
                              int max_right, double max_distance_px, int32_t* match_dev, double* cost_dev,
                              void* stream);
+
+/* okp_stereo_associate_f64 with one fundamental matrix PER PAIR, F_dev [B,9] in device memory: association between two
+ * frames of a moving camera, whose F follows from the two poses (scripts/label.py:285-297 builds exactly that pair
+ * geometry for its two-view triangulation). */
+int okp_associate_pairs_f64(const double* F_dev, const double* left_dev, const int32_t* n_left_dev,
+                            const double* right_dev, const int32_t* n_right_dev, int B, int max_left,
+                            int max_right, double max_distance_px, int32_t* match_dev, double* cost_dev,
+                            void* stream);
 
 /* Evaluation bookkeeping. Replaces Results.add of the reference's
  * scripts/eval_model.py:141-187 for a batch of N frames, reading the decode tables in place:

@@ -20,7 +20,7 @@ EXPORTS = [
     'okp_extract_peaks_bf16', 'okp_group_objects_bf16', 'okp_decode_bf16',
     'okp_eval_match_f64', 'okp_eval_summary_f64', 'okp_record_doubles', 'okp_pack_records_f64',
     'okp_rasterise_targets_f32', 'okp_host_pack_scratch_bytes', 'okp_host_pack_tiles_f32', 'okp_scatter_tiles_f32',
-    'okp_record_bytes', 'okp_decode_emit_f32', 'okp_decode_emit_bf16',
+    'okp_record_bytes', 'okp_decode_emit_f32', 'okp_decode_emit_bf16', 'okp_triangulate_tracks_f64', 'okp_associate_pairs_f64',
 ]
 
 
@@ -30,11 +30,13 @@ class OkpError(RuntimeError):
         super().__init__(f"{where}: {_abi.ERRORS.get(code, code)} ({strerror(code)})")
 
 
-def build(verbose=False, tuning=False):
+def build(verbose=False, tuning=False, output=None):
     """Compile csrc/okp_api.cu for sm_100a into libokp.so (nvcc cross-compiles without a GPU).
     tuning=True adds -DOKP_TUNING_KNOBS: the OKP_* environment variables of tools/sweep_k1.py override the launch-plan
-    constants (the shipped library reads no environment)."""
+    constants (the shipped library reads no environment). output: write the library there instead of libokp.so (the sweep
+    tools build libokp_tuning.so beside the shipped one and point LIBRARY_PATH at it before the first lib() call)."""
     import subprocess
+    target = LIBRARY_PATH if output is None else output
     src = os.path.join(_HERE, 'csrc', 'okp_api.cu')
     # the host side of the sparse transfer is plain C++ (OpenMP; its AVX2 loop is a run-time-dispatched target function,
     # so no -mavx2 here and the file also builds on aarch64 hosts): g++ compiles it, nvcc links it in
@@ -45,7 +47,7 @@ def build(verbose=False, tuning=False):
     if host.returncode != 0:
         raise RuntimeError("g++ failed:\n" + host.stdout + host.stderr)
     cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
-           '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static', '-o', LIBRARY_PATH, src, host_obj, '-lgomp']
+           '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static', '-o', target, src, host_obj, '-lgomp']
     if tuning:
         cmd.insert(1, '-DOKP_TUNING_KNOBS')
     if verbose:
@@ -54,7 +56,7 @@ def build(verbose=False, tuning=False):
     result = subprocess.run(cmd, capture_output=True, text=True)
     if result.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + result.stdout + result.stderr)
-    with open(STAMP_PATH, 'w') as handle:
+    with open(target + '.stamp', 'w') as handle:
         handle.write(_source_digest() + ('\ntuning' if tuning else '') + '\n')
     return result.stdout + result.stderr
 
@@ -90,7 +92,7 @@ def lib():
     if not os.path.exists(LIBRARY_PATH):
         raise ImportError(f"{LIBRARY_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU fallback for the decode path)")
-    if needs_build():
+    if LIBRARY_PATH.endswith('libokp.so') and needs_build():
         import warnings
         warnings.warn(f"{LIBRARY_PATH} is older than its sources (csrc/, include/okp.h): rebuild it with "
                       "`python -c 'import __graft_entry__ as g; g.build()'`", RuntimeWarning, stacklevel=2)
@@ -138,6 +140,10 @@ def lib():
     L.okp_reprojection_filter_f64.argtypes = [vp, vp, vp, vp, P(_abi.OkpCamera), i32, i32, dbl, vp, vp]
     L.okp_triangulate_robust_f64.restype = i32
     L.okp_triangulate_robust_f64.argtypes = [vp, vp, vp, P(_abi.OkpCamera), i32, i32, dbl, i32, vp, vp, vp, vp]
+    L.okp_triangulate_tracks_f64.restype = i32
+    L.okp_triangulate_tracks_f64.argtypes = [vp, vp, vp, P(_abi.OkpCamera), i32, i32, i32, dbl, i32, vp, vp, vp, vp]
+    L.okp_associate_pairs_f64.restype = i32
+    L.okp_associate_pairs_f64.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, dbl, vp, vp, vp]
     L.okp_correct_matches_f64.restype = i32
     L.okp_correct_matches_f64.argtypes = [P(dbl), vp, vp, i32, i32, vp, vp, vp]
     L.okp_stereo_associate_f64.restype = i32

@@ -73,7 +73,9 @@ int check_shape(int N, int C, int H, int W) {
     return OKP_OK;
 }
 
-inline int overflow_grid(int maps) { return (maps + 255) / 256 < kSmCount ? (maps + 255) / 256 : kSmCount; }
+// CTAs of the overflow fix-up and the maps each of them owns (okp_peaks_overflow_kernel)
+inline int overflow_grid(int maps) { return maps < OKP_OVERFLOW_CTAS ? maps : OKP_OVERFLOW_CTAS; }
+inline int overflow_maps_per_cta(int maps) { return (maps + overflow_grid(maps) - 1) / overflow_grid(maps); }
 
 // tile lists: one per (map, tile) for the generic kernels, one per (overflow CTA, tile) for the strip path
 size_t workspace_for(const PeakPlan& p, int maps, int K, bool strip) {
@@ -157,7 +159,7 @@ int launch_overflow(const T* heat_dev, const PeakCall& call, int maps, const Okp
     auto kernel = okp_peaks_overflow_kernel<256, T>;
     OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)call.plan.smem_bytes));
     kernel<<<overflow_grid(maps), 256, call.plan.smem_bytes, s>>>(heat_dev, call.plan.geo, params->threshold, params->max_peaks,
-                                                                   call.tile_count, call.tile_peaks, *tables);
+                                                                   overflow_maps_per_cta(maps), call.tile_count, call.tile_peaks, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }
@@ -254,9 +256,8 @@ int make_group_args(const void* depth_dev, const void* centers_dev, int N, int C
     a->N = N; a->C = C; a->H = H; a->W = W; a->S = S; a->P = P;
     a->have_camera = camera != nullptr;
     const int K = params->max_peaks, O = params->max_objects;
-    a->stash = 1;
-    size_t per_frame = okp_group_smem_bytes(C, K, O, S, true);
-    if (per_frame > 160 * 1024) { a->stash = 0; per_frame = okp_group_smem_bytes(C, K, O, S, false); }
+    const size_t per_frame = okp_group_smem_bytes(C, K, O);
+    if (per_frame > 200 * 1024) return OKP_E_CAPACITY;
     a->frame_smem_bytes = (int)per_frame;
     return convert_sink(sink, O, C, P, &a->sinks);
 }
@@ -472,7 +473,22 @@ int okp_triangulate_robust_f64(const double* obs_dev, uint8_t* valid_dev, const 
     if (!obs_dev || !poses_dev || !camera || !out_dev || !err_dev) return OKP_E_NULL;
     const size_t smem = sizeof(double) * 24 * (size_t)V;
     okp_triangulate_robust_kernel<<<(P + 127) / 128, 128, smem, (cudaStream_t)stream>>>(
-        obs_dev, valid_dev, poses_dev, *camera, P, V, max_error_px, max_rounds, out_dev, err_dev, dropped_dev);
+        obs_dev, valid_dev, poses_dev, *camera, P, V, max_error_px, max_rounds, out_dev, err_dev, dropped_dev, 0);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_triangulate_tracks_f64(const double* obs_dev, uint8_t* valid_dev, const double* poses_dev,
+                               const OkpCamera* camera, int G, int Pg, int V, double max_error_px, int max_rounds,
+                               double* out_dev, double* err_dev, int32_t* dropped_dev, void* stream) {
+    if (G < 0 || Pg < 1 || V < 1 || V > OKP_MAX_VIEWS || max_rounds < 0 || G > 65535) return OKP_E_SHAPE;
+    if ((long long)G * Pg > 0x7fffffffLL) return OKP_E_SHAPE;
+    if (G == 0) return OKP_OK;
+    if (!obs_dev || !poses_dev || !camera || !out_dev || !err_dev) return OKP_E_NULL;
+    const size_t smem = sizeof(double) * 24 * (size_t)V;
+    const int threads = Pg < 128 ? (Pg + 31) / 32 * 32 : 128;
+    okp_triangulate_robust_kernel<<<dim3((Pg + threads - 1) / threads, G), threads, smem, (cudaStream_t)stream>>>(
+        obs_dev, valid_dev, poses_dev, *camera, G * Pg, V, max_error_px, max_rounds, out_dev, err_dev, dropped_dev, Pg);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }
@@ -499,7 +515,22 @@ int okp_stereo_associate_f64(const double* F, const double* left_dev, const int3
     OkpMat3 Fm;
     for (int i = 0; i < 9; ++i) Fm.m[i] = F[i];
     const size_t smem = sizeof(double) * (size_t)max_left * max_right;
-    okp_associate_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(Fm, left_dev, n_left_dev, right_dev, n_right_dev,
+    okp_associate_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(Fm, nullptr, left_dev, n_left_dev, right_dev, n_right_dev,
+                                                               max_left, max_right, max_distance_px, match_dev, cost_dev);
+    OKP_CUDA_CHECK(cudaGetLastError());
+    return OKP_OK;
+}
+
+int okp_associate_pairs_f64(const double* F_dev, const double* left_dev, const int32_t* n_left_dev, const double* right_dev,
+                            const int32_t* n_right_dev, int B, int max_left, int max_right, double max_distance_px,
+                            int32_t* match_dev, double* cost_dev, void* stream) {
+    if (B < 0 || max_left < 1 || max_right < 1 || max_left > OKP_ASSOC_MAX || max_right > OKP_ASSOC_MAX) return OKP_E_SHAPE;
+    if (B == 0) return OKP_OK;
+    if (!F_dev || !left_dev || !n_left_dev || !right_dev || !n_right_dev || !match_dev || !cost_dev) return OKP_E_NULL;
+    OkpMat3 unused;
+    memset(&unused, 0, sizeof(unused));
+    const size_t smem = sizeof(double) * (size_t)max_left * max_right;
+    okp_associate_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(unused, F_dev, left_dev, n_left_dev, right_dev, n_right_dev,
                                                                max_left, max_right, max_distance_px, match_dev, cost_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;

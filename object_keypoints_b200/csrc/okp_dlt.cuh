@@ -138,9 +138,12 @@ __global__ void __launch_bounds__(128)
 okp_triangulate_robust_kernel(const double* __restrict__ obs, uint8_t* __restrict__ valid,
                               const double* __restrict__ poses, OkpCamera cam, int P, int V, double max_error,
                               int max_rounds, double* __restrict__ out, double* __restrict__ err,
-                              int32_t* __restrict__ dropped) {
+                              int32_t* __restrict__ dropped, int group_points) {
     extern __shared__ double s_pose[];                 // [V][12] world -> camera, then [V][12] K * pose
     double* s_proj = s_pose + 12 * V;
+    // group_points > 0: the points come in groups of that many, each with its own V poses (the 16 frames a track of a
+    // moving camera was seen from); blockIdx.y is the group. 0: one pose set for every point.
+    if (group_points > 0) poses += (size_t)blockIdx.y * V * 16;
     for (int i = threadIdx.x; i < V * 12; i += blockDim.x) s_pose[i] = poses[(i / 12) * 16 + (i % 12)];
     __syncthreads();
     for (int i = threadIdx.x; i < V * 12; i += blockDim.x) {          // camera_utils.py:125-130: K @ T[:3]
@@ -149,7 +152,11 @@ okp_triangulate_robust_kernel(const double* __restrict__ obs, uint8_t* __restric
         s_proj[i] = r == 0 ? cam.fx * T[c] + cam.cx * T[8 + c] : (r == 1 ? cam.fy * T[4 + c] + cam.cy * T[8 + c] : T[8 + c]);
     }
     __syncthreads();
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (group_points > 0) {
+        if (p >= group_points) return;
+        p += blockIdx.y * group_points;
+    }
     if (p >= P) return;
     unsigned long long mask = 0;
     for (int v = 0; v < V; ++v)

@@ -100,18 +100,15 @@ struct OkpGroupArgs {
     int S;                          // max(1, max(keypoint_config))
     int P;                          // points per object in a record: 1 + sum(keypoint_config)
     int have_camera;
-    int stash;                      // kept keypoints are also held in shared memory for the 3D lift
     int frame_smem_bytes;           // okp_group_smem_bytes()
 };
 
-// Shared-memory bytes ONE frame (= one warp) of the grouping needs; `stash` = the kept keypoints are also
-// held in shared memory for the 3D lift (dropped when the worst-case capacities would not fit).
-static inline size_t okp_group_smem_bytes(int C, int K, int O, int S, bool stash) {
+// Shared-memory bytes ONE frame (= one warp) of the grouping needs.
+static inline size_t okp_group_smem_bytes(int C, int K, int O) {
     size_t bytes = (size_t)O * 2 * sizeof(double);                                                  // centres
-    bytes += (size_t)C * K * (2 * sizeof(double) + 2 * sizeof(float) + sizeof(float) + sizeof(int));
-    bytes += (size_t)O * C * sizeof(int);
-    if (stash) bytes += (size_t)O * C * S * 2 * sizeof(float);
-    bytes += (OKP_MAX_MAPS + 1) * sizeof(int);                                                      // counts, flags
+    bytes += (size_t)C * K * (2 * sizeof(double) + 2 * sizeof(float) + sizeof(float) + 2 * sizeof(int));
+    bytes += (size_t)O * C * sizeof(int) + (size_t)O * sizeof(int);
+    bytes += (2 * OKP_MAX_MAPS + 2) * sizeof(int);                                                  // counts, starts, flags
     return (bytes + 15) / 16 * 16;
 }
 
@@ -122,10 +119,12 @@ struct OkpGroupScratch {
     float* xy;                      // [C][K][2] centroid (x, y)        -- filled by the caller
     float* conf;                    // [C][K]                           -- filled by the caller
     int* obj;                       // [C][K]    object of a peak, -1 = none
-    int* kept;                      // [O][C]    keypoints kept per (object, map)
+    int* rank;                      // [C][K]    position of a spoke peak among the peaks of its (object, map)
+    int* assigned;                  // [O][C]    detections per (object, map)
+    int* nvotes;                    // [O]       votes per object
     int* counts;                    // [OKP_MAX_MAPS] min(peaks of the map, K) -- filled by the caller
+    int* start;                     // [OKP_MAX_MAPS + 1] prefix of counts: the frame's peaks as one compact list
     unsigned int* flags;            // [1]       OKP_FLAG_* seen so far     -- initialised by the caller
-    float* kept_xy;                 // [O][C][S][2] (only with stash)
 };
 
 __device__ __forceinline__ OkpGroupScratch okp_group_scratch(unsigned char* mine, int C, int K, int O) {
@@ -135,18 +134,31 @@ __device__ __forceinline__ OkpGroupScratch okp_group_scratch(unsigned char* mine
     g.xy = reinterpret_cast<float*>(g.vote + (size_t)C * K * 2);
     g.conf = g.xy + (size_t)C * K * 2;
     g.obj = reinterpret_cast<int*>(g.conf + (size_t)C * K);
-    g.kept = g.obj + (size_t)C * K;
-    g.counts = g.kept + (size_t)O * C;
-    g.flags = reinterpret_cast<unsigned int*>(g.counts + OKP_MAX_MAPS);
-    g.kept_xy = reinterpret_cast<float*>(g.flags + 1);
+    g.rank = g.obj + (size_t)C * K;
+    g.assigned = g.rank + (size_t)C * K;
+    g.nvotes = g.assigned + (size_t)O * C;
+    g.counts = g.nvotes + O;
+    g.start = g.counts + OKP_MAX_MAPS;
+    g.flags = reinterpret_cast<unsigned int*>(g.start + OKP_MAX_MAPS + 1);
     return g;
 }
 
-// Latency is what the grouping is made of (a frame is ~40 peaks, and every 3D lift is a serial float64
-// Newton + tan chain of a few microseconds): ONE WARP PER FRAME. Expects g.xy / g.conf / g.counts / g.flags to
-// hold the frame's peaks (raster order per map); every later phase works on shared memory, results leave as
-// fire-and-forget stores. Global round trips on the critical path: centre-vector gather -> depth gather.
-// No block-level barrier: warps are independent.
+// Grouping + 3D lift of ONE frame by ONE warp. Expects g.xy / g.conf / g.counts / g.flags to hold the frame's peaks
+// (raster order per map).
+//
+// Shape of the work (round 2). A frame is ~10-40 peaks; the first version of this routine gave a lane to every
+// (object), then every (object, map), then every (object, map, slot) and let it scan the peak lists -- ten active lanes
+// per instruction and, measured in the fused kernel, more issue slots for the per-object vote lists than for the float64
+// Newton iterations. Now the frame's peaks are ONE compact list (map-major, raster order inside a map = the order the
+// reference walks them in, pipeline.py:115-128) and a lane owns a PEAK:
+//   pass 1  spoke peaks: centre-vector gather, vote, nearest centre (squared distances; a square root only for the
+//           minimum and for distances within rounding of it, which decides np.argmin's first-minimum rule exactly);
+//           __match_any_sync over (object) and (object, map) gives every peak its slot in the object's vote list and
+//           its rank among the detections of its (object, map) without any scan;
+//   (o, c)  one lane per (object, map): counts, and the rare over-detection cases (arg-max confidence / clustering);
+//   pass 2  every peak that is kept writes its keypoint slot and lifts itself to 3D (Newton undistortion + tan in
+//           float64 -- two warp passes for 40 peaks instead of three over padded [O][C][S] slots).
+// Global round trips on the critical path: centre-vector gather -> depth gather. No block-level barrier.
 //   OkpDecodeParams.lean_tables == 0: every slot of the frame's object tables that is not written is reset (zero / -1),
 //                  as include/okp.h promises by default;
 //   lean_tables == 1: only the valid slots are written (the tables of a 64x64 frame are a quarter of its heatmap
@@ -154,8 +166,9 @@ __device__ __forceinline__ OkpGroupScratch okp_group_scratch(unsigned char* mine
 template <typename E>
 __device__ __forceinline__ void okp_group_frame(const int n, const int lane, const OkpGroupScratch& g, const OkpGroupArgs& a,
                                                 const OkpDecodeTables& t) {
-    const bool CLEAR = a.prm.lean_tables == 0;
     constexpr int THREADS = 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    const bool CLEAR = a.prm.lean_tables == 0;
     const int C = a.C, H = a.H, W = a.W, S = a.S;
     const int K = a.prm.max_peaks, O = a.prm.max_objects, V = a.prm.max_votes, T = C - 1;
     const size_t HW = (size_t)H * W;
@@ -164,6 +177,7 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
     const E* centers = reinterpret_cast<const E*>(a.centers);
     unsigned int& s_flags = *g.flags;
     const int* s_counts = g.counts;
+    const unsigned lt = (1u << lane) - 1u;
 
     const int n_center = s_counts[0];
     const int n_obj = n_center < O ? n_center : O;
@@ -175,14 +189,14 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
         for (int i = lane; i < oc; i += THREADS) { assigned[i] = 0; count[i] = 0; }
         int32_t* peak = t.kp_peak + (size_t)n * ocs;
         for (int i = lane; i < ocs; i += THREADS) peak[i] = -1;
-        float* xy = t.kp_xy + (size_t)n * ocs * 2;
-        for (int i = lane; i < ocs * 2; i += THREADS) xy[i] = 0.0f;
+        float2* xy = reinterpret_cast<float2*>(t.kp_xy) + (size_t)n * ocs;
+        for (int i = lane; i < ocs; i += THREADS) xy[i] = make_float2(0.0f, 0.0f);
         double* point = t.kp_point + (size_t)n * ocs * 3;
         for (int i = lane; i < ocs * 3; i += THREADS) point[i] = 0.0;
         int32_t* nv = t.n_votes + (size_t)n * O;
         for (int i = lane; i < O; i += THREADS) nv[i] = 0;
-        double* votes = t.votes + (size_t)n * O * V * 2;
-        for (int i = lane; i < O * V * 2; i += THREADS) votes[i] = 0.0;
+        double2* votes = reinterpret_cast<double2*>(t.votes) + (size_t)n * O * V;
+        for (int i = lane; i < O * V; i += THREADS) votes[i] = make_double2(0.0, 0.0);
     }
     if (n_center == 0) {                                   // pipeline.py:105-106
         if (lane == 0) {
@@ -192,99 +206,105 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
         }
         return;
     }
-    if (lane == 0 && n_center > O) atomicOr(&s_flags, OKP_FLAG_OBJECT_OVERFLOW);
+    if (lane == 0) {
+        if (n_center > O) atomicOr(&s_flags, OKP_FLAG_OBJECT_OVERFLOW);
+        int at = 0;
+        for (int c = 0; c < C; ++c) { g.start[c] = at; at += s_counts[c]; }
+        g.start[C] = at;
+    }
+    // ---- centre peaks become objects (pipeline.py:109-114) ----
+    for (int k = lane; k < n_center; k += THREADS) {
+        const int o = k < n_obj ? k : -1;
+        g.obj[k] = o;
+        if (o >= 0) { g.center[o][0] = (double)g.xy[2 * k]; g.center[o][1] = (double)g.xy[2 * k + 1]; }
+        t.peak_object[m0 * K + k] = o;
+    }
+    for (int i = lane; i < n_obj * C; i += THREADS) g.assigned[i] = 0;
+    for (int o = lane; o < n_obj; o += THREADS) g.nvotes[o] = 0;
+    __syncwarp();
+    const int total = g.start[C];
 
-    // ---- centre peaks become objects (pipeline.py:109-114); spoke peaks fetch their centre vector ----
-    for (int i = lane; i < C * K; i += THREADS) {
-        const int c = i / K, k = i - c * K;
-        if (k >= s_counts[c]) continue;
-        const size_t s = (m0 + c) * K + k;
-        const float px = g.xy[2 * i], py = g.xy[2 * i + 1];
-        if (c == 0) {
-            const int o = k < n_obj ? k : -1;
-            g.obj[i] = o;
-            if (o >= 0) { g.center[o][0] = (double)px; g.center[o][1] = (double)py; }
-            t.peak_object[s] = o;
-        } else {
+    // ---- pass 1: spoke peaks vote for a centre (pipeline.py:115-128); vote-list slots and (object, map) ranks ----
+    for (int base = g.start[1]; base < total; base += THREADS) {
+        const int idx = base + lane;
+        const bool active = idx < total;
+        int c = 1, i = 0, arg = -1;
+        double vx = 0.0, vy = 0.0;
+        if (active) {
+            while (idx >= g.start[c + 1]) ++c;
+            const int k = idx - g.start[c];
+            i = c * K + k;
+            const size_t s = (m0 + c) * K + k;
+            const float px = g.xy[2 * i], py = g.xy[2 * i + 1];
             const int xi = okp_clamp(__float2int_rn(px), 0, W - 1);       // np.round = half to even
             const int yi = okp_clamp(__float2int_rn(py), 0, H - 1);
             const E* cmap = centers + ((size_t)n * T + (c - 1)) * 2 * HW;
-            const double vx = ((double)xi + 0.5) + (double)okp_ld<E>(cmap + (size_t)yi * W + xi);
-            const double vy = ((double)yi + 0.5) + (double)okp_ld<E>(cmap + HW + (size_t)yi * W + xi);
+            vx = ((double)xi + 0.5) + (double)okp_ld<E>(cmap + (size_t)yi * W + xi);
+            vy = ((double)yi + 0.5) + (double)okp_ld<E>(cmap + HW + (size_t)yi * W + xi);
             g.vote[2 * i] = vx; g.vote[2 * i + 1] = vy;
             reinterpret_cast<double2*>(t.peak_vote)[s] = make_double2(vx, vy);
-        }
-    }
-    __syncwarp();
-
-    // ---- spoke peaks vote for a centre (pipeline.py:115-128) ----
-    for (int i = K + lane; i < C * K; i += THREADS) {
-        const int c = i / K, k = i - c * K;
-        if (k >= s_counts[c]) continue;
-        const double vx = g.vote[2 * i], vy = g.vote[2 * i + 1];
-        int arg = 0;
-        double dmin = 0.0;
-        for (int o = 0; o < n_obj; ++o) {
-            const double dx = g.center[o][0] - vx, dy = g.center[o][1] - vy;
-            const double d = sqrt(dx * dx + dy * dy);
-            if (o == 0 || d < dmin) { dmin = d; arg = o; }             // first minimum, like np.argmin
-        }
-        if (dmin > a.prm.outlier_distance) {
-            atomicOr(&s_flags, OKP_FLAG_OUTLIER_SKIPPED);              // the reference prints and skips
-            arg = -1;
-        }
-        g.obj[i] = arg;
-        t.peak_object[(m0 + c) * K + k] = arg;
-    }
-    __syncwarp();
-
-    // ---- votes per object, in assignment order (type-major, raster order inside a type) ----
-    for (int o = lane; o < n_obj; o += THREADS) {
-        const size_t ob = (size_t)n * O + o;
-        int nv = 0;
-        for (int c = 1; c < C; ++c) {
-            for (int k = 0; k < s_counts[c]; ++k) {
-                if (g.obj[c * K + k] != o) continue;
-                if (nv < V) {
-                    reinterpret_cast<double2*>(t.votes)[ob * V + nv] = make_double2(g.vote[(c * K + k) * 2], g.vote[(c * K + k) * 2 + 1]);
-                } else {
-                    atomicOr(&s_flags, OKP_FLAG_VOTE_OVERFLOW);
-                }
-                ++nv;
+            // nearest centre = first minimum of sqrt(d2) like np.argmin over np.linalg.norm. sqrt is monotone, so the
+            // minimum is sqrt(min d2); it is attained by every object whose d2 rounds to the same square root, i.e. whose
+            // d2 lies within a few ulp of the minimum: only those need their own square root
+            double m2 = 0.0;
+            for (int o = 0; o < n_obj; ++o) {
+                const double dx = g.center[o][0] - vx, dy = g.center[o][1] - vy;
+                const double d2 = dx * dx + dy * dy;
+                if (o == 0 || d2 < m2) m2 = d2;
             }
+            const double dmin = sqrt(m2);
+            const double near = m2 * (1.0 + 1e-15);
+            for (int o = 0; o < n_obj; ++o) {
+                const double dx = g.center[o][0] - vx, dy = g.center[o][1] - vy;
+                const double d2 = dx * dx + dy * dy;
+                if (d2 == m2 || (d2 <= near && sqrt(d2) == dmin)) { arg = o; break; }
+            }
+            if (dmin > a.prm.outlier_distance) {
+                atomicOr(&s_flags, OKP_FLAG_OUTLIER_SKIPPED);              // the reference prints and skips
+                arg = -1;
+            }
+            g.obj[i] = arg;
+            t.peak_object[s] = arg;
         }
-        t.n_votes[ob] = nv;
+        const bool member = active && arg >= 0;
+        const unsigned same_o = __match_any_sync(FULL, member ? arg : (int)(0x80000000u | (unsigned)lane));
+        const unsigned same_oc = __match_any_sync(FULL, member ? ((c << 8) | arg) : (int)(0x80000000u | (unsigned)lane));
+        int r_o = 0, r_oc = 0;
+        if (member) {
+            r_o = __popc(same_o & lt);
+            r_oc = __popc(same_oc & lt);
+            const int slot = g.nvotes[arg] + r_o;                          // assignment order: map-major, raster inside a map
+            if (slot < V) reinterpret_cast<double2*>(t.votes)[((size_t)n * O + arg) * V + slot] = make_double2(vx, vy);
+            else atomicOr(&s_flags, OKP_FLAG_VOTE_OVERFLOW);
+            g.rank[i] = g.assigned[arg * C + c] + r_oc;
+        }
+        __syncwarp();
+        if (member) {
+            if (r_o == 0) g.nvotes[arg] += __popc(same_o);
+            if (r_oc == 0) g.assigned[arg * C + c] += __popc(same_oc);
+        }
+        __syncwarp();
     }
+    for (int o = lane; o < n_obj; o += THREADS) t.n_votes[(size_t)n * O + o] = g.nvotes[o];
 
-    // ---- per (object, map): resolve over-detection ----
-    float* kept_xy = a.stash ? g.kept_xy : t.kp_xy + (size_t)n * O * C * S * 2;
+    // ---- per (object, map): counts; the over-detection cases are resolved (and lifted) here, one lane each ----
     for (int i = lane; i < n_obj * C; i += THREADS) {
         const int o = i / C, c = i - o * C;
         const size_t oc = ((size_t)n * O + o) * C + c;
         const int limit = a.config.cfg[c];
-        const int* obj = g.obj + c * K;
-        const float* xy = g.xy + (size_t)c * K * 2;
-        int cnt = 0;
-        for (int k = 0; k < s_counts[c]; ++k) cnt += (obj[k] == o);
+        const int cnt = c == 0 ? 1 : g.assigned[i];
         t.kp_assigned[oc] = cnt;
-        g.kept[i] = 0;
-        if (cnt == 0) {                                    // pipeline.py:150-152: empty array
-            if (!CLEAR) t.kp_count[oc] = 0;
-            okp_record_count(a.sinks, n, O, C, o, c, 0);
+        if (cnt <= limit) {                                // everything is kept (pass 2); cnt == 0: pipeline.py:150-152
+            if (cnt > 0 || !CLEAR) t.kp_count[oc] = cnt;
+            okp_record_count(a.sinks, n, O, C, o, c, cnt);
             continue;
         }
+        const int* obj = g.obj + c * K;
+        const float* xy = g.xy + (size_t)c * K * 2;
         float pts[OKP_MAX_SLOTS][2];
         int ids[OKP_MAX_SLOTS];
         int kept = 0;
-        if (cnt <= limit) {
-            for (int k = 0; k < s_counts[c]; ++k)
-                if (obj[k] == o) {
-                    ids[kept] = k;
-                    pts[kept][0] = xy[2 * k];
-                    pts[kept][1] = xy[2 * k + 1];
-                    ++kept;
-                }
-        } else if (limit == 1) {                           // pipeline.py:139-142: most confident detection
+        if (limit == 1) {                                  // pipeline.py:139-142: most confident detection
             int arg = -1;
             float best = 0.0f;
             for (int k = 0; k < s_counts[c]; ++k)
@@ -309,29 +329,46 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
         }
         t.kp_count[oc] = kept;
         okp_record_count(a.sinks, n, O, C, o, c, kept);
-        g.kept[i] = kept;
         for (int s = 0; s < kept; ++s) {
             t.kp_peak[oc * S + s] = ids[s];
             reinterpret_cast<float2*>(t.kp_xy)[oc * S + s] = make_float2(pts[s][0], pts[s][1]);
-            if (a.stash) { g.kept_xy[((size_t)i * S + s) * 2] = pts[s][0]; g.kept_xy[((size_t)i * S + s) * 2 + 1] = pts[s][1]; }
+            double p3[3] = {0.0, 0.0, 0.0};
+            if (a.have_camera) {
+                okp_detection_to_point(pts[s][0], pts[s][1], depth + (m0 + c) * HW, H, W, a.cam, a.prm.compat_clip_bug, p3);
+                double* out = t.kp_point + (oc * S + s) * 3;
+                out[0] = p3[0]; out[1] = p3[1]; out[2] = p3[2];
+            }
+            okp_record_point(a.sinks, n, O, C, a.P, a.config, o, c, s, p3);
         }
     }
-    __syncwarp();                                       // also makes the kp_xy stores visible to the warp (no stash)
 
-    // ---- lift every kept keypoint to 3D, one thread each (pipeline.py:164-171, 189-199); the point goes to the
-    // table and, when the caller asked for them, into the compact record of every sink (okp_records.cuh) ----
-    for (int i = lane; i < n_obj * C * S; i += THREADS) {
-        const int ocl = i / S, s = i - ocl * S;        // ocl = o * C + c inside the frame
-        if (s >= g.kept[ocl]) continue;
-        const int o = ocl / C, c = ocl - o * C;
+    // ---- pass 2: every kept peak writes its keypoint slot and lifts itself to 3D (pipeline.py:164-171, 189-199); the
+    // point goes to the table and, when the caller asked for them, into the compact record of every sink ----
+    for (int base = 0; base < total; base += THREADS) {
+        const int idx = base + lane;
+        if (idx >= total) continue;
+        int c = 0;
+        while (idx >= g.start[c + 1]) ++c;
+        const int k = idx - g.start[c];
+        const int i = c * K + k;
+        const int o = g.obj[i];
+        if (o < 0) continue;
+        int slot = 0;
+        if (c > 0) {
+            if (g.assigned[o * C + c] > a.config.cfg[c]) continue;     // resolved above
+            slot = g.rank[i];
+        }
+        const size_t ocs = (((size_t)n * O + o) * C + c) * S + slot;
+        const float px = g.xy[2 * i], py = g.xy[2 * i + 1];
+        t.kp_peak[ocs] = k;
+        reinterpret_cast<float2*>(t.kp_xy)[ocs] = make_float2(px, py);
         double p3[3] = {0.0, 0.0, 0.0};
         if (a.have_camera) {
-            okp_detection_to_point(kept_xy[((size_t)ocl * S + s) * 2], kept_xy[((size_t)ocl * S + s) * 2 + 1],
-                                   depth + (m0 + c) * HW, H, W, a.cam, a.prm.compat_clip_bug, p3);
-            double* out = t.kp_point + (((size_t)n * O * C + ocl) * S + s) * 3;
+            okp_detection_to_point(px, py, depth + (m0 + c) * HW, H, W, a.cam, a.prm.compat_clip_bug, p3);
+            double* out = t.kp_point + ocs * 3;
             out[0] = p3[0]; out[1] = p3[1]; out[2] = p3[2];
         }
-        okp_record_point(a.sinks, n, O, C, a.P, a.config, o, c, s, p3);
+        okp_record_point(a.sinks, n, O, C, a.P, a.config, o, c, slot, p3);
     }
     __syncwarp();
     if (lane == 0) {

@@ -254,26 +254,33 @@ okp_merge_peaks_kernel(const int32_t* __restrict__ tile_count, const OkpPeakReco
 }
 
 // ---------------------------------------------------------------------------------------------
-// Overflow path of the strip kernel (okp_peaks_strip.cuh): maps with more peaks than the table
-// holds need the FIRST K in raster order. Every CTA looks at a slice of peak_count; a map that
-// overflowed is redone tile by tile with the generic routine (tile lists in the CTA's own slice of
-// the workspace) and merged by warp 0. With no
-// overflow the kernel is one coalesced read of peak_count.
+// Overflow path of the stream kernel (okp_peaks_stream.cuh): maps with more peaks than the table
+// holds need the FIRST K in raster order (and the true count), maps with negative / NaN values the exact
+// arithmetic. Every CTA owns a contiguous slice of `per_cta` maps: one coalesced look at their peak_count;
+// the maps of the slice that overflowed are redone tile by tile with the generic routine (tile lists in the
+// CTA's own slice of the workspace) and merged by warp 0. With no overflow the kernel is that one look.
+// The slices are small (maps / min(maps, OKP_OVERFLOW_CTAS)), so a batch in which EVERY map overflows -- an
+// untrained network, BASELINE config 5 -- is spread over the whole GPU (round 1 used 256-map slices: 768 such
+// maps ran on three CTAs).
 // ---------------------------------------------------------------------------------------------
+#define OKP_OVERFLOW_CTAS 592                 // 4 per SM
+
 template <int THREADS, typename T>
 __global__ void __launch_bounds__(THREADS)
-okp_peaks_overflow_kernel(const T* __restrict__ heat, OkpTileGeometry g, float threshold, int K,
+okp_peaks_overflow_kernel(const T* __restrict__ heat, OkpTileGeometry g, float threshold, int K, int per_cta,
                           int32_t* __restrict__ tile_count, OkpPeakRecord* __restrict__ tile_peaks, OkpDecodeTables t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_count;
     __shared__ int s_over[THREADS];
     const int tiles_per_map = g.tiles_y * g.tiles_x;
-    for (int base = blockIdx.x * THREADS; base < g.maps; base += gridDim.x * THREADS) {
+    const int first = blockIdx.x * per_cta;
+    const int last = first + per_cta < g.maps ? first + per_cta : g.maps;
+    for (int base = first; base < last; base += THREADS) {
         const int mine = base + threadIdx.x;
-        const int over = (mine < g.maps && t.peak_count[mine] > K) ? 1 : 0;
+        const int over = (mine < last && t.peak_count[mine] > K) ? 1 : 0;
         s_over[threadIdx.x] = over;
         if (!__syncthreads_or(over)) continue;
-        for (int i = 0; i < THREADS && base + i < g.maps; ++i) {
+        for (int i = 0; i < THREADS && base + i < last; ++i) {
             if (!s_over[i]) continue;                     // uniform: shared flag
             const int m = base + i;
             for (int tile = 0; tile < tiles_per_map; ++tile)

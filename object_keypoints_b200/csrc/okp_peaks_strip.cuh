@@ -117,6 +117,7 @@ __device__ __forceinline__ void okp_mbar_wait(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!okp_mbar_try_wait_suspend(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();
+        __nanosleep(20);                                  // a waiting warp must not eat the issue slots of the working ones
     }
 }
 __device__ __forceinline__ void okp_mbar_arrive(uint64_t* bar) {

@@ -280,14 +280,16 @@ okp_correct_matches_kernel(OkpMat3 F, const double* __restrict__ left, const dou
 #define OKP_ASSOC_MAX 64
 
 __global__ void __launch_bounds__(32)
-okp_associate_kernel(OkpMat3 Fm, const double* __restrict__ left, const int32_t* __restrict__ n_left,
-                     const double* __restrict__ right, const int32_t* __restrict__ n_right, int ML, int MR,
-                     double max_distance, int32_t* __restrict__ match, double* __restrict__ match_cost) {
+okp_associate_kernel(OkpMat3 Fm, const double* __restrict__ F_pairs, const double* __restrict__ left,
+                     const int32_t* __restrict__ n_left, const double* __restrict__ right,
+                     const int32_t* __restrict__ n_right, int ML, int MR, double max_distance,
+                     int32_t* __restrict__ match, double* __restrict__ match_cost) {
     extern __shared__ double s_cost[];               // [ML][MR]
     __shared__ unsigned long long s_used_left, s_used_right;
     const int b = blockIdx.x, lane = threadIdx.x;
     const int nl = okp_clamp(n_left[b], 0, ML), nr = okp_clamp(n_right[b], 0, MR);
-    const double* F = Fm.m;
+    // one F for every pair (a stereo rig) or one per pair (two frames of a moving camera: scripts/label.py:285-305)
+    const double* F = F_pairs ? F_pairs + 9 * (size_t)b : Fm.m;
     const double* L = left + (size_t)b * ML * 2;
     const double* R = right + (size_t)b * MR * 2;
     for (int e = lane; e < nl * nr; e += 32) {

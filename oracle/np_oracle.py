@@ -673,3 +673,4 @@ def extract_peak_tables(heat, threshold=0.5, nms_size=5, use_box_sum=True, top_k
                 out['peak_xy'][n, c, k] = xy
                 out['peak_conf'][n, c, k] = conf
     return out
+
