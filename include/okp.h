@@ -89,6 +89,11 @@ typedef struct OkpDecodeParams {
                                  everything else keeps whatever the buffer held. For callers that read by the counts (the
                                  tables of a 64x64 frame are a quarter of its heatmap bytes: clearing them is the decode's
                                  largest DRAM write). */
+    int32_t single_pass;      /* okp_decode_*: 0 (default) = two launches, the peak kernel and then the grouping / 3D lift with
+                                 one warp per frame; 1 = ONE streaming pass, the grouping runs in the peak kernel's epilogue
+                                 warps straight from the sorted peak list in shared memory (no second kernel re-reads the
+                                 peak tables). Same tables either way; the two-launch form is the faster one on a B200
+                                 (DESIGN.md section 3), the single pass saves a launch when N is small. */
 } OkpDecodeParams;
 
 /* Fixed-capacity structure-of-arrays output. N frames, C maps, K = max_peaks, O = max_objects,

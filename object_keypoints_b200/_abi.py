@@ -36,7 +36,8 @@ class OkpDecodeParams(ctypes.Structure):
     _fields_ = [('threshold', ctypes.c_float), ('nms_size', ctypes.c_int32), ('box_sum', ctypes.c_int32),
                 ('compat_clip_bug', ctypes.c_int32), ('outlier_distance', ctypes.c_double),
                 ('max_peaks', ctypes.c_int32), ('max_objects', ctypes.c_int32), ('max_votes', ctypes.c_int32),
-                ('kmeans_iterations', ctypes.c_int32), ('top_k', ctypes.c_int32), ('lean_tables', ctypes.c_int32)]
+                ('kmeans_iterations', ctypes.c_int32), ('top_k', ctypes.c_int32), ('lean_tables', ctypes.c_int32),
+                ('single_pass', ctypes.c_int32)]
 
 
 class OkpRecordSink(ctypes.Structure):
@@ -80,7 +81,8 @@ def table_shapes(N, C, keypoint_config, params):
 
 
 def make_params(threshold=0.5, outlier_distance=20.0, max_peaks=32, max_objects=16, max_votes=16,
-                compat_clip_bug=True, kmeans_iterations=16, nms_size=5, box_sum=True, top_k=0, lean_tables=False):
+                compat_clip_bug=True, kmeans_iterations=16, nms_size=5, box_sum=True, top_k=0, lean_tables=False,
+                single_pass=False):
     if not (1 <= max_peaks <= OKP_MAX_PEAKS):
         raise ValueError(f"max_peaks must be in [1, {OKP_MAX_PEAKS}]")
     if not (1 <= max_objects <= OKP_MAX_OBJECTS):
@@ -92,7 +94,8 @@ def make_params(threshold=0.5, outlier_distance=20.0, max_peaks=32, max_objects=
     return OkpDecodeParams(threshold=threshold, nms_size=int(nms_size), box_sum=int(bool(box_sum)), top_k=int(top_k),
                            compat_clip_bug=int(bool(compat_clip_bug)),
                            outlier_distance=outlier_distance, max_peaks=max_peaks, max_objects=max_objects,
-                           max_votes=max_votes, kmeans_iterations=kmeans_iterations, lean_tables=int(bool(lean_tables)))
+                           max_votes=max_votes, kmeans_iterations=kmeans_iterations, lean_tables=int(bool(lean_tables)),
+                           single_pass=int(bool(single_pass)))
 
 
 def pack_camera(camera):

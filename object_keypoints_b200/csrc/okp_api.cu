@@ -8,6 +8,7 @@
 #include "okp_peaks.cuh"
 #include "okp_peaks_strip.cuh"
 #include "okp_peaks_stream.cuh"
+#include "okp_peaks_tile.cuh"
 #include "okp_geometry.cuh"
 #include "okp_group.cuh"
 #include "okp_dlt.cuh"
@@ -22,7 +23,8 @@ namespace {
 constexpr int kSmCount = 148;            // B200: 2 dies x 74 SMs
 
 struct PeakPlan {
-    bool strip;                          // tuned strip kernel + overflow path, else generic tile kernel + merge
+    bool strip;                          // tuned TMA kernel (tile or stream) + overflow path, else generic tile kernel + merge
+    bool tile;                           // the sparse tile kernel (okp_peaks_tile.cuh) covers the call, else the stream kernel
     OkpStripPlan sp;
     OkpTileGeometry geo;                 // generic tiles (also the strip kernel's overflow path)
     size_t smem_bytes;
@@ -37,7 +39,10 @@ PeakPlan plan_peaks(int maps, int H, int W, int K, int esize, const OkpDecodePar
     memset(&p, 0, sizeof(p));
     // the tuned TMA kernels implement the reference's configuration only (5x5 window on the 5x5 box sum)
     const bool reference_mode = prm->nms_size == 5 && prm->box_sum == 1;
-    p.strip = reference_mode && okp_strip_plan(maps, H, W, K, esize, &p.sp);
+    OkpTilePlan probe;
+    p.tile = reference_mode && okp_env_int("OKP_PEAKS_TILE", 0, 1, 0) != 0 &&
+             okp_tile_plan(maps, 1, H, W, K, esize, prm->threshold, 0, prm->lean_tables, &probe);
+    p.strip = p.tile || (reference_mode && okp_strip_plan(maps, H, W, K, esize, &p.sp));
     p.geo.H = H; p.geo.W = W; p.geo.maps = maps;
     p.geo.radius = prm->nms_size / 2; p.geo.box_sum = prm->box_sum ? 1 : 0;
     p.geo.TW = W <= 64 ? round_up(W, 8) : 64;
@@ -64,6 +69,7 @@ int check_params(const OkpDecodeParams* prm) {
     if ((prm->nms_size != 5 && prm->nms_size != 3) || (prm->box_sum != 0 && prm->box_sum != 1)) return OKP_E_UNSUPPORTED;
     if (prm->top_k < 0 || prm->top_k > prm->max_peaks) return OKP_E_CAPACITY;
     if (prm->lean_tables != 0 && prm->lean_tables != 1) return OKP_E_UNSUPPORTED;
+    if (prm->single_pass != 0 && prm->single_pass != 1) return OKP_E_UNSUPPORTED;
     return OKP_OK;
 }
 
@@ -181,9 +187,15 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     const PeakPlan& p = call.plan;
 
     if (call.strip) {
-        OkpStreamPlan stream_plan;
-        if (!okp_stream_plan(maps, C, H, W, K, (int)sizeof(T), 0, params->lean_tables, &stream_plan)) return OKP_E_UNSUPPORTED;
-        rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, s);
+        if (p.tile) {
+            OkpTilePlan tile_plan;
+            if (!okp_tile_plan(maps, C, H, W, K, (int)sizeof(T), params->threshold, 0, params->lean_tables, &tile_plan)) return OKP_E_UNSUPPORTED;
+            rc = okp_tile_launch<T>(heat_dev, tile_plan, params->threshold, *tables, nullptr, s);
+        } else {
+            OkpStreamPlan stream_plan;
+            if (!okp_stream_plan(maps, C, H, W, K, (int)sizeof(T), 0, params->lean_tables, &stream_plan)) return OKP_E_UNSUPPORTED;
+            rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, s);
+        }
         if (rc != OKP_OK) return rc;
         rc = launch_overflow<T>(heat_dev, call, maps, params, tables, s);
         if (rc != OKP_OK) return rc;
@@ -310,15 +322,25 @@ int decode(const T* heat_dev, const T* depth_dev, const T* centers_dev, int N, i
     if (rc != OKP_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     OkpStreamPlan stream_plan;
-    const bool fused = call.strip && params->top_k == 0 &&
-                       okp_stream_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), a.frame_smem_bytes,
-                                       params->lean_tables, &stream_plan) && stream_plan.F > 0;
+    OkpTilePlan tile_plan;
+    // One fused pass (grouping in the peak kernel's epilogue warps) or two launches (peaks, then one warp per frame): the
+    // grouping is a chain of latencies (gathers from HBM, float64 Newton + tan), and a launch of its own overlaps thousands
+    // of them where the fused form has two epilogue warps per SM. Measured (profiles/r02c_fused_vs_split.txt): the split
+    // form is faster at every size, so it is the default; OkpDecodeParams.single_pass asks for the fused one.
+    bool fused = params->single_pass != 0 && call.strip && params->top_k == 0;
+    if (fused) {
+        fused = call.plan.tile ? okp_tile_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), params->threshold, a.frame_smem_bytes,
+                                               params->lean_tables, &tile_plan) && tile_plan.sp.F > 0
+                               : okp_stream_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), a.frame_smem_bytes,
+                                                 params->lean_tables, &stream_plan) && stream_plan.F > 0;
+    }
     if (!fused) {
         rc = extract_peaks<T>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
         if (rc != OKP_OK) return rc;
         return launch_group<T>(a, 0, tables, s);
     }
-    rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, &a, s);
+    rc = call.plan.tile ? okp_tile_launch<T>(heat_dev, tile_plan, params->threshold, *tables, &a, s)
+                        : okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, &a, s);
     if (rc != OKP_OK) return rc;
     // fix-up launches: maps that overflowed the fast path are redone exactly, then their frames are grouped. With no such
     // map each is one read of peak_count / n_objects

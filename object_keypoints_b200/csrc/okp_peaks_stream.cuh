@@ -46,6 +46,235 @@ __device__ __forceinline__ void okp_named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// The epilogue warps' loop (shared by the stream kernel above and the tile kernel of okp_peaks_tile.cuh): one finished
+// candidate buffer at a time -- exact box sums from L2, undecided neighbours, raster ranks, table rows and, fused, the
+// frame's grouping and 3D lift. et: thread index among the sp.EW epilogue warps; stride: groups between two of this CTA's
+// groups (gridDim.x).
+template <typename T, bool FUSED>
+__device__ __forceinline__ void okp_stream_epilogue(unsigned char* smem, const OkpStreamPlan& sp, const T* __restrict__ heat,
+                                                    const float threshold, const OkpDecodeTables& t, const OkpGroupArgs& ga,
+                                                    const int et, const int my_groups) {
+    const OkpStripPlan& p = sp.s;
+    const int H = p.H, W = p.W;
+    OkpStripPeak* peaks = reinterpret_cast<OkpStripPeak*>(smem + sp.off_peaks);                // [M][PK]
+    uint32_t* items = reinterpret_cast<uint32_t*>(smem + sp.off_items);                        // [IC]
+    int* n_peaks = reinterpret_cast<int*>(smem + sp.off_misc);                                 // [M]
+    int* n_items = n_peaks + p.M;                                                              // [1]
+    int* cand_start = n_items + 1;                                                             // [M + 1] prefix of candidate counts
+    int* pend = cand_start + p.M + 1;                                                          // [M] fused: frame f is left to the fix-up launches
+    uint64_t* cand_full = reinterpret_cast<uint64_t*>(smem + sp.off_mbar) + 2 * OKP_STRIP_MAX_NS;
+    uint64_t* cand_free = cand_full + 2;
+    const int ethreads = sp.EW * 32;
+    for (int it = 0; it < my_groups; ++it) {
+        const int buf = it & 1;
+        const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
+        okp_mbar_wait(cand_full + buf, (uint32_t)((it >> 1) & 1));
+        OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]);
+        int* n_pending = reinterpret_cast<int*>(smem + sp.off_count[buf]);
+        int* redo = n_pending + p.M;
+
+        // candidates are few and sit at the front of each map's list: index them densely so that every
+        // lane has one (all loads of a pass in flight together) instead of walking M * PK mostly empty slots
+        if (et == 0) {
+            int at = 0;
+            for (int mm = 0; mm < p.M; ++mm) {
+                cand_start[mm] = at;
+                at += first_map + mm < p.maps ? okp_min(n_pending[mm], p.PK) : 0;
+            }
+            cand_start[p.M] = at;
+        }
+        okp_named_barrier(1, ethreads);
+        const int candidates = cand_start[p.M];
+
+        // A: exact box sum (the reference's raster-order adds) and centroid of every candidate
+        for (int idx = et; idx < candidates; idx += ethreads) {
+            int lo = 0, hi = p.M;                                 // last mm with cand_start[mm] <= idx
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
+            const int mm = lo, i = mm * p.PK + (idx - cand_start[mm]);
+            OkpStripPeak pk;
+            pk.key = -1; pk.score = 0.0f; pk.cx = 0.0f; pk.cy = 0.0f; pk.conf = 0.0f;
+            {
+                const OkpStripCandidate cd = pending[i];
+                const int y = cd.key / W, x = cd.key - y * W;
+                const T* src = heat + (size_t)(first_map + mm) * H * W;
+                float q[25];
+                // almost every candidate is an interior pixel: 25 unconditional loads at constant offsets
+                // (a fifth of the instructions of the border-checked form, which matters because the
+                // epilogue warps are latency-bound: profiles/r01m_k1_64x64_ncu.md)
+                const bool interior = y >= 2 && y + 2 < H && x >= 2 && x + 2 < W;
+                if (interior) {
+                    const T* corner = src + (size_t)(y - 2) * W + (x - 2);
+#pragma unroll
+                    for (int k = 0; k < 25; ++k) q[k] = okp_ld<T>(corner + (size_t)(k / 5) * W + k % 5);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 25; ++k) {
+                        const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+                        const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+                        q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;
+                    }
+                }
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 25; ++k) sum = __fadd_rn(sum, q[k]);
+                if (sum > threshold) {
+                    float sy = 0.0f, sx = 0.0f, spr = 0.0f;
+                    if (interior) {                           // same operations in the same order, nothing masked
+#pragma unroll
+                        for (int k = 0; k < 25; ++k) {
+                            sy = __fadd_rn(sy, __fmul_rn(q[k], (float)(y + k / 5 - 2)));
+                            sx = __fadd_rn(sx, __fmul_rn(q[k], (float)(x + k % 5 - 2)));
+                            spr = __fadd_rn(spr, q[k]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 25; ++k) {
+                            const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
+                            const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
+                            if (in) {
+                                sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
+                                sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
+                                spr = __fadd_rn(spr, q[k]);
+                            }
+                        }
+                    }
+                    pk.key = cd.key;
+                    pk.score = sum;
+                    pk.cx = __fdiv_rn(sx, spr);
+                    pk.cy = __fdiv_rn(sy, spr);
+                    pk.conf = spr;
+                    uint32_t ties = cd.ties;
+                    ties &= (y >= 2 ? 0x1Fu : 0u) | (y >= 1 ? 0x3E0u : 0u) | 0x6C00u | (y + 1 < H ? 0xF8000u : 0u) | (y + 2 < H ? 0x1F00000u : 0u);
+                    ties &= (x >= 2 ? 0x108421u : 0u) | (x >= 1 ? 0x210842u : 0u) | 0x421084u | (x + 1 < W ? 0x842108u : 0u) | (x + 2 < W ? 0x1084210u : 0u);
+                    if (ties) {
+                        const int at = atomicAdd(n_items, __popc(ties));
+                        if (at + __popc(ties) > p.IC) {
+                            redo[mm] = 1;
+                            for (int n = at; n < p.IC; ++n) items[n] = 0xFFFFFFFFu;
+                        } else {
+                            int n = at;
+                            while (ties) {
+                                const int k = __ffs(ties) - 1;
+                                ties &= ties - 1;
+                                items[n++] = ((uint32_t)i << 5) | (uint32_t)k;
+                            }
+                        }
+                    }
+                }
+            }
+            peaks[i] = pk;
+        }
+        okp_named_barrier(1, ethreads);
+
+        // B: undecided neighbours -- exact box sum against the candidate's
+        {
+            const int total_items = okp_min(*n_items, p.IC);
+            for (int n = et; n < total_items; n += ethreads) {
+                const uint32_t item = items[n];
+                if (item == 0xFFFFFFFFu) continue;
+                const int i = (int)(item >> 5), k = (int)(item & 31u);
+                const int mm = i / p.PK;
+                const int key = pending[i].key;
+                const int y = key / W, x = key - y * W;
+                const T* src = heat + (size_t)(first_map + mm) * H * W;
+                if (okp_exact_box_sum<T>(src, H, W, y + k / 5 - 2, x + k % 5 - 2) > peaks[i].score) peaks[i].key = -1;
+            }
+        }
+        okp_named_barrier(1, ethreads);
+        for (int idx = et; idx < candidates; idx += ethreads) {
+            int lo = 0, hi = p.M;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
+            if (peaks[lo * p.PK + (idx - cand_start[lo])].key >= 0) atomicAdd(n_peaks + lo, 1);
+        }
+        okp_named_barrier(1, ethreads);
+
+        // C: raster order (rank by key), final tables, unused slots cleared (not with lean tables). Fused: the sorted
+        // rows also go into the frame's grouping scratch, which is what phase D works from.
+        const int K = p.K;
+        for (int mm = 0; mm < p.M && first_map + mm < p.maps; ++mm) {
+            const int map = first_map + mm;
+            const int total = (redo[mm] || n_pending[mm] > p.PK) ? K + 1 : n_peaks[mm];
+            if (et == 0) {
+                t.peak_count[map] = total;
+                if (FUSED) {
+                    const int f = mm / sp.C, c = mm - f * sp.C;
+                    const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
+                                                                ga.prm.max_objects);
+                    g.counts[c] = total < K ? total : K;
+                    if (c == 0) *g.flags = 0;
+                    if (total > K) pend[f] = 1;
+                } else if (t.flags && map % sp.C == 0) {
+                    t.flags[map / sp.C] = 0;                 // a stale OKP_FLAG_GENERIC_PATH must not survive (okp_group_kernel keeps the bit)
+                }
+            }
+            if (total > K || sp.lean) continue;              // tables of an overflowing map are written by the overflow path
+            for (int slot = et; slot < K; slot += ethreads) {
+                const size_t dst = (size_t)map * K + slot;
+                t.peak_object[dst] = -1;
+                reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
+                if (slot >= total) {
+                    reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(-1, -1);
+                    t.peak_score[dst] = 0.0f;
+                    reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(0.0f, 0.0f);
+                    t.peak_conf[dst] = 0.0f;
+                }
+            }
+        }
+        for (int idx = et; idx < candidates; idx += ethreads) {
+            int lo = 0, hi = p.M;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
+            const int mm = lo, i = mm * p.PK + (idx - cand_start[mm]);
+            const OkpStripPeak pk = peaks[i];
+            if (pk.key < 0) continue;
+            if (redo[mm] || n_pending[mm] > p.PK || n_peaks[mm] > K) continue;
+            const OkpStripPeak* mine = peaks + (size_t)mm * p.PK;
+            const int np = n_pending[mm];
+            int rank = 0;
+            for (int j = 0; j < np; ++j) { const int kj = mine[j].key; rank += (kj >= 0 && kj < pk.key); }
+            const size_t dst = (size_t)(first_map + mm) * K + rank;
+            const int y = pk.key / W;
+            reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(y, pk.key - y * W);
+            t.peak_score[dst] = pk.score;
+            reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(pk.cx, pk.cy);
+            t.peak_conf[dst] = pk.conf;
+            if (sp.lean) {                                   // the row's assignment columns, which the clearing loop did not reset
+                t.peak_object[dst] = -1;
+                reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
+            }
+            if (FUSED) {
+                const int f = mm / sp.C, c = mm - f * sp.C;
+                const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
+                                                            ga.prm.max_objects);
+                g.xy[2 * (c * K + rank)] = pk.cx; g.xy[2 * (c * K + rank) + 1] = pk.cy;
+                g.conf[c * K + rank] = pk.conf;
+            }
+        }
+        okp_named_barrier(1, ethreads);
+        // hand the candidate buffer back, cleared: the compute warps never wait for the grouping below
+        for (int i = et; i < 2 * p.M; i += ethreads) n_pending[i] = 0;
+        for (int i = et; i < p.M + 1; i += ethreads) n_peaks[i] = 0;
+        okp_named_barrier(1, ethreads);
+        if ((et & 31) == 0) okp_mbar_arrive(cand_free + buf);
+
+        // D (fused): grouping + 3D lift + compact record, one warp per frame, from the sorted peak list in shared memory
+        if (FUSED) {
+            const int first_frame = first_map / sp.C;
+            for (int f = et >> 5; f < sp.F && first_frame + f < ga.N; f += sp.EW) {
+                const int n = first_frame + f;
+                if (pend[f]) {                               // okp_group_kernel keeps OKP_FLAG_GENERIC_PATH: not from this call
+                    if ((et & 31) == 0) { t.n_objects[n] = OKP_GROUP_PENDING; t.flags[n] = 0; }
+                } else {
+                    const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
+                                                                ga.prm.max_objects);
+                    okp_group_frame<T>(n, et & 31, g, ga, t);
+                }
+            }
+            okp_named_barrier(1, ethreads);                  // phase C of the next group rewrites the scratches
+            for (int i = et; i < p.M; i += ethreads) pend[i] = 0;
+        }
+    }
+}
+
 template <typename T, bool FUSED>
 // 96 registers: two CTAs of 320 threads per SM (__maxnreg__ and __launch_bounds__ exclude each other; the launch uses at
 // most OKP_STRIP_MAX_THREADS = 640 threads, which 96 registers also allow)
@@ -166,216 +395,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
         }
     } else {
         // ------------------------------- epilogue warps: one finished candidate buffer at a time ---------
-        const int et = tid - (compute_warps + 1) * 32;                // thread index among the epilogue warps
-        const int ethreads = sp.EW * 32;
-        for (int it = 0; it < my_groups; ++it) {
-            const int buf = it & 1;
-            const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
-            okp_mbar_wait(cand_full + buf, (uint32_t)((it >> 1) & 1));
-            OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]);
-            int* n_pending = reinterpret_cast<int*>(smem + sp.off_count[buf]);
-            int* redo = n_pending + p.M;
-
-            // candidates are few and sit at the front of each map's list: index them densely so that every
-            // lane has one (all loads of a pass in flight together) instead of walking M * PK mostly empty slots
-            if (et == 0) {
-                int at = 0;
-                for (int mm = 0; mm < p.M; ++mm) {
-                    cand_start[mm] = at;
-                    at += first_map + mm < p.maps ? okp_min(n_pending[mm], p.PK) : 0;
-                }
-                cand_start[p.M] = at;
-            }
-            okp_named_barrier(1, ethreads);
-            const int candidates = cand_start[p.M];
-
-            // A: exact box sum (the reference's raster-order adds) and centroid of every candidate
-            for (int idx = et; idx < candidates; idx += ethreads) {
-                int lo = 0, hi = p.M;                                 // last mm with cand_start[mm] <= idx
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
-                const int mm = lo, i = mm * p.PK + (idx - cand_start[mm]);
-                OkpStripPeak pk;
-                pk.key = -1; pk.score = 0.0f; pk.cx = 0.0f; pk.cy = 0.0f; pk.conf = 0.0f;
-                {
-                    const OkpStripCandidate cd = pending[i];
-                    const int y = cd.key / W, x = cd.key - y * W;
-                    const T* src = heat + (size_t)(first_map + mm) * H * W;
-                    float q[25];
-                    // almost every candidate is an interior pixel: 25 unconditional loads at constant offsets
-                    // (a fifth of the instructions of the border-checked form, which matters because the
-                    // epilogue warps are latency-bound: profiles/r01m_k1_64x64_ncu.md)
-                    const bool interior = y >= 2 && y + 2 < H && x >= 2 && x + 2 < W;
-                    if (interior) {
-                        const T* corner = src + (size_t)(y - 2) * W + (x - 2);
-#pragma unroll
-                        for (int k = 0; k < 25; ++k) q[k] = okp_ld<T>(corner + (size_t)(k / 5) * W + k % 5);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 25; ++k) {
-                            const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                            const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                            q[k] = in ? okp_ld<T>(src + (size_t)i2 * W + j2) : 0.0f;
-                        }
-                    }
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 25; ++k) sum = __fadd_rn(sum, q[k]);
-                    if (sum > threshold) {
-                        float sy = 0.0f, sx = 0.0f, spr = 0.0f;
-                        if (interior) {                           // same operations in the same order, nothing masked
-#pragma unroll
-                            for (int k = 0; k < 25; ++k) {
-                                sy = __fadd_rn(sy, __fmul_rn(q[k], (float)(y + k / 5 - 2)));
-                                sx = __fadd_rn(sx, __fmul_rn(q[k], (float)(x + k % 5 - 2)));
-                                spr = __fadd_rn(spr, q[k]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 25; ++k) {
-                                const int i2 = y + k / 5 - 2, j2 = x + k % 5 - 2;
-                                const bool in = i2 >= 0 && i2 < H && j2 >= 0 && j2 < W;
-                                if (in) {
-                                    sy = __fadd_rn(sy, __fmul_rn(q[k], (float)i2));
-                                    sx = __fadd_rn(sx, __fmul_rn(q[k], (float)j2));
-                                    spr = __fadd_rn(spr, q[k]);
-                                }
-                            }
-                        }
-                        pk.key = cd.key;
-                        pk.score = sum;
-                        pk.cx = __fdiv_rn(sx, spr);
-                        pk.cy = __fdiv_rn(sy, spr);
-                        pk.conf = spr;
-                        uint32_t ties = cd.ties;
-                        ties &= (y >= 2 ? 0x1Fu : 0u) | (y >= 1 ? 0x3E0u : 0u) | 0x6C00u | (y + 1 < H ? 0xF8000u : 0u) | (y + 2 < H ? 0x1F00000u : 0u);
-                        ties &= (x >= 2 ? 0x108421u : 0u) | (x >= 1 ? 0x210842u : 0u) | 0x421084u | (x + 1 < W ? 0x842108u : 0u) | (x + 2 < W ? 0x1084210u : 0u);
-                        if (ties) {
-                            const int at = atomicAdd(n_items, __popc(ties));
-                            if (at + __popc(ties) > p.IC) {
-                                redo[mm] = 1;
-                                for (int n = at; n < p.IC; ++n) items[n] = 0xFFFFFFFFu;
-                            } else {
-                                int n = at;
-                                while (ties) {
-                                    const int k = __ffs(ties) - 1;
-                                    ties &= ties - 1;
-                                    items[n++] = ((uint32_t)i << 5) | (uint32_t)k;
-                                }
-                            }
-                        }
-                    }
-                }
-                peaks[i] = pk;
-            }
-            okp_named_barrier(1, ethreads);
-
-            // B: undecided neighbours -- exact box sum against the candidate's
-            {
-                const int total_items = okp_min(*n_items, p.IC);
-                for (int n = et; n < total_items; n += ethreads) {
-                    const uint32_t item = items[n];
-                    if (item == 0xFFFFFFFFu) continue;
-                    const int i = (int)(item >> 5), k = (int)(item & 31u);
-                    const int mm = i / p.PK;
-                    const int key = pending[i].key;
-                    const int y = key / W, x = key - y * W;
-                    const T* src = heat + (size_t)(first_map + mm) * H * W;
-                    if (okp_exact_box_sum<T>(src, H, W, y + k / 5 - 2, x + k % 5 - 2) > peaks[i].score) peaks[i].key = -1;
-                }
-            }
-            okp_named_barrier(1, ethreads);
-            for (int idx = et; idx < candidates; idx += ethreads) {
-                int lo = 0, hi = p.M;
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
-                if (peaks[lo * p.PK + (idx - cand_start[lo])].key >= 0) atomicAdd(n_peaks + lo, 1);
-            }
-            okp_named_barrier(1, ethreads);
-
-            // C: raster order (rank by key), final tables, unused slots cleared (not with lean tables). Fused: the sorted
-            // rows also go into the frame's grouping scratch, which is what phase D works from.
-            const int K = p.K;
-            for (int mm = 0; mm < p.M && first_map + mm < p.maps; ++mm) {
-                const int map = first_map + mm;
-                const int total = (redo[mm] || n_pending[mm] > p.PK) ? K + 1 : n_peaks[mm];
-                if (et == 0) {
-                    t.peak_count[map] = total;
-                    if (FUSED) {
-                        const int f = mm / sp.C, c = mm - f * sp.C;
-                        const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
-                                                                    ga.prm.max_objects);
-                        g.counts[c] = total < K ? total : K;
-                        if (c == 0) *g.flags = 0;
-                        if (total > K) pend[f] = 1;
-                    } else if (t.flags && map % sp.C == 0) {
-                        t.flags[map / sp.C] = 0;                 // a stale OKP_FLAG_GENERIC_PATH must not survive (okp_group_kernel keeps the bit)
-                    }
-                }
-                if (total > K || sp.lean) continue;              // tables of an overflowing map are written by the overflow path
-                for (int slot = et; slot < K; slot += ethreads) {
-                    const size_t dst = (size_t)map * K + slot;
-                    t.peak_object[dst] = -1;
-                    reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
-                    if (slot >= total) {
-                        reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(-1, -1);
-                        t.peak_score[dst] = 0.0f;
-                        reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(0.0f, 0.0f);
-                        t.peak_conf[dst] = 0.0f;
-                    }
-                }
-            }
-            for (int idx = et; idx < candidates; idx += ethreads) {
-                int lo = 0, hi = p.M;
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_start[mid] <= idx) lo = mid; else hi = mid; }
-                const int mm = lo, i = mm * p.PK + (idx - cand_start[mm]);
-                const OkpStripPeak pk = peaks[i];
-                if (pk.key < 0) continue;
-                if (redo[mm] || n_pending[mm] > p.PK || n_peaks[mm] > K) continue;
-                const OkpStripPeak* mine = peaks + (size_t)mm * p.PK;
-                const int np = n_pending[mm];
-                int rank = 0;
-                for (int j = 0; j < np; ++j) { const int kj = mine[j].key; rank += (kj >= 0 && kj < pk.key); }
-                const size_t dst = (size_t)(first_map + mm) * K + rank;
-                const int y = pk.key / W;
-                reinterpret_cast<int2*>(t.peak_yx)[dst] = make_int2(y, pk.key - y * W);
-                t.peak_score[dst] = pk.score;
-                reinterpret_cast<float2*>(t.peak_xy)[dst] = make_float2(pk.cx, pk.cy);
-                t.peak_conf[dst] = pk.conf;
-                if (sp.lean) {                                   // the row's assignment columns, which the clearing loop did not reset
-                    t.peak_object[dst] = -1;
-                    reinterpret_cast<double2*>(t.peak_vote)[dst] = make_double2(0.0, 0.0);
-                }
-                if (FUSED) {
-                    const int f = mm / sp.C, c = mm - f * sp.C;
-                    const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
-                                                                ga.prm.max_objects);
-                    g.xy[2 * (c * K + rank)] = pk.cx; g.xy[2 * (c * K + rank) + 1] = pk.cy;
-                    g.conf[c * K + rank] = pk.conf;
-                }
-            }
-            okp_named_barrier(1, ethreads);
-            // hand the candidate buffer back, cleared: the compute warps never wait for the grouping below
-            for (int i = et; i < 2 * p.M; i += ethreads) n_pending[i] = 0;
-            for (int i = et; i < p.M + 1; i += ethreads) n_peaks[i] = 0;
-            okp_named_barrier(1, ethreads);
-            if ((et & 31) == 0) okp_mbar_arrive(cand_free + buf);
-
-            // D (fused): grouping + 3D lift + compact record, one warp per frame, from the sorted peak list in shared memory
-            if (FUSED) {
-                const int first_frame = first_map / sp.C;
-                for (int f = et >> 5; f < sp.F && first_frame + f < ga.N; f += sp.EW) {
-                    const int n = first_frame + f;
-                    if (pend[f]) {                               // okp_group_kernel keeps OKP_FLAG_GENERIC_PATH: not from this call
-                        if ((et & 31) == 0) { t.n_objects[n] = OKP_GROUP_PENDING; t.flags[n] = 0; }
-                    } else {
-                        const OkpGroupScratch g = okp_group_scratch(smem + sp.off_group + (size_t)f * ga.frame_smem_bytes, sp.C, K,
-                                                                    ga.prm.max_objects);
-                        okp_group_frame<T>(n, et & 31, g, ga, t);
-                    }
-                }
-                okp_named_barrier(1, ethreads);                  // phase C of the next group rewrites the scratches
-                for (int i = et; i < p.M; i += ethreads) pend[i] = 0;
-            }
-        }
+        okp_stream_epilogue<T, FUSED>(smem, sp, heat, threshold, t, ga, tid - (compute_warps + 1) * 32, my_groups);
     }
 }
 

@@ -111,13 +111,14 @@ class KeypointDecoder:
 
     def __init__(self, keypoint_config, prediction_size, camera=None, device=None, max_peaks=32, max_objects=16,
                  max_votes=16, threshold=0.5, outlier_distance=20.0, compat_clip_bug=True, nms_size=5, box_sum=True,
-                 top_k=0, lean_tables=False):
+                 top_k=0, lean_tables=False, single_pass=False):
         self.cfg = _abi.check_keypoint_config(keypoint_config)
         self.C = 1 + len(self.cfg)
         self.H, self.W = int(prediction_size[0]), int(prediction_size[1])
         self.params = _abi.make_params(threshold=threshold, outlier_distance=outlier_distance, max_peaks=max_peaks,
                                        max_objects=max_objects, max_votes=max_votes, compat_clip_bug=compat_clip_bug,
-                                       nms_size=nms_size, box_sum=box_sum, top_k=top_k, lean_tables=lean_tables)
+                                       nms_size=nms_size, box_sum=box_sum, top_k=top_k, lean_tables=lean_tables,
+                                       single_pass=single_pass)
         self.device = _device(device)
         self._cfg_array = (ctypes.c_int32 * max(len(self.cfg), 1))(*self.cfg)
         self._camera = None

@@ -71,7 +71,7 @@ def test_version_and_strerror(lib):
 def test_struct_sizes_match_header():
     # OkpCamera: 4 + 4 + 9 doubles + 2 int32; OkpDecodeParams: see header; tables: 16 pointers
     assert ctypes.sizeof(_abi.OkpCamera) == 17 * 8 + 8
-    assert ctypes.sizeof(_abi.OkpDecodeParams) == 48
+    assert ctypes.sizeof(_abi.OkpDecodeParams) == 56
     assert _abi.OkpDecodeParams.top_k.offset == 40
     assert ctypes.sizeof(_abi.OkpDecodeTables) == 16 * ctypes.sizeof(ctypes.c_void_p)
     assert _abi.OkpDecodeParams.outlier_distance.offset == 16

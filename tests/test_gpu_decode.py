@@ -43,12 +43,13 @@ def test_cuda_matches_reference_fixture(name):
     assert_tables_match(got, reference_tables(g))
 
 
+@pytest.mark.parametrize('single_pass', [False, True])
 @pytest.mark.parametrize('name', DECODE_FIXTURES)
-def test_cuda_matches_oracle_on_fixture_inputs(name):
+def test_cuda_matches_oracle_on_fixture_inputs(name, single_pass):
     from oracle import c_oracle
     g = load_golden(name)
     cfg, camera = list(g['keypoint_config']), golden_camera(g)
-    got = gpu_decode(g['heat'], g['depth'], g['centers'], cfg, camera)
+    got = gpu_decode(g['heat'], g['depth'], g['centers'], cfg, camera, single_pass=single_pass)
     assert_matches_oracle(got, c_oracle.decode(g['heat'], g['depth'], g['centers'], cfg, camera))
 
 
@@ -59,7 +60,8 @@ def test_cuda_matches_oracle_on_fixture_inputs(name):
     ([2], (40, 56), 8, (1, 1)),              # odd sizes, ragged tiles
     ([1, 3], (37, 93), 8, (1, 1)),           # sizes that are not multiples of anything
 ])
-def test_cuda_matches_oracle_on_seeded_batches(cfg, size, frames, objects):
+@pytest.mark.parametrize('single_pass', [False, True])
+def test_cuda_matches_oracle_on_seeded_batches(cfg, size, frames, objects, single_pass):
     from oracle import c_oracle
     from object_keypoints_b200 import synthetic
     layout = {}
@@ -70,7 +72,7 @@ def test_cuda_matches_oracle_on_seeded_batches(cfg, size, frames, objects):
         synthetic.default_camera((180, 320)) if size == (180, 320) else \
         __import__('object_keypoints_b200').camera_utils.FisheyeCamera(
             np.array([[50.0, 0, size[1] / 2], [0, 50.0, size[0] / 2], [0, 0, 1]]), np.array([0.1, 0.01, -0.02, 0.003]), size)
-    got = gpu_decode(batch.heat, batch.depth, batch.centers, cfg, camera)
+    got = gpu_decode(batch.heat, batch.depth, batch.centers, cfg, camera, single_pass=single_pass)
     assert_matches_oracle(got, c_oracle.decode(batch.heat, batch.depth, batch.centers, cfg, camera))
     assert got['n_objects'].sum() > 0
 
@@ -413,7 +415,8 @@ def test_record_pack_kernel_equals_the_torch_packing():
 
 @pytest.mark.parametrize('cfg,size,lean', [([1, 3], (64, 64), False), ([1, 3], (64, 64), True), ([1, 1, 1], (64, 64), False),
                                            ([1, 3], (37, 93), False)])
-def test_compact_records_emitted_by_the_decode_kernel(cfg, size, lean):
+@pytest.mark.parametrize('single_pass', [False, True])
+def test_compact_records_emitted_by_the_decode_kernel(cfg, size, lean, single_pass):
     """okp_decode_emit_*: the record every frame's grouping writes into the sink (the multi-GPU gather's payload) equals
     the torch packing of the tables -- fused kernel (64x64), generic path + stand-alone grouping (37x93), frames that
     take the overflow fix-up, several steps through the slot ring of sharding.RecordExchange (world 1: 'local')."""
@@ -426,7 +429,7 @@ def test_compact_records_emitted_by_the_decode_kernel(cfg, size, lean):
     heat[5, 0, 10, 10] = -0.25                                         # a negative value: exact path for that map
     heat[7, 0] = 0.0                                                   # no centres
     camera = synthetic.default_camera((64, 64))
-    decoder = KeypointDecoder(cfg, size, camera=camera, lean_tables=lean)
+    decoder = KeypointDecoder(cfg, size, camera=camera, lean_tables=lean, single_pass=single_pass)
     exchange = sharding.RecordExchange(decoder, 23, world=1, rank=0)
     assert exchange.transport == 'local' and exchange.record_bytes == sharding.compact_layout(16, cfg)['record_bytes']
     tables = decoder.tables(23)
@@ -597,8 +600,9 @@ def test_sparse_host_transfer_gives_the_tables_of_the_dense_copy():
             np.testing.assert_array_equal(got[name].numpy().view(np.uint8), want[name].numpy().view(np.uint8), err_msg=name)
 
 
+@pytest.mark.parametrize('single_pass', [False, True])
 @pytest.mark.parametrize('workload,frames', [('config4_180x320', 256), ('config4_64x64', 1024)])
-def test_headline_bench_workload_is_bitwise_the_oracle(workload, frames):
+def test_headline_bench_workload_is_bitwise_the_oracle(workload, frames, single_pass):
     """The very frames bench.py times (synthetic.torch_grid_batch with bench.py's seed 1004 and grid) decoded on the GPU
     against the C oracle: bitwise integer and float32 tables, 3D points <= 1e-4 relative. The oracle was checked against the
     unmodified reference on frames of this generator; this closes the remaining GPU-vs-oracle comparison."""
@@ -608,7 +612,7 @@ def test_headline_bench_workload_is_bitwise_the_oracle(workload, frames):
     w = bench.WORKLOADS[workload]
     heat, depth, centers, n_obj = synthetic.torch_grid_batch(frames, w['cfg'], w['size'], seed=1004, grid=w['grid'], device='cuda')
     camera = synthetic.default_camera(w['size'])
-    decoder = KeypointDecoder(w['cfg'], w['size'], camera=camera)
+    decoder = KeypointDecoder(w['cfg'], w['size'], camera=camera, single_pass=single_pass)
     got = decoder.decode_batch(heat, depth, centers).numpy()
     want = c_oracle.decode(heat.cpu().numpy(), depth.cpu().numpy(), centers.cpu().numpy(), w['cfg'], camera)
     assert_matches_oracle(got, want)

@@ -21,7 +21,7 @@ flags = sys.argv[5:]
 lean = 'lean' in flags
 if 'nocam' in flags:
     camera = None                      # grouping without the 3D lift (isolates the float64 Newton / tan chains)
-dec = KeypointDecoder([1, 3], (H, W), camera=camera, lean_tables=lean)
+dec = KeypointDecoder([1, 3], (H, W), camera=camera, lean_tables=lean, single_pass='single' in flags)
 tables = dec.tables(frames)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 k1 = k3 = 0.0
@@ -45,5 +45,5 @@ fused = ev[0].elapsed_time(ev[1]) / reps
 gb = frames * 3 * H * W * heat.element_size() / 1e9
 print(f"{shape} {dtype} frames={frames} env={ {k: v for k, v in os.environ.items() if k.startswith('OKP_')} } "
       f"K1 {k1 * 1e3:.1f} us = {gb / (k1 / 1e3):.0f} GB/s ({gb / (k1 / 1e3) / 6547.2:.3f} of measured HBM peak); group {k3 * 1e3:.1f} us; "
-      f"FUSED decode {' '.join(flags)} {fused * 1e3:.1f} us = {gb / (fused / 1e3) / 6547.2:.3f}; "
+      f"decode_batch {' '.join(flags)} {fused * 1e3:.1f} us = {gb / (fused / 1e3) / 6547.2:.3f}; "
       f"objects/frame {float(tables['n_objects'].float().mean()):.2f}")
