@@ -155,12 +155,13 @@ int okp_group_objects_f32(const float* depth_dev, const float* centers_dev, int 
  * *dev_ptr_out; OKP_E_UNSUPPORTED if the buffer is pageable or not mapped into the current device. */
 int okp_host_alias(const void* host_ptr, void** dev_ptr_out);
 
-/* Replaces ObjectKeypointPipeline.__call__ (pipeline.py:182-200) for a batch of N frames. For the reference's
- * configuration (nms_size 5, box_sum 1, top_k 0) on shapes the TMA kernel covers this is ONE streaming pass: the
+/* Replaces ObjectKeypointPipeline.__call__ (pipeline.py:182-200) for a batch of N frames:
+ * okp_extract_peaks_f32 followed by okp_group_objects_f32 on the same stream (two launches plus the overflow fix-up,
+ * which is a no-op unless a map overflowed max_peaks). With OkpDecodeParams.single_pass, for the reference's
+ * configuration (nms_size 5, box_sum 1, top_k 0) on shapes the TMA kernel covers, ONE streaming pass instead: the
  * grouping and the 3D lift of a frame run in the epilogue warps of the peak kernel, from the frame's peak list in
- * shared memory, while the next frames stream (plus two fix-up launches that are no-ops unless a map overflowed
- * max_peaks). Otherwise: okp_extract_peaks_f32 followed by okp_group_objects_f32 on the same stream. Same tables
- * either way. heat_dev must be 16-byte aligned (OKP_E_UNSUPPORTED otherwise). */
+ * shared memory, while the next frames stream. Same tables either way. heat_dev must be 16-byte aligned
+ * (OKP_E_UNSUPPORTED otherwise). */
 int okp_decode_f32(const float* heat_dev, const float* depth_dev, const float* centers_dev,
                    int N, int C, int H, int W, const int32_t* keypoint_config,
                    const OkpCamera* camera, const OkpDecodeParams* params,
@@ -212,6 +213,17 @@ int okp_decode_emit_bf16(const void* heat_dev, const void* depth_dev, const void
                          const OkpCamera* camera, const OkpDecodeParams* params,
                          const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes,
                          const OkpRecordSink* sink, void* stream);
+/* okp_group_objects_* with the record sink of okp_decode_emit_*: the second half of the two-launch decode for callers
+ * that run the halves themselves (e.g. to put an event between them; ObjectExtraction + DetectionToPoint,
+ * pipeline.py:104-171,189-199). sink may be NULL. */
+int okp_group_objects_emit_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
+                               const int32_t* keypoint_config, const OkpCamera* camera,
+                               const OkpDecodeParams* params, const OkpDecodeTables* tables,
+                               const OkpRecordSink* sink, void* stream);
+int okp_group_objects_emit_bf16(const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
+                                const int32_t* keypoint_config, const OkpCamera* camera,
+                                const OkpDecodeParams* params, const OkpDecodeTables* tables,
+                                const OkpRecordSink* sink, void* stream);
 
 /* Replaces FisheyeCamera.undistort (camera_utils.py:75-81, cv2.fisheye.undistortPoints with
  * P = K). xy_dev/out_dev: [n,2] float64. round_to_f32 != 0 reproduces OpenCV's float32 output

@@ -21,6 +21,7 @@ EXPORTS = [
     'okp_eval_match_f64', 'okp_eval_summary_f64', 'okp_record_doubles', 'okp_pack_records_f64',
     'okp_rasterise_targets_f32', 'okp_host_pack_scratch_bytes', 'okp_host_pack_tiles_f32', 'okp_scatter_tiles_f32',
     'okp_record_bytes', 'okp_decode_emit_f32', 'okp_decode_emit_bf16', 'okp_triangulate_tracks_f64', 'okp_associate_pairs_f64',
+    'okp_group_objects_emit_f32', 'okp_group_objects_emit_bf16',
 ]
 
 
@@ -126,6 +127,9 @@ def lib():
         emit = getattr(L, f'okp_decode_emit_{suffix}')
         emit.restype = i32
         emit.argtypes = L.okp_decode_f32.argtypes[:-1] + [P(_abi.OkpRecordSink), vp]
+        group_emit = getattr(L, f'okp_group_objects_emit_{suffix}')
+        group_emit.restype = i32
+        group_emit.argtypes = L.okp_group_objects_f32.argtypes[:-1] + [P(_abi.OkpRecordSink), vp]
     L.okp_host_alias.restype = i32
     L.okp_host_alias.argtypes = [vp, P(vp)]
     L.okp_fisheye_undistort_f64.restype = i32

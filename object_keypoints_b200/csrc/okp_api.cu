@@ -8,7 +8,9 @@
 #include "okp_peaks.cuh"
 #include "okp_peaks_strip.cuh"
 #include "okp_peaks_stream.cuh"
-#include "okp_peaks_tile.cuh"
+#ifdef OKP_TUNING_KNOBS
+#include "okp_peaks_tile.cuh"      // experimental sparse tile form of K1: tuning build only (profiles/r02e_tile_kernel.md)
+#endif
 #include "okp_geometry.cuh"
 #include "okp_group.cuh"
 #include "okp_dlt.cuh"
@@ -39,9 +41,12 @@ PeakPlan plan_peaks(int maps, int H, int W, int K, int esize, const OkpDecodePar
     memset(&p, 0, sizeof(p));
     // the tuned TMA kernels implement the reference's configuration only (5x5 window on the 5x5 box sum)
     const bool reference_mode = prm->nms_size == 5 && prm->box_sum == 1;
+    p.tile = false;
+#ifdef OKP_TUNING_KNOBS
     OkpTilePlan probe;
     p.tile = reference_mode && okp_env_int("OKP_PEAKS_TILE", 0, 1, 0) != 0 &&
              okp_tile_plan(maps, 1, H, W, K, esize, prm->threshold, 0, prm->lean_tables, &probe);
+#endif
     p.strip = p.tile || (reference_mode && okp_strip_plan(maps, H, W, K, esize, &p.sp));
     p.geo.H = H; p.geo.W = W; p.geo.maps = maps;
     p.geo.radius = prm->nms_size / 2; p.geo.box_sum = prm->box_sum ? 1 : 0;
@@ -187,11 +192,14 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     const PeakPlan& p = call.plan;
 
     if (call.strip) {
+#ifdef OKP_TUNING_KNOBS
         if (p.tile) {
             OkpTilePlan tile_plan;
             if (!okp_tile_plan(maps, C, H, W, K, (int)sizeof(T), params->threshold, 0, params->lean_tables, &tile_plan)) return OKP_E_UNSUPPORTED;
             rc = okp_tile_launch<T>(heat_dev, tile_plan, params->threshold, *tables, nullptr, s);
-        } else {
+        } else
+#endif
+        {
             OkpStreamPlan stream_plan;
             if (!okp_stream_plan(maps, C, H, W, K, (int)sizeof(T), 0, params->lean_tables, &stream_plan)) return OKP_E_UNSUPPORTED;
             rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, s);
@@ -322,25 +330,34 @@ int decode(const T* heat_dev, const T* depth_dev, const T* centers_dev, int N, i
     if (rc != OKP_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     OkpStreamPlan stream_plan;
+#ifdef OKP_TUNING_KNOBS
     OkpTilePlan tile_plan;
+#endif
     // One fused pass (grouping in the peak kernel's epilogue warps) or two launches (peaks, then one warp per frame): the
     // grouping is a chain of latencies (gathers from HBM, float64 Newton + tan), and a launch of its own overlaps thousands
     // of them where the fused form has two epilogue warps per SM. Measured (profiles/r02c_fused_vs_split.txt): the split
     // form is faster at every size, so it is the default; OkpDecodeParams.single_pass asks for the fused one.
     bool fused = params->single_pass != 0 && call.strip && params->top_k == 0;
     if (fused) {
-        fused = call.plan.tile ? okp_tile_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), params->threshold, a.frame_smem_bytes,
-                                               params->lean_tables, &tile_plan) && tile_plan.sp.F > 0
-                               : okp_stream_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), a.frame_smem_bytes,
-                                                 params->lean_tables, &stream_plan) && stream_plan.F > 0;
+#ifdef OKP_TUNING_KNOBS
+        if (call.plan.tile)
+            fused = okp_tile_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), params->threshold, a.frame_smem_bytes,
+                                  params->lean_tables, &tile_plan) && tile_plan.sp.F > 0;
+        else
+#endif
+            fused = okp_stream_plan(N * C, C, H, W, params->max_peaks, (int)sizeof(T), a.frame_smem_bytes, params->lean_tables,
+                                    &stream_plan) && stream_plan.F > 0;
     }
     if (!fused) {
         rc = extract_peaks<T>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
         if (rc != OKP_OK) return rc;
         return launch_group<T>(a, 0, tables, s);
     }
-    rc = call.plan.tile ? okp_tile_launch<T>(heat_dev, tile_plan, params->threshold, *tables, &a, s)
-                        : okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, &a, s);
+#ifdef OKP_TUNING_KNOBS
+    if (call.plan.tile) rc = okp_tile_launch<T>(heat_dev, tile_plan, params->threshold, *tables, &a, s);
+    else
+#endif
+        rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, &a, s);
     if (rc != OKP_OK) return rc;
     // fix-up launches: maps that overflowed the fast path are redone exactly, then their frames are grouped. With no such
     // map each is one read of peak_count / n_objects
@@ -427,6 +444,19 @@ int okp_decode_emit_bf16(const void* heat_dev, const void* depth_dev, const void
                          const OkpRecordSink* sink, void* stream) {
     return decode<__nv_bfloat16>((const __nv_bfloat16*)heat_dev, (const __nv_bfloat16*)depth_dev, (const __nv_bfloat16*)centers_dev,
                                  N, C, H, W, keypoint_config, camera, params, tables, workspace_dev, workspace_bytes, sink, stream);
+}
+
+int okp_group_objects_emit_f32(const float* depth_dev, const float* centers_dev, int N, int C, int H, int W,
+                               const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                               const OkpDecodeTables* tables, const OkpRecordSink* sink, void* stream) {
+    return group_objects<float>(depth_dev, centers_dev, N, C, H, W, keypoint_config, camera, params, tables, sink, stream);
+}
+
+int okp_group_objects_emit_bf16(const void* depth_dev, const void* centers_dev, int N, int C, int H, int W,
+                                const int32_t* keypoint_config, const OkpCamera* camera, const OkpDecodeParams* params,
+                                const OkpDecodeTables* tables, const OkpRecordSink* sink, void* stream) {
+    return group_objects<__nv_bfloat16>((const __nv_bfloat16*)depth_dev, (const __nv_bfloat16*)centers_dev, N, C, H, W,
+                                        keypoint_config, camera, params, tables, sink, stream);
 }
 
 int okp_fisheye_undistort_f64(const double* xy_dev, int n, const OkpCamera* camera, int round_to_f32,

@@ -68,7 +68,7 @@ __device__ __forceinline__ void okp_stream_epilogue(unsigned char* smem, const O
     for (int it = 0; it < my_groups; ++it) {
         const int buf = it & 1;
         const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
-        okp_mbar_wait(cand_full + buf, (uint32_t)((it >> 1) & 1));
+        okp_mbar_wait(cand_full + buf, (uint32_t)((it >> 1) & 1), 400);
         OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]);
         int* n_pending = reinterpret_cast<int*>(smem + sp.off_count[buf]);
         int* redo = n_pending + p.M;

@@ -111,13 +111,17 @@ __device__ __forceinline__ bool okp_mbar_try_wait_suspend(uint64_t* bar, uint32_
     return ok != 0;
 }
 // Waits for the phase with the given parity. A wait that lasts longer than ~2 s of SM clocks can only
-// be a protocol bug: trap (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void okp_mbar_wait(uint64_t* bar, uint32_t parity) {
+// be a protocol bug: trap (the launch fails with an error) instead of hanging the GPU. The loop is lean on purpose -- a
+// waiting warp shares its scheduler with working ones: the clock is read once per 256 polls, and `pause_ns` is the sleep
+// between polls (20 ns where the wait is on the critical path; the epilogue warps, which wait tens of microseconds for a
+// group's candidates, pass a longer one).
+__device__ __forceinline__ void okp_mbar_wait(uint64_t* bar, uint32_t parity, unsigned pause_ns = 20) {
     if (okp_mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!okp_mbar_try_wait_suspend(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-        __nanosleep(20);                                  // a waiting warp must not eat the issue slots of the working ones
+    for (unsigned polls = 1;; ++polls) {
+        if (okp_mbar_try_wait_suspend(bar, parity)) return;
+        if ((polls & 255u) == 0u && clock64() - t0 > 4000000000LL) __trap();
+        __nanosleep(pause_ns);
     }
 }
 __device__ __forceinline__ void okp_mbar_arrive(uint64_t* bar) {

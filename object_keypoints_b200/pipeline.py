@@ -167,11 +167,13 @@ class KeypointDecoder:
         """Bytes of one compact per-frame record (okp_decode_emit_*, include/okp.h)."""
         return int(self._lib.okp_record_bytes(self.params.max_objects, self.C, self._cfg_array))
 
-    def decode_batch(self, heat, depth, centers, tables=None, stream=None, records=None):
+    def decode_batch(self, heat, depth, centers, tables=None, stream=None, records=None, peaks_done=None):
         """heat [N,C,H,W], depth [N,C,H,W], centers [N,C-1,2,H,W] (float32 or bfloat16; CUDA tensors
         are used in place, host arrays are copied) -> DecodeTables on the device. No synchronisation.
         records: an ``_abi.OkpRecordSink`` (sharding.RecordExchange.begin()): the kernel also writes every frame's
-        compact record into the sink's buffers while it decodes (the multi-GPU gather)."""
+        compact record into the sink's buffers while it decodes (the multi-GPU gather).
+        peaks_done: a ``torch.cuda.Event`` recorded between the peak kernel (+ its overflow fix-up) and the grouping
+        kernel -- the two halves are then enqueued by two C calls instead of one (bench.py times K1 with it)."""
         heat, heat_kind = _as_device_map(heat, self.device)
         self._check(heat)
         depth, depth_kind = _as_device_map(depth, self.device)
@@ -186,9 +188,7 @@ class KeypointDecoder:
         tables = self.tables(N) if tables is None else tables
         ws = self._workspace_for(N)
         cam = ctypes.byref(self._camera) if self._camera is not None else None
-        if heat_kind != depth_kind and records is not None:
-            raise ValueError("records need heatmaps and depth / centre maps of one element type")
-        if heat_kind == depth_kind:
+        if heat_kind == depth_kind and peaks_done is None:
             rc = getattr(self._lib, f'okp_decode_emit_{heat_kind}')(
                 heat.data_ptr(), depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array, cam,
                 ctypes.byref(self.params), ctypes.byref(tables.struct), ws.data_ptr(), ws.numel(),
@@ -199,10 +199,13 @@ class KeypointDecoder:
                 heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params), ctypes.byref(tables.struct),
                 ws.data_ptr(), ws.numel(), _stream_handle(stream))
             _lib.check(rc, f'okp_extract_peaks_{heat_kind}')
-            rc = getattr(self._lib, f'okp_group_objects_{depth_kind}')(
+            if peaks_done is not None:
+                peaks_done.record(torch.cuda.current_stream(self.device) if stream is None else stream)
+            rc = getattr(self._lib, f'okp_group_objects_emit_{depth_kind}')(
                 depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array, cam,
-                ctypes.byref(self.params), ctypes.byref(tables.struct), _stream_handle(stream))
-            _lib.check(rc, f'okp_group_objects_{depth_kind}')
+                ctypes.byref(self.params), ctypes.byref(tables.struct),
+                ctypes.byref(records) if records is not None else None, _stream_handle(stream))
+            _lib.check(rc, f'okp_group_objects_emit_{depth_kind}')
         return tables
 
     HOST_RESULT_TABLES = ('n_objects', 'flags', 'kp_count', 'kp_xy', 'kp_point')

@@ -110,8 +110,12 @@ void okp_oracle_detection_to_point_f32(const float* xy, int n, const float* dept
  * A2-A5: box sum, NMS, threshold, centroid -- pipeline.py:46-79, models.py:55-58
  * ------------------------------------------------------------------------------------- */
 /* torch's max_pool2d update rule, `if (val > max || isnan(val)) max = val` (ATen MaxPoolKernel): NaN propagates, so no
- * pixel within reach of a NaN box sum passes `x == hmax` (perception/models.py:55-58). Still vectorises. */
-#define MAXF(a, b) (((b) > (a) || (b) != (b)) ? (b) : (a))
+ * pixel within reach of a NaN box sum passes `x == hmax` (perception/models.py:55-58). That form does not vectorise
+ * (2.8x slower end to end), so it runs only on maps whose box sums hold a NaN (one vectorised look); every other map
+ * takes the plain maximum, which gives the same result when no operand is NaN. */
+#define MAXF_NAN(a, b) (((b) > (a) || (b) != (b)) ? (b) : (a))
+#define MAXF_FAST(a, b) ((a) > (b) ? (a) : (b))
+#define MAXF(a, b) (nan_aware ? MAXF_NAN(a, b) : MAXF_FAST(a, b))
 
 typedef struct {
     float* padded;   /* (H+4) x (W+4), zero border */
@@ -119,8 +123,21 @@ typedef struct {
     float* rowmax;   /* (H+4) x W */
 } MapScratch;
 
+static inline __attribute__((always_inline)) void find_peaks_map_impl(const float* p, int H, int W, float threshold,
+        MapScratch* s, int K, int32_t* count, int32_t* yx, float* score_out, float* xy, float* conf, const int nan_aware);
+
 static void find_peaks_map(const float* p, int H, int W, float threshold, MapScratch* s,
                            int K, int32_t* count, int32_t* yx, float* score_out, float* xy, float* conf) {
+    /* a box sum is NaN only if a NaN or an Inf enters it (x - x is 0 for every finite x): one vectorised look decides
+     * which maximum runs */
+    int has_nan = 0;
+    for (size_t i = 0; i < (size_t)H * W; ++i) has_nan |= !(p[i] - p[i] == 0.0f);
+    if (has_nan) find_peaks_map_impl(p, H, W, threshold, s, K, count, yx, score_out, xy, conf, 1);
+    else find_peaks_map_impl(p, H, W, threshold, s, K, count, yx, score_out, xy, conf, 0);
+}
+
+static inline __attribute__((always_inline)) void find_peaks_map_impl(const float* p, int H, int W, float threshold,
+        MapScratch* s, int K, int32_t* count, int32_t* yx, float* score_out, float* xy, float* conf, const int nan_aware) {
     const int PW = W + 4;
     memset(s->padded, 0, sizeof(float) * (size_t)(H + 4) * PW);
     for (int y = 0; y < H; ++y) memcpy(s->padded + (size_t)(y + 2) * PW + 2, p + (size_t)y * W, sizeof(float) * W);
