@@ -282,17 +282,28 @@ int make_group_args(const void* depth_dev, const void* centers_dev, int N, int C
     return convert_sink(sink, O, C, P, &a->sinks);
 }
 
-template <typename T>
-int launch_group(const OkpGroupArgs& a, int only_pending, const OkpDecodeTables* tables, cudaStream_t s) {
-    int warps = (int)((size_t)(48 * 1024) / a.frame_smem_bytes);          // frames per CTA: one warp each
-    if (warps > 4) warps = 4;
-    if (warps < 1) warps = 1;
-    const size_t smem = (size_t)a.frame_smem_bytes * warps;
-    auto kernel = okp_group_kernel<T>;
+template <typename T, int LANES>
+int launch_group_lanes(const OkpGroupArgs& a, int only_pending, const OkpDecodeTables* tables, cudaStream_t s) {
+    const int most = 128 / LANES;                                          // frames per CTA: LANES lanes each
+    int frames = (int)((size_t)(48 * 1024) / a.frame_smem_bytes);
+    if (frames > most) frames = most;
+    if (LANES == 16) frames &= ~1;                                         // whole warps (the caller checked that two frames fit)
+    if (frames < 1) frames = 1;
+    const size_t smem = (size_t)a.frame_smem_bytes * frames;
+    auto kernel = okp_group_kernel<T, LANES>;
     if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(a.N + warps - 1) / warps, warps * 32, smem, s>>>(a, only_pending, *tables);
+    const int threads = frames * LANES;
+    kernel<<<(a.N + frames - 1) / frames, threads, smem, s>>>(a, only_pending, *tables);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
+}
+
+// Small frames hold few peaks (a 64x64 valve frame: ~10): half a warp per frame, two frames per warp (okp_group.cuh).
+template <typename T>
+int launch_group(const OkpGroupArgs& a, int only_pending, const OkpDecodeTables* tables, cudaStream_t s) {
+    const bool small = (long long)a.H * a.W <= 96LL * 96LL && 2 * (size_t)a.frame_smem_bytes <= 48 * 1024 &&
+                       okp_env_int("OKP_GROUP_LANES", 16, 32, 16) == 16;
+    return small ? launch_group_lanes<T, 16>(a, only_pending, tables, s) : launch_group_lanes<T, 32>(a, only_pending, tables, s);
 }
 
 template <typename T>
@@ -552,8 +563,8 @@ int okp_correct_matches_f64(const double* F, const double* left_dev, const doubl
     if (!F || !left_dev || !right_dev || !left_out_dev || !right_out_dev) return OKP_E_NULL;
     OkpMat3 Fm;
     for (int i = 0; i < 9; ++i) Fm.m[i] = F[i];
-    okp_correct_matches_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(Fm, left_dev, right_dev, n, round_to_f32,
-                                                                              left_out_dev, right_out_dev);
+    okp_correct_matches_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(Fm, okp_epipoles(Fm), left_dev, right_dev, n,
+                                                                              round_to_f32, left_out_dev, right_out_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

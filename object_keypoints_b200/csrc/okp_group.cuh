@@ -163,11 +163,15 @@ __device__ __forceinline__ OkpGroupScratch okp_group_scratch(unsigned char* mine
 //                  as include/okp.h promises by default;
 //   lean_tables == 1: only the valid slots are written (the tables of a 64x64 frame are a quarter of its heatmap
 //                  bytes; clearing them costs more DRAM traffic than the frame's peaks).
-template <typename E>
+// LANES = 32: a warp per frame. LANES = 16: half a warp per frame (small frames -- a 64x64 valve frame is ~10 peaks, and
+// the kernel is issue-bound with 12 active lanes per instruction: two frames per warp halve the warp instructions per
+// frame). `lane` is the thread's index inside its frame, FULL the mask of the frame's lanes in the warp; the two halves of
+// a warp run independently (every warp-level primitive below names the frame's own mask).
+template <typename E, int LANES = 32>
 __device__ __forceinline__ void okp_group_frame(const int n, const int lane, const OkpGroupScratch& g, const OkpGroupArgs& a,
                                                 const OkpDecodeTables& t) {
-    constexpr int THREADS = 32;
-    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int THREADS = LANES;
+    const unsigned FULL = LANES == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
     const bool CLEAR = a.prm.lean_tables == 0;
     const int C = a.C, H = a.H, W = a.W, S = a.S;
     const int K = a.prm.max_peaks, O = a.prm.max_objects, V = a.prm.max_votes, T = C - 1;
@@ -177,7 +181,7 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
     const E* centers = reinterpret_cast<const E*>(a.centers);
     unsigned int& s_flags = *g.flags;
     const int* s_counts = g.counts;
-    const unsigned lt = (1u << lane) - 1u;
+    const unsigned lt = ((1u << (threadIdx.x & 31)) - 1u) & FULL;      // the frame's lanes below this one
 
     const int n_center = s_counts[0];
     const int n_obj = n_center < O ? n_center : O;
@@ -221,7 +225,7 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
     }
     for (int i = lane; i < n_obj * C; i += THREADS) g.assigned[i] = 0;
     for (int o = lane; o < n_obj; o += THREADS) g.nvotes[o] = 0;
-    __syncwarp();
+    __syncwarp(FULL);
     const int total = g.start[C];
 
     // ---- pass 1: spoke peaks vote for a centre (pipeline.py:115-128); vote-list slots and (object, map) ranks ----
@@ -278,12 +282,12 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
             else atomicOr(&s_flags, OKP_FLAG_VOTE_OVERFLOW);
             g.rank[i] = g.assigned[arg * C + c] + r_oc;
         }
-        __syncwarp();
+        __syncwarp(FULL);
         if (member) {
             if (r_o == 0) g.nvotes[arg] += __popc(same_o);
             if (r_oc == 0) g.assigned[arg * C + c] += __popc(same_oc);
         }
-        __syncwarp();
+        __syncwarp(FULL);
     }
     for (int o = lane; o < n_obj; o += THREADS) t.n_votes[(size_t)n * O + o] = g.nvotes[o];
 
@@ -370,7 +374,7 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
         }
         okp_record_point(a.sinks, n, O, C, a.P, a.config, o, c, slot, p3);
     }
-    __syncwarp();
+    __syncwarp(FULL);
     if (lane == 0) {
         const unsigned int f = s_flags;
         t.n_objects[n] = n_obj; t.flags[n] = f;
@@ -382,27 +386,29 @@ __device__ __forceinline__ void okp_group_frame(const int n, const int lane, con
 // The frame's peak records are pulled from the tables into shared memory with one round trip. only_pending != 0: only
 // frames marked OKP_GROUP_PENDING by the fused decode kernel are processed (the fix-up launch: with no overflowing map
 // it is one read of n_objects per frame).
-template <typename E>
+template <typename E, int LANES>
 __global__ void __launch_bounds__(128)
 okp_group_kernel(const __grid_constant__ OkpGroupArgs a, const int only_pending, const OkpDecodeTables t) {
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr int SHIFT = LANES == 32 ? 5 : 4;
+    const int lane = threadIdx.x & (LANES - 1);
+    const unsigned mask = LANES == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+    const int n = blockIdx.x * (blockDim.x >> SHIFT) + (threadIdx.x >> SHIFT);
     if (n >= a.N) return;
     if (only_pending && t.n_objects[n] != OKP_GROUP_PENDING) return;
     const int C = a.C, K = a.prm.max_peaks, O = a.prm.max_objects;
     extern __shared__ __align__(16) unsigned char group_smem[];
-    const OkpGroupScratch g = okp_group_scratch(group_smem + (size_t)(threadIdx.x >> 5) * a.frame_smem_bytes, C, K, O);
+    const OkpGroupScratch g = okp_group_scratch(group_smem + (size_t)(threadIdx.x >> SHIFT) * a.frame_smem_bytes, C, K, O);
     const size_t m0 = (size_t)n * C;
     // OKP_FLAG_GENERIC_PATH is a property of the call, written by the peak extraction: keep it
     if (lane == 0) *g.flags = t.flags[n] & OKP_FLAG_GENERIC_PATH;
-    __syncwarp();
+    __syncwarp(mask);
     if (lane < C) {
         const int c = t.peak_count[m0 + lane];
         g.counts[lane] = c < K ? c : K;
         if (c > K) atomicOr(g.flags, OKP_FLAG_PEAK_OVERFLOW);
     }
-    __syncwarp();
-    for (int i = lane; i < C * K; i += 32) {
+    __syncwarp(mask);
+    for (int i = lane; i < C * K; i += LANES) {
         const int c = i / K, k = i - c * K;
         if (k >= g.counts[c]) continue;
         const size_t s = (m0 + c) * K + k;
@@ -410,6 +416,6 @@ okp_group_kernel(const __grid_constant__ OkpGroupArgs a, const int only_pending,
         g.xy[2 * i] = p.x; g.xy[2 * i + 1] = p.y;
         g.conf[i] = t.peak_conf[s];
     }
-    __syncwarp();
-    okp_group_frame<E>(n, lane, g, a, t);
+    __syncwarp(mask);
+    okp_group_frame<E, LANES>(n, lane, g, a, t);
 }

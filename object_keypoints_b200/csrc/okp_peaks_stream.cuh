@@ -38,6 +38,7 @@ struct OkpStreamPlan {
     int C;                        // maps per frame
     int F;                        // fused: frames per group (M = F * C); 0 = peaks only
     int lean;                     // OkpDecodeParams.lean_tables
+    int edge_only;                // 1: every batch runs the border-checked step variant (small maps: one variant in the i-cache)
     int smem_bytes;
     int threads;                  // compute warps + producer warp + epilogue warps
 };
@@ -381,7 +382,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
                 okp_mbar_wait(full + stage, full_parity);
                 const unsigned char* raw = smem + (size_t)stage * p.stage_bytes + thread_raw;
                 const int y0 = b * RB - 4;
-                if (b >= 2 && y0 + 4 < H)
+                if (!sp.edge_only && b >= 2 && y0 + 4 < H)
                     okp_strip_batch<false, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
                 else
                     okp_strip_batch<true, T>(raw, row_pitch, pr, hp, sv, sign, y0, L);
@@ -408,6 +409,14 @@ static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esi
     memset(&sp, 0, sizeof(sp));
     if (!okp_strip_plan(maps, H, W, K, esize, &sp.s)) return false;
     OkpStripPlan& p = sp.s;
+    // small maps (64x64: 14 row batches per group): 224 compute threads leave room for a second epilogue warp inside 320
+    // threads, and three stages stream as well as four (r02h / r02i sweeps: 464 -> 440 us float32, 566 -> 505 us bfloat16)
+    const bool small_map = p.nb <= 20;
+    if (small_map) {
+        if (okp_env_int("OKP_STRIP_STAGES", 0, OKP_STRIP_MAX_NS, 0) == 0) p.NS = 3;
+        const int cap = okp_env_int("OKP_STRIP_THREADS", 0, OKP_STRIP_MAX_THREADS - 32, 0) == 0 ? 224 : OKP_STRIP_MAX_THREADS;
+        if (p.M * p.strips > cap && cap / p.strips >= 1) p.M = cap / p.strips;      // resized below
+    }
     sp.C = C;
     sp.lean = lean;
     const bool fused = group_frame_bytes > 0;
@@ -420,7 +429,8 @@ static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esi
         p.half_stride = okp_round_up_int(p.half_bytes, 128);
         p.stage_bytes = p.halves * p.half_stride;
     };
-    if (fused) resize(p.M / C * C);
+    resize(fused ? p.M / C * C : p.M);
+    sp.edge_only = okp_env_int("OKP_STREAM_EDGE_ONLY", 0, 1, 0);
     sp.EW = okp_env_int("OKP_STREAM_EPILOGUE_WARPS", 0, 4, 0);    // 0: decided below, once M is known
     // the second candidate buffer costs PK * 8 bytes per map: give it back from the per-CTA budget by re-planning M
     const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;

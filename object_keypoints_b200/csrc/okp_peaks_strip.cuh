@@ -330,7 +330,10 @@ static inline bool okp_strip_plan(int maps, int H, int W, int K, int esize, OkpS
     const int per_map = p.NS * OKP_STRIP_RB * p.BW * p.halves * esize +
                         p.PK * (int)(sizeof(OkpStripCandidate) + sizeof(OkpStripPeak)) + items_per_map * 4 + 12;
     const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;   // default: two CTAs per SM
-    const int max_threads = okp_env_int("OKP_STRIP_THREADS", 32, OKP_STRIP_MAX_THREADS - 32, 288);
+    // 256 compute threads + the producer warp + one epilogue warp = 320 threads: two CTAs per SM at 96 registers. (288 let a
+    // 64x64 bfloat16 plan -- more maps fit its shared-memory budget -- grow to 352 threads, i.e. ONE CTA per SM: 719 us
+    // against the float32 plan's 454 us for the same pixels, profiles/r02f_bench_k1.txt)
+    const int max_threads = okp_env_int("OKP_STRIP_THREADS", 32, OKP_STRIP_MAX_THREADS - 32, 256);
     int M = (budget - 1024) / per_map;
     if (M > max_threads / p.strips) M = max_threads / p.strips;
     if (M > maps) M = maps;

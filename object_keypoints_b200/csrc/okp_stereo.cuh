@@ -149,10 +149,22 @@ __host__ __device__ __noinline__ int okp_poly6_roots(const double* k, OkpComplex
     return n;
 }
 
+// The epipoles of F itself, once per call (host): right null vector (F e = 0) and left null vector (e^T F = 0).
+struct OkpEpipoles { double right[3], left[3]; };
+__host__ __device__ __forceinline__ OkpEpipoles okp_epipoles(const OkpMat3& Fm) {
+    double B[3][3], Bt[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { B[r][c] = Fm.m[3 * r + c]; Bt[r][c] = Fm.m[3 * c + r]; }
+    OkpEpipoles e;
+    okp_null_vector3(B, e.right);
+    okp_null_vector3(Bt, e.left);
+    return e;
+}
+
 // One pair: Hartley-Sturm correction (__host__ too: tools/host_check_stereo.cu runs it on the CPU
 // of the build container, which has no GPU). F row-major with x2^T F x1 = 0.
-__host__ __device__ __forceinline__ void okp_correct_pair(const OkpMat3& Fm, double x1, double y1, double x2, double y2,
-                                                 double* o1, double* o2) {
+__host__ __device__ __forceinline__ void okp_correct_pair(const OkpMat3& Fm, const OkpEpipoles& ep, double x1, double y1,
+                                                          double x2, double y2, double* o1, double* o2) {
     const double* F = Fm.m;
     // F~ = T2^T F T1 with T = [[1,0,x],[0,1,y],[0,0,1]]: both points move to the origin
     double A[3][3];
@@ -164,34 +176,31 @@ __host__ __device__ __forceinline__ void okp_correct_pair(const OkpMat3& Fm, dou
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r) A[r][2] = A[r][0] * x1 + A[r][1] * y1 + A[r][2];
-    // epipoles: F~ e1 = 0, e2^T F~ = 0, scaled so that e_x^2 + e_y^2 = 1
-    double B[3][3], Bt[3][3], e1[3], e2[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { B[r][c] = A[r][c]; Bt[r][c] = A[c][r]; }
-    okp_null_vector3(B, e1);
-    okp_null_vector3(Bt, e2);
+    // epipoles: F~ e1 = 0, e2^T F~ = 0, scaled so that e_x^2 + e_y^2 = 1. F~ = T2^T F T1, so F (T1 e1) = 0 and
+    // (T2 e2)^T F = 0: e = T^-1 (epipole of F) -- a translation of F's own epipoles (round 1 ran two 3x3 Jacobi SVDs of F~
+    // per pair for them)
+    const double e1[3] = {ep.right[0] - x1 * ep.right[2], ep.right[1] - y1 * ep.right[2], ep.right[2]};
+    const double e2[3] = {ep.left[0] - x2 * ep.left[2], ep.left[1] - y2 * ep.left[2], ep.left[2]};
     const double s1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1]);
     const double s2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1]);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) { e1[r] /= s1; e2[r] /= s2; }
+    const double e1x = e1[0] / s1, e1y = e1[1] / s1, e1z = e1[2] / s1;
+    const double e2x = e2[0] / s2, e2y = e2[1] / s2, e2z = e2[2] / s2;
     // F' = R2 F~ R1^T with R = [[ex, ey, 0], [-ey, ex, 0], [0, 0, 1]]: epipoles onto the x axes
     double G[3][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        G[0][c] = e2[0] * A[0][c] + e2[1] * A[1][c];
-        G[1][c] = -e2[1] * A[0][c] + e2[0] * A[1][c];
+        G[0][c] = e2x * A[0][c] + e2y * A[1][c];
+        G[1][c] = -e2y * A[0][c] + e2x * A[1][c];
         G[2][c] = A[2][c];
     }
     double Fp[3][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        Fp[r][0] = G[r][0] * e1[0] + G[r][1] * e1[1];
-        Fp[r][1] = -G[r][0] * e1[1] + G[r][1] * e1[0];
+        Fp[r][0] = G[r][0] * e1x + G[r][1] * e1y;
+        Fp[r][1] = -G[r][0] * e1y + G[r][1] * e1x;
         Fp[r][2] = G[r][2];
     }
-    const double f1 = e1[2], f2 = e2[2], a = Fp[1][1], b = Fp[1][2], c = Fp[2][1], d = Fp[2][2];
+    const double f1 = e1z, f2 = e2z, a = Fp[1][1], b = Fp[1][2], c = Fp[2][1], d = Fp[2][2];
     const double f1_2 = f1 * f1, f1_4 = f1_2 * f1_2, f2_2 = f2 * f2, f2_4 = f2_2 * f2_2;
     const double a2 = a * a, b2 = b * b, c2 = c * c, d2 = d * d;
     // g(t) = t ((a t + b)^2 + f2^2 (c t + d)^2)^2 - (a d - b c)(1 + f1^2 t^2)^2 (a t + b)(c t + d), expanded
@@ -250,19 +259,19 @@ __host__ __device__ __forceinline__ void okp_correct_pair(const OkpMat3& Fm, dou
     const double p1x = l1[0] / l1[2], p1y = l1[1] / l1[2];
     const double p2x = l2[0] / l2[2], p2y = l2[1] / l2[2];
     // back through R^T and the translations
-    o1[0] = e1[0] * p1x - e1[1] * p1y + x1;
-    o1[1] = e1[1] * p1x + e1[0] * p1y + y1;
-    o2[0] = e2[0] * p2x - e2[1] * p2y + x2;
-    o2[1] = e2[1] * p2x + e2[0] * p2y + y2;
+    o1[0] = e1x * p1x - e1y * p1y + x1;
+    o1[1] = e1y * p1x + e1x * p1y + y1;
+    o2[0] = e2x * p2x - e2y * p2y + x2;
+    o2[1] = e2y * p2x + e2x * p2y + y2;
 }
 
 __global__ void __launch_bounds__(64)
-okp_correct_matches_kernel(OkpMat3 F, const double* __restrict__ left, const double* __restrict__ right, int n,
+okp_correct_matches_kernel(OkpMat3 F, OkpEpipoles ep, const double* __restrict__ left, const double* __restrict__ right, int n,
                            int round_to_f32, double* __restrict__ left_out, double* __restrict__ right_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double o1[2], o2[2];
-    okp_correct_pair(F, left[2 * i], left[2 * i + 1], right[2 * i], right[2 * i + 1], o1, o2);
+    okp_correct_pair(F, ep, left[2 * i], left[2 * i + 1], right[2 * i], right[2 * i + 1], o1, o2);
     if (round_to_f32) {                               // OpenCV returns the input dtype (float32 in camera_utils.py:93-101)
         o1[0] = (double)(float)o1[0]; o1[1] = (double)(float)o1[1];
         o2[0] = (double)(float)o2[0]; o2[1] = (double)(float)o2[1];
