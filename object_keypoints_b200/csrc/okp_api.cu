@@ -91,7 +91,8 @@ inline int overflow_maps_per_cta(int maps) { return (maps + overflow_grid(maps) 
 // tile lists: one per (map, tile) for the generic kernels, one per (overflow CTA, tile) for the strip path
 size_t workspace_for(const PeakPlan& p, int maps, int K, bool strip) {
     const size_t tiles = strip ? (size_t)overflow_grid(maps) * p.tiles_per_map : (size_t)maps * p.tiles_per_map;
-    return align_up(tiles * sizeof(int32_t), 256) + tiles * K * sizeof(OkpPeakRecord) + 256;
+    // + alignment slack in front, + the launch's group counter (okp_peaks_stream.cuh) behind the lists
+    return align_up(tiles * sizeof(int32_t), 256) + align_up(tiles * K * sizeof(OkpPeakRecord), 256) + 256 + 256;
 }
 
 }  // namespace
@@ -136,6 +137,7 @@ struct PeakCall {
     bool strip;
     int32_t* tile_count;
     OkpPeakRecord* tile_peaks;
+    int* group_counter;                  // one int the stream kernel's CTAs claim their groups from
 };
 
 template <typename T>
@@ -160,6 +162,7 @@ int prepare_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
     uintptr_t base = align_up((uintptr_t)workspace_dev, 256);
     call->tile_count = (int32_t*)base;
     call->tile_peaks = (OkpPeakRecord*)(base + align_up(tiles * sizeof(int32_t), 256));
+    call->group_counter = (int*)((uintptr_t)call->tile_peaks + align_up(tiles * K * sizeof(OkpPeakRecord), 256));
     return OKP_OK;
 }
 
@@ -202,7 +205,7 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
         {
             OkpStreamPlan stream_plan;
             if (!okp_stream_plan(maps, C, H, W, K, (int)sizeof(T), 0, params->lean_tables, &stream_plan)) return OKP_E_UNSUPPORTED;
-            rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, s);
+            rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, call.group_counter, s);
         }
         if (rc != OKP_OK) return rc;
         rc = launch_overflow<T>(heat_dev, call, maps, params, tables, s);
@@ -368,7 +371,7 @@ int decode(const T* heat_dev, const T* depth_dev, const T* centers_dev, int N, i
     if (call.plan.tile) rc = okp_tile_launch<T>(heat_dev, tile_plan, params->threshold, *tables, &a, s);
     else
 #endif
-        rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, &a, s);
+        rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, &a, call.group_counter, s);
     if (rc != OKP_OK) return rc;
     // fix-up launches: maps that overflowed the fast path are redone exactly, then their frames are grouped. With no such
     // map each is one read of peak_count / n_objects

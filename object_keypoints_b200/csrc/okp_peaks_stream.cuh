@@ -49,12 +49,13 @@ __device__ __forceinline__ void okp_named_barrier(int id, int threads) {
 
 // The epilogue warps' loop (shared by the stream kernel above and the tile kernel of okp_peaks_tile.cuh): one finished
 // candidate buffer at a time -- exact box sums from L2, undecided neighbours, raster ranks, table rows and, fused, the
-// frame's grouping and 3D lift. et: thread index among the sp.EW epilogue warps; stride: groups between two of this CTA's
-// groups (gridDim.x).
+// frame's grouping and 3D lift. et: thread index among the sp.EW epilogue warps. claimed: the CTA's groups are the ones its
+// producer lane claimed from the launch's counter (ids in the ring behind the mbarriers, -1 = no more), else group
+// blockIdx.x + it * gridDim.x for it < my_groups.
 template <typename T, bool FUSED>
 __device__ __forceinline__ void okp_stream_epilogue(unsigned char* smem, const OkpStreamPlan& sp, const T* __restrict__ heat,
                                                     const float threshold, const OkpDecodeTables& t, const OkpGroupArgs& ga,
-                                                    const int et, const int my_groups) {
+                                                    const int et, const int my_groups, const bool claimed) {
     const OkpStripPlan& p = sp.s;
     const int H = p.H, W = p.W;
     OkpStripPeak* peaks = reinterpret_cast<OkpStripPeak*>(smem + sp.off_peaks);                // [M][PK]
@@ -65,11 +66,14 @@ __device__ __forceinline__ void okp_stream_epilogue(unsigned char* smem, const O
     int* pend = cand_start + p.M + 1;                                                          // [M] fused: frame f is left to the fix-up launches
     uint64_t* cand_full = reinterpret_cast<uint64_t*>(smem + sp.off_mbar) + 2 * OKP_STRIP_MAX_NS;
     uint64_t* cand_free = cand_full + 2;
+    const volatile int* group_ring = reinterpret_cast<const volatile int*>(cand_free + 2);    // [8] claimed group ids (claimed)
     const int ethreads = sp.EW * 32;
-    for (int it = 0; it < my_groups; ++it) {
+    for (int it = 0; claimed || it < my_groups; ++it) {
         const int buf = it & 1;
-        const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
         okp_mbar_wait(cand_full + buf, (uint32_t)((it >> 1) & 1), 400);
+        const int group = claimed ? group_ring[it & 7] : blockIdx.x + it * gridDim.x;
+        if (group < 0) break;                                                                  // the end marker
+        const int first_map = group * p.M;
         OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]);
         int* n_pending = reinterpret_cast<int*>(smem + sp.off_count[buf]);
         int* redo = n_pending + p.M;
@@ -282,7 +286,7 @@ template <typename T, bool FUSED>
 __global__ void __maxnreg__(96)
 okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ heat, const __grid_constant__ OkpStreamPlan sp,
                         float threshold, float thr_lo, const __grid_constant__ OkpDecodeTables t,
-                        const __grid_constant__ OkpGroupArgs ga) {
+                        const __grid_constant__ OkpGroupArgs ga, int* __restrict__ group_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int RB = OKP_STRIP_RB;
     const OkpStripPlan& p = sp.s;
@@ -297,6 +301,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
     uint64_t* done = full + OKP_STRIP_MAX_NS;                               // [NS] compute warps finished the batch
     uint64_t* cand_full = done + OKP_STRIP_MAX_NS;                          // [2] candidate buffer complete
     uint64_t* cand_free = cand_full + 2;                                    // [2] epilogue finished with the buffer
+    volatile int* group_ring = reinterpret_cast<volatile int*>(cand_free + 2);   // [8] group id of iteration it (it & 7), -1 = end
 
     const int tid = threadIdx.x;
     const int H = p.H, W = p.W;
@@ -317,6 +322,11 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
     }
     __syncthreads();
 
+    // Groups are CLAIMED from a counter of the launch (zeroed by the caller), one at a time, by the producer lane: a CTA
+    // that becomes resident late -- another kernel held its SM, e.g. the exchange barrier of the previous step beside a
+    // multi-GPU decode -- simply takes fewer groups. With the static round-robin of round 1 such a CTA delayed the whole
+    // launch by its lag (K1 stretched 479 -> 518 us on 8 GPUs). The id travels to the compute warps behind the `full`
+    // barrier of the group's first batch and to the epilogue warps behind `cand_full`; -1 ends the roles' loops.
     const int my_groups = blockIdx.x < sp.groups ? (sp.groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
     if (warp == compute_warps) {
@@ -326,8 +336,18 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
             int stage = 0;
             uint32_t parity = 0;
             long long q = 0;
-            for (int it = 0; it < my_groups; ++it) {
-                const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
+            for (int it = 0;; ++it) {
+                int group = atomicAdd(group_counter, 1);
+                if (group >= sp.groups) group = -1;
+                group_ring[it & 7] = group;                   // ordered before the arrive below (release)
+                if (group < 0) {                              // end marker: complete the phase the compute warps wait for
+                    if (q >= NS) {
+                        while (!okp_mbar_try_wait_suspend(done + stage, parity)) {}
+                    }
+                    okp_mbar_arrive(full + stage);
+                    break;
+                }
+                const int first_map = group * p.M;
                 for (int b = 0; b < p.nb; ++b, ++q) {
                     if (q >= NS) {                            // every compute warp has left the stage (sleeps in hardware)
                         while (!okp_mbar_try_wait_suspend(done + stage, parity)) {}
@@ -363,9 +383,15 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
         const int row_pitch = p.BW * (int)sizeof(T);
         int stage = 0;
         uint32_t full_parity = 0;
-        for (int it = 0; it < my_groups; ++it) {
+        for (int it = 0;; ++it) {
             const int buf = it & 1;
             if (it >= 2) okp_mbar_wait(cand_free + buf, (uint32_t)(((it >> 1) - 1) & 1));   // the epilogue released the buffer
+            okp_mbar_wait(full + stage, full_parity);                 // the group's first batch -- or the end marker
+            if (group_ring[it & 7] < 0) {
+                __syncwarp();
+                if ((tid & 31) == 0) okp_mbar_arrive(cand_full + buf);                      // pass the marker on to the epilogue warps
+                break;
+            }
             int* count = reinterpret_cast<int*>(smem + sp.off_count[buf]);
             L.pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]) + (size_t)mm * p.PK;
             L.n_pending = count + mm;
@@ -379,7 +405,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
 #pragma unroll
             for (int j = 0; j < 4; ++j) hp[j] = 0.0f;
             for (int b = 0; b < p.nb; ++b) {
-                okp_mbar_wait(full + stage, full_parity);
+                if (b > 0) okp_mbar_wait(full + stage, full_parity);
                 const unsigned char* raw = smem + (size_t)stage * p.stage_bytes + thread_raw;
                 const int y0 = b * RB - 4;
                 if (!sp.edge_only && b >= 2 && y0 + 4 < H)
@@ -396,7 +422,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
         }
     } else {
         // ------------------------------- epilogue warps: one finished candidate buffer at a time ---------
-        okp_stream_epilogue<T, FUSED>(smem, sp, heat, threshold, t, ga, tid - (compute_warps + 1) * 32, my_groups);
+        okp_stream_epilogue<T, FUSED>(smem, sp, heat, threshold, t, ga, tid - (compute_warps + 1) * 32, my_groups, true);
     }
 }
 
@@ -445,7 +471,7 @@ static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esi
         off = okp_round_up_int(off, 16);
         sp.off_group = off;
         if (fused) off += (p.M / C) * group_frame_bytes;
-        sp.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 4) * 8;
+        sp.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 4) * 8 + 32;       // mbarriers + the ring of claimed group ids
         sp.smem_bytes = off;
         const int step = fused ? C : 1;
         if ((off <= budget && p.threads <= compute_limit) || p.M == step) break;
@@ -466,7 +492,8 @@ static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esi
 // ga: grouping arguments (fused form, sp.F > 0) or NULL (peaks only).
 template <typename T>
 static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, float threshold,
-                                    const OkpDecodeTables& tables, const OkpGroupArgs* ga, cudaStream_t stream) {
+                                    const OkpDecodeTables& tables, const OkpGroupArgs* ga, int* group_counter_dev,
+                                    cudaStream_t stream) {
     const OkpStripPlan& p = sp.s;
     OkpEncodeTiledFn encode = okp_encode_tiled_fn();
     if (!encode) return OKP_E_CUDA;
@@ -494,7 +521,9 @@ static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, floa
     long long grid = (long long)per_sm * sms;               // persistent: every CTA resident, groups dealt round-robin
     if (grid > sp.groups) grid = sp.groups;
     const float thr_lo = threshold - OKP_STRIP_THRESHOLD_SLACK * fabsf(threshold);
-    kernel<<<(unsigned)grid, sp.threads, sp.smem_bytes, stream>>>(tmap, heat, sp, threshold, thr_lo, tables, fused ? *ga : none);
+    OKP_CUDA_CHECK(cudaMemsetAsync(group_counter_dev, 0, sizeof(int), stream));
+    kernel<<<(unsigned)grid, sp.threads, sp.smem_bytes, stream>>>(tmap, heat, sp, threshold, thr_lo, tables, fused ? *ga : none,
+                                                                  group_counter_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
     return OKP_OK;
 }

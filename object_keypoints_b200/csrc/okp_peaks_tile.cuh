@@ -384,7 +384,7 @@ okp_peaks_tile_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restr
         }
     } else {
         // ------------------------------- epilogue warps: one finished candidate buffer at a time ---------
-        okp_stream_epilogue<T, FUSED>(smem, sp, heat, threshold, t, ga, tid - (CW + 1) * 32, my_groups);
+        okp_stream_epilogue<T, FUSED>(smem, sp, heat, threshold, t, ga, tid - (CW + 1) * 32, my_groups, false);
     }
 }
 
@@ -467,7 +467,7 @@ static inline bool okp_tile_plan(int maps, int C, int H, int W, int K, int esize
         off = okp_round_up_int(off, 16);
         sp.off_group = off;
         if (fused) off += (M / C) * group_frame_bytes;
-        sp.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 4) * 8;
+        sp.off_mbar = off; off += (2 * OKP_STRIP_MAX_NS + 4) * 8 + 32;
         sp.smem_bytes = off;
         if (off <= budget) break;
         if (M > unit) { M -= unit; continue; }

@@ -45,6 +45,11 @@ def _host_threads():
     return max(1, cores // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))
 
 
+def _local_world():
+    import os
+    return max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+
+
 def _as_device_f32(x, device):
     """NumPy array / CPU tensor / CUDA tensor -> contiguous float32 CUDA tensor."""
     if isinstance(x, np.ndarray):
@@ -220,6 +225,7 @@ class KeypointDecoder:
         return alias.value
 
     SPARSE_CAPACITY = 0.5          # fall back to the dense copy when more than this share of a chunk's tiles is marked
+    SPARSE_MAX_LOCAL_WORLD = int(__import__('os').environ.get('OKP_SPARSE_MAX_LOCAL_WORLD', '4'))   # see _sparse_ok
     SPARSE_MIN_THREADS = 2         # sparse='auto' runs the host pass from this many host threads per rank on: the scheduler
                                    # below hands it a chunk only when it will finish before the copy engine could have moved
                                    # the remaining chunks densely, so a slow pass (few threads) just takes fewer chunks
@@ -228,10 +234,12 @@ class KeypointDecoder:
         """The sparse transfer holds for the reference's configuration only (csrc/okp_sparse.cuh)."""
         if sparse in (False, 'off', None):
             return False
-        # the pass reads every heatmap byte from host memory: it pays while PCIe, not host DRAM, is the limit (8 threads pack
-        # at about the rate of one Gen5 x16 link). Round 1 switched it off below 8 threads per rank, which left 4- and 8-rank
-        # runs on the dense copy alone; now the chunk scheduler decides (see SPARSE_MIN_THREADS)
-        if sparse == 'auto' and _host_threads() < self.SPARSE_MIN_THREADS:
+        # The pass trades PCIe bytes for host-DRAM bytes: it reads every heatmap byte once with the CPU and sends ~19 % of
+        # them, i.e. 1.19x the dense copy's host-memory traffic for 0.19x of its PCIe traffic. It pays while the rank's
+        # PCIe link is the limit (1-2 ranks per host: 121 k against 79 k frames/s on one GPU, 198 k against 156 k on two) and
+        # costs when the ranks of a host together saturate its memory first (8 ranks on a 32-core host: 246 k against 262 k
+        # frames/s, gpurun_out/r2j) -- so 'auto' also looks at how many ranks share the host.
+        if sparse == 'auto' and (_host_threads() < self.SPARSE_MIN_THREADS or _local_world() > self.SPARSE_MAX_LOCAL_WORLD):
             return False
         return (self.params.nms_size == 5 and self.params.box_sum == 1 and self.params.threshold > 0.0 and
                 heat.device.type == 'cpu' and heat.dtype == torch.float32 and heat.is_contiguous())
