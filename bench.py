@@ -223,9 +223,9 @@ def time_decode(decoder, inputs, tables, steps, warmup=3):
 
 def secondary_64x64(device, peaks, steps):
     """The network's real output resolution (KeypointNet emits 64x64): 32768 valve frames of 64x64 (1.61 GB of
-    float32 heatmaps, far above the 126 MB L2), float32 and bfloat16, whole step = the fused decode kernel + its two no-op
-    fix-up launches, lean tables (only valid slots are written: at this size clearing the tables would be a quarter of the
-    DRAM traffic). Parity of this workload: tests/test_gpu_decode.py::test_headline_bench_workload_is_bitwise_the_oracle."""
+    float32 heatmaps, far above the 126 MB L2), float32 and bfloat16, whole step = peak kernel + overflow fix-up + grouping
+    kernel, lean tables (only valid slots are written: at this size clearing the tables would be a quarter of the DRAM
+    traffic). Parity of this workload: tests/test_gpu_decode.py::test_headline_bench_workload_is_bitwise_the_oracle."""
     import torch
     from object_keypoints_b200 import KeypointDecoder, synthetic
     w = WORKLOADS['config4_64x64']
@@ -419,6 +419,29 @@ def run_ours(args):
     elapsed_ms = start.elapsed_time(stop)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / args.steps
 
+    # ---- sustained behaviour: ~1 s of back-to-back steps (the K timed steps above last ~10 ms), clocks sampled throughout ----
+    sustained = None
+    if not args.no_sustained:
+        count = max(args.steps, int(1000.0 / max(elapsed_ms / args.steps, 0.05)))
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(count):
+            step()
+        if world > 1:
+            exchange.finish()
+        s1.record()
+        barrier()
+        ms = torch.tensor([s0.elapsed_time(s1) / count], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            sustained = {'steps': count, 'ms_per_step': float(ms), 'frames_per_s': world * frames / (float(ms) / 1e3),
+                         'clocks': sampler2.stop()}
+
     # ---- parity, outside the timed region ----
     # N > 1: the gathered rows of EVERY rank against a re-pack of that rank's own tables (plain torch + NCCL all_gather)
     gathered_check = None
@@ -514,6 +537,8 @@ def run_ours(args):
             line['parity'] = parity
         if strong is not None:
             line['strong'] = strong
+        if sustained is not None:
+            line['sustained'] = sustained
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = baseline
         if world == 1 and not args.no_secondary:
@@ -653,7 +678,8 @@ def main():
     ap.add_argument('--e2e-frames', type=int, default=2048)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-secondary', action='store_true', help="skip the 64x64 lines (N = 1)")
+    ap.add_argument('--no-secondary', action='store_true', help="skip the 64x64 / config 3 / config 5 lines (N = 1)")
+    ap.add_argument('--no-sustained', action='store_true', help="skip the ~1 s sustained run")
     ap.add_argument('--exchange', default='gather', choices=['gather', 'allgather'],
                     help="N > 1: gather the records to rank 0 (north_star) or to every rank")
     ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],

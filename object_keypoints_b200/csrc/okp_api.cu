@@ -172,9 +172,9 @@ int launch_overflow(const T* heat_dev, const PeakCall& call, int maps, const Okp
                     const OkpDecodeTables* tables, cudaStream_t s) {
     auto kernel = okp_peaks_overflow_kernel<256, T>;
     OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)call.plan.smem_bytes));
-    kernel<<<overflow_grid(maps), 256, call.plan.smem_bytes, s>>>(heat_dev, call.plan.geo, params->threshold, params->max_peaks,
-                                                                   overflow_maps_per_cta(maps), call.tile_count, call.tile_peaks, *tables);
-    OKP_CUDA_CHECK(cudaGetLastError());
+    OKP_CUDA_CHECK(okp_launch_dependent(kernel, dim3(overflow_grid(maps)), dim3(256), call.plan.smem_bytes, s, heat_dev, call.plan.geo,
+                                        params->threshold, params->max_peaks, overflow_maps_per_cta(maps), call.tile_count,
+                                        call.tile_peaks, *tables));
     return OKP_OK;
 }
 
@@ -296,8 +296,7 @@ int launch_group_lanes(const OkpGroupArgs& a, int only_pending, const OkpDecodeT
     auto kernel = okp_group_kernel<T, LANES>;
     if (smem > 48 * 1024) OKP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = frames * LANES;
-    kernel<<<(a.N + frames - 1) / frames, threads, smem, s>>>(a, only_pending, *tables);
-    OKP_CUDA_CHECK(cudaGetLastError());
+    OKP_CUDA_CHECK(okp_launch_dependent(kernel, dim3((a.N + frames - 1) / frames), dim3(threads), smem, s, a, only_pending, *tables));
     return OKP_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/okp.h"
 
@@ -39,4 +40,23 @@ template <typename T> __device__ __forceinline__ float okp_ld(const T* p);
 template <> __device__ __forceinline__ float okp_ld<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float okp_ld<__nv_bfloat16>(const __nv_bfloat16* p) {
     return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
+// Programmatic dependent launch (sm_90+): a kernel launched with okp_launch_dependent() may be scheduled while the kernel
+// in front of it on the stream drains -- its launch latency (2-4 us between dependent kernels on a B200) overlaps the
+// predecessor's tail. It must call okp_wait_for_predecessor() before it touches anything the predecessor wrote; the wait
+// returns when the predecessor grid has completed and its writes are visible (a no-op under an ordinary launch).
+__device__ __forceinline__ void okp_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KernelArgs, typename... Args>
+static inline cudaError_t okp_launch_dependent(void (*kernel)(KernelArgs...), dim3 grid, dim3 block, size_t smem,
+                                               cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t config;
+    memset(&config, 0, sizeof(config));
+    config.gridDim = grid; config.blockDim = block; config.dynamicSmemBytes = smem; config.stream = stream;
+    cudaLaunchAttribute attribute;
+    attribute.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attribute.val.programmaticStreamSerializationAllowed = 1;
+    config.attrs = &attribute; config.numAttrs = 1;
+    return cudaLaunchKernelEx(&config, kernel, KernelArgs(args)...);
 }

@@ -393,6 +393,7 @@ okp_group_kernel(const __grid_constant__ OkpGroupArgs a, const int only_pending,
     const int lane = threadIdx.x & (LANES - 1);
     const unsigned mask = LANES == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
     const int n = blockIdx.x * (blockDim.x >> SHIFT) + (threadIdx.x >> SHIFT);
+    okp_wait_for_predecessor();                           // launched as a programmatic dependent of the peak / fix-up kernel
     if (n >= a.N) return;
     if (only_pending && t.n_objects[n] != OKP_GROUP_PENDING) return;
     const int C = a.C, K = a.prm.max_peaks, O = a.prm.max_objects;

@@ -272,6 +272,7 @@ okp_peaks_overflow_kernel(const T* __restrict__ heat, OkpTileGeometry g, float t
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_count;
     __shared__ int s_over[THREADS];
+    okp_wait_for_predecessor();                           // launched as a programmatic dependent of the peak kernel
     const int tiles_per_map = g.tiles_y * g.tiles_x;
     const int first = blockIdx.x * per_cta;
     const int last = first + per_cta < g.maps ? first + per_cta : g.maps;

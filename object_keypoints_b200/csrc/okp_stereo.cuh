@@ -74,12 +74,16 @@ __host__ __device__ __forceinline__ OkpComplex okp_cmul(OkpComplex a, OkpComplex
     return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
 }
 __host__ __device__ __forceinline__ OkpComplex okp_cdiv(OkpComplex a, OkpComplex b) {      // Smith's algorithm
-    if (fabs(b.re) >= fabs(b.im)) {
-        const double r = b.im / b.re, den = b.re + b.im * r;
-        return {(a.re + a.im * r) / den, (a.im - a.re * r) / den};
-    }
-    const double r = b.re / b.im, den = b.re * r + b.im;
-    return {(a.re * r + a.im) / den, (a.im * r - a.re) / den};
+    // branch-free (selects): the two cases of the textbook form differ by which component of b is the pivot; with
+    // p = pivot, q = the other one, x / y = the matching components of a, both cases are ((x + y r) / den, +-(y - x r) / den)
+    // -- the same operations on the same operands as the two-branch form, so the quotient is bit-identical, and the lanes
+    // of a warp no longer split on |b.re| >= |b.im|
+    const bool big = fabs(b.re) >= fabs(b.im);
+    const double p = big ? b.re : b.im, q = big ? b.im : b.re;
+    const double x = big ? a.re : a.im, y = big ? a.im : a.re;
+    const double r = q / p, den = p + q * r;
+    const double im = (y - x * r) / den;
+    return {(x + y * r) / den, big ? im : -im};
 }
 
 // All complex roots of k[0] + k[1] t + ... + k[6] t^6 (degree n <= 6 after leading zeros are
@@ -111,6 +115,13 @@ __host__ __device__ __noinline__ int okp_poly6_roots(const double* k, OkpComplex
         }
         i = best;
     }
+    // Convergence: the largest relative correction of a sweep below 1e-14 -- or no longer contracting once it is small.
+    // Aberth-Ehrlich converges cubically, so a sweep that is within 1e-9 of the roots and does not shrink the correction
+    // fourfold has reached the rounding floor of an ill-conditioned root (the far roots of a sideways rig sit at |t| ~ 1e6
+    // and stall at ~1e-15 .. 1e-13). Round 1 asked every root for 4e-16: one pair in five never got there and ran to the
+    // cap of 200 sweeps, and with it the other 31 pairs of its warp (ncu r02m: 4 of 32 lanes active, 19.9 ms per 2^20
+    // pairs). The winner is polished by Newton steps on g below, so the result does not move (<= 1e-12 px).
+    double previous = 1e300;
     for (int it = 0; it < 200; ++it) {
         double worst = 0.0;
         for (int r = 0; r < n; ++r) {
@@ -144,7 +155,8 @@ __host__ __device__ __noinline__ int okp_poly6_roots(const double* k, OkpComplex
             const double rel = (fabs(w.re) + fabs(w.im)) / (fabs(x.re) + fabs(x.im) + 1e-300);
             if (rel > worst) worst = rel;
         }
-        if (worst < 4e-16) break;
+        if (worst < 1e-14 || (worst < 1e-9 && worst > 0.25 * previous)) break;
+        previous = worst;
     }
     return n;
 }

@@ -8,6 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import pytest
+
 from object_keypoints_b200 import sharding
 
 
@@ -138,3 +140,27 @@ def test_gather_over_gloo_world_size_2(tmp_path):
     for r in range(world):
         ok, rows = np.load(os.path.join(str(tmp_path), f'ok_{r}.npy'))
         assert ok == 1 and rows == frames_total
+
+
+@pytest.mark.gpu
+def test_record_exchange_on_the_gpus_of_this_box():
+    """The multi-GPU exchange on hardware: every transport (NCCL all_gather / gather, peer stores to every
+    rank / to one root) through seven pipelined steps against the torch packing + plain all_gather of the same tables,
+    including a frame whose record comes from the overflow fix-up. Runs tools/check_exchange.py under torchrun on all GPUs
+    of the box; skipped on a single-GPU box (the N = 2 and N = 8 logs of the round are in profiles/)."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU visible: the exchange needs at least two ranks")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    run = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(root, 'tools', 'check_exchange.py')],
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
+    lines = [line for line in run.stdout.splitlines() if line.startswith('rank ')]
+    assert len(lines) == n and not any('FAILED' in line for line in lines), run.stdout[-2000:]
