@@ -367,7 +367,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=device)
+        import datetime
+        # a protocol bug must cost minutes, not the watchdog's default ten
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=180))
     w = WORKLOADS[args.workload]
     frames = w['frames']
     H, W = w['size']
@@ -422,7 +424,7 @@ def run_ours(args):
     # ---- sustained behaviour: ~1 s of back-to-back steps (the K timed steps above last ~10 ms), clocks sampled throughout ----
     sustained = None
     if not args.no_sustained:
-        count = max(args.steps, int(1000.0 / max(elapsed_ms / args.steps, 0.05)))
+        count = max(args.steps, args.sustained_steps)          # the SAME on every rank: each step is a cross-rank exchange
         sampler2 = ClockSampler(local_rank)
         if rank == 0:
             sampler2.start()
@@ -680,6 +682,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help="skip the 64x64 / config 3 / config 5 lines (N = 1)")
     ap.add_argument('--no-sustained', action='store_true', help="skip the ~1 s sustained run")
+    ap.add_argument('--sustained-steps', type=int, default=2000)
     ap.add_argument('--exchange', default='gather', choices=['gather', 'allgather'],
                     help="N > 1: gather the records to rank 0 (north_star) or to every rank")
     ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
