@@ -522,9 +522,12 @@ def run_ours(args):
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args.workload, world, args.exchange),
-            'exchange': (f"{exchange.transport}: " + ('the decode kernel stores every frame\'s compact record straight into the '
-                                                     'gathering rank over NVLink (no pack kernel); completion = a device-side barrier'
-                                                     if exchange.transport == 'peer' else 'compact records + NCCL')
+            'exchange': (f"{exchange.transport}{'/staged' if getattr(exchange, 'staged', False) else ''}: " +
+                         ('the grouping kernel writes every frame\'s compact record into a local buffer, the exchange stream pushes '
+                          'the buffer into the gathering rank with one peer copy over NVLink (copy engine, no SM); completion = a '
+                          'device-side barrier' if getattr(exchange, 'staged', False) else
+                          'the grouping kernel stores every frame\'s compact record straight into the gathering rank over NVLink; '
+                          'completion = a device-side barrier' if exchange.transport == 'peer' else 'compact records + NCCL')
                          + ", overlapped with the next step's decode") if world > 1 else None,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                          'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peak_kind,

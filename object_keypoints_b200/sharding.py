@@ -143,9 +143,13 @@ class RecordExchange:
     rank (consume it on the compute stream before that).
 
     Transports:
-      'peer'  the buffers are symmetric (peer-mapped) memory and the sink of a step is the destination rank's buffer: the
-              decode kernel's record stores travel over NVLink / NVSwitch while it streams heatmaps -- no pack kernel, no
-              copy, no NCCL on the data path; completion is a device-side barrier.
+      'peer'  the gather buffers are symmetric (peer-mapped) memory; completion is a device-side barrier, no NCCL on the
+              data path. ``staged=True`` (default): the grouping kernel writes the step's records into a LOCAL buffer and the
+              exchange stream pushes them into the destination rank's buffer with one peer copy (copy engine over NVLink /
+              NVSwitch: no SM, overlapped with the next step's decode). ``staged=False``: the sink of a step IS the
+              destination rank's buffer, the kernel's record stores travel over NVLink while it runs -- no copy at all,
+              but with 8 ranks gathering to one root the seven streams of stores meet at the root's NVLink ingress
+              (34 MB per step at 900 GB/s = 38 us) and stall the grouping kernels that issue them.
       'nccl'  the sink is a local send buffer, NCCL all_gather_into_tensor / gather moves it.
       'auto'  'peer' when symmetric memory can be set up on this box, else 'nccl'.
 
@@ -155,7 +159,7 @@ class RecordExchange:
     """
     LAG = 2
 
-    def __init__(self, decoder, frames, world=None, rank=None, transport='auto', depth=4, group=None, root=None):
+    def __init__(self, decoder, frames, world=None, rank=None, transport='auto', depth=4, group=None, root=None, staged=True):
         import ctypes
         from . import _abi
         self._ctypes, self._abi = ctypes, _abi
@@ -188,10 +192,15 @@ class RecordExchange:
                 self.peer_error = f"{type(error).__name__}: {error}"
                 transport = 'nccl'
         self.transport = transport
+        self.staged = bool(staged) and transport == 'peer'
         if transport != 'peer':
             self.buffers = [torch.zeros(shape, dtype=torch.uint8, device=self.device) for _ in range(self.depth)]
         self.send = [torch.zeros((self.N, self.record_bytes), dtype=torch.uint8, device=self.device) for _ in range(self.depth)] \
-            if transport == 'nccl' else None
+            if transport == 'nccl' or self.staged else None
+        if self.staged:                                      # this rank's rows inside every destination's gather buffer
+            targets = range(self.world) if self.root is None else [self.root]
+            self._remote_rows = [[handle.get_buffer(t, shape, torch.uint8)[self.rank * self.N:(self.rank + 1) * self.N]
+                                  for t in targets] for handle in self.handles]
         self.done = [torch.cuda.Event() for _ in range(self.depth)]
         self._sinks = [self._make_sink(slot) for slot in range(self.depth)]
 
@@ -211,10 +220,12 @@ class RecordExchange:
         dist.barrier(group=group)                            # nobody stores into a buffer that is still being zeroed
 
     def _make_sink(self, slot):
-        if self.transport == 'peer':
+        if self.transport == 'peer' and not self.staged:
             peers = [int(p) for p in self.handles[slot].buffer_ptrs]
             targets = peers if self.root is None else [peers[self.root]]
             first_row = self.rank * self.N
+        elif self.transport == 'peer':
+            targets, first_row = [self.send[slot].data_ptr()], 0
         elif self.transport == 'nccl':
             targets, first_row = [self.send[slot].data_ptr()], 0
         else:
@@ -241,7 +252,10 @@ class RecordExchange:
         out = self.buffers[slot]
         with torch.cuda.stream(self.stream):
             if self.transport == 'peer':
-                self.handles[slot].barrier(channel=0)       # every rank's stores have landed
+                if self.staged:
+                    for rows in self._remote_rows[slot]:
+                        rows.copy_(self.send[slot], non_blocking=True)
+                self.handles[slot].barrier(channel=0)       # every rank's records have landed
             elif self.transport == 'nccl':
                 if self.root is None:
                     dist.all_gather_into_tensor(out, self.send[slot], group=self.group)

@@ -15,10 +15,11 @@ dist.init_process_group('nccl', device_id=device)
 cfg, size, frames = [1, 3], (64, 64), 257
 decoder = KeypointDecoder(cfg, size, camera=synthetic.default_camera(size), device=device)
 report = {}
-for transport, root in (('nccl', None), ('peer', None), ('nccl', 0), ('peer', 0), ('peer', world - 1)):
-    label = f"{transport}/{'allgather' if root is None else 'gather->' + str(root)}"
+for transport, root, staged in (('nccl', None, True), ('peer', None, True), ('nccl', 0, True), ('peer', 0, True), ('peer', world - 1, True),
+                                ('peer', None, False), ('peer', 0, False)):
+    label = f"{transport}{'' if staged or transport != 'peer' else '-direct'}/{'allgather' if root is None else 'gather->' + str(root)}"
     try:
-        exchange = sharding.RecordExchange(decoder, frames, world=world, rank=rank, transport=transport, root=root)
+        exchange = sharding.RecordExchange(decoder, frames, world=world, rank=rank, transport=transport, root=root, staged=staged)
         tables = decoder.tables(frames)
         for step in range(7):                                     # more steps than ring slots
             batch = synthetic.make_batch(frames, cfg, size, seed=100 * step + rank, objects=(1, 3))
