@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence: launch list of the bench command, full captures of K1 (180x320 f32, 64x64 f32 / bf16), the grouping kernel,
 # launch list + full captures of the kernels beside the decode path.
-tag=${1:-r2m}
+tag=${1:-evidence}
 out=gpurun_out/$tag
 mkdir -p $out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:okp_ -c 80 --csv --log-file $out/launches.csv \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # N GPUs: the bench line (weak scaling, strong scaling block, e2e).
-tag=${1:-r2j}; n=${2:-8}
+tag=${1:-multi}; n=${2:-8}
 out=gpurun_out/$tag
 mkdir -p $out
 nvidia-smi --query-gpu=name --format=csv,noheader | head -1 > $out/gpu.txt; nproc >> $out/gpu.txt
