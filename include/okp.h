@@ -124,7 +124,9 @@ typedef struct OkpDecodeTables {
 int okp_version(void);
 const char* okp_strerror(int code);
 
-/* Scratch bytes okp_decode_* / okp_extract_peaks_* need for this problem size (either element type). */
+/* Scratch bytes okp_decode_* / okp_extract_peaks_* need for this problem size (either element type): the tile lists of the
+ * overflow fix-up and the counter the peak kernel's CTAs claim their work from. The contents need no initialisation and
+ * mean nothing between calls, but two calls that may run concurrently (different streams) need different workspaces. */
 size_t okp_decode_workspace_bytes(int N, int C, int H, int W, const OkpDecodeParams* params);
 
 /* Replaces KeypointExtractionComponent.__call__ (perception/pipeline.py:64-91) including

@@ -115,3 +115,32 @@ def test_decode_tables_are_views_into_one_allocation():
     assert host['peak_yx'][1, 2, 3, 1] == -1 and host['peak_xy'].dtype == np.float32
     empty = DecodeTables(0, 3, [1, 3], params, torch.device('cpu'))
     assert empty.numpy()['n_objects'].shape == (0,)
+
+
+def test_bench_arms_share_one_config_and_rank_independent_step_counts():
+    """bench.py: both arms print the same `config` object (the driver's same_config check), and nothing that decides how many
+    exchange steps a rank runs depends on rank-local measurements (a rank-local count once deadlocked the 8-GPU run)."""
+    import ast
+    import inspect
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    for workload in bench.WORKLOADS:
+        assert bench.workload_config(workload, 8, 'gather') == bench.workload_config(workload, 8, 'gather')
+    source = inspect.getsource(bench.run_ours)
+    tree = ast.parse(source)
+    counts = [node for node in ast.walk(tree) if isinstance(node, ast.Assign) and
+              any(isinstance(t, ast.Name) and t.id == 'count' for t in node.targets)]
+    assert counts, "the sustained block's step count is gone"
+    for node in counts:
+        names = {n.id for n in ast.walk(node.value) if isinstance(n, ast.Name)}
+        assert names <= {'max', 'args'}, f"sustained step count depends on {names - {'max', 'args'}}"
+
+
+def test_sparse_auto_looks_at_the_ranks_per_host(monkeypatch):
+    from object_keypoints_b200 import pipeline
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '8')
+    assert pipeline._local_world() == 8 and pipeline._local_world() > pipeline.KeypointDecoder.SPARSE_MAX_LOCAL_WORLD
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '2')
+    assert pipeline._local_world() <= pipeline.KeypointDecoder.SPARSE_MAX_LOCAL_WORLD
