@@ -140,6 +140,14 @@ int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W,
                           const OkpDecodeParams* params, const OkpDecodeTables* tables,
                           void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* okp_extract_peaks_f32 with two optional CUDA events (cudaEvent_t passed as void*, NULL = none) recorded on `stream` right
+ * before and right after the peak kernel itself -- i.e. without the work counter's memset in front of it and the overflow
+ * fix-up behind it: for callers that time the kernel (bench.py's roofline figure). Same work, same tables. */
+int okp_extract_peaks_events_f32(const float* heat_dev, int N, int C, int H, int W,
+                                 const OkpDecodeParams* params, const OkpDecodeTables* tables,
+                                 void* workspace_dev, size_t workspace_bytes, void* event_before, void* event_after,
+                                 void* stream);
+
 /* Replaces ObjectExtraction.__call__ (pipeline.py:104-153) and the DetectionToPoint loop of
  * ObjectKeypointPipeline.__call__ (pipeline.py:189-199, 164-171; camera_utils.py:31-34,75-81)
  * for every frame, reading the peak_* tables. depth_dev [N,C,H,W], centers_dev [N,C-1,2,H,W]:

@@ -21,7 +21,7 @@ EXPORTS = [
     'okp_eval_match_f64', 'okp_eval_summary_f64', 'okp_record_doubles', 'okp_pack_records_f64',
     'okp_rasterise_targets_f32', 'okp_host_pack_scratch_bytes', 'okp_host_pack_tiles_f32', 'okp_scatter_tiles_f32',
     'okp_record_bytes', 'okp_decode_emit_f32', 'okp_decode_emit_bf16', 'okp_triangulate_tracks_f64', 'okp_associate_pairs_f64',
-    'okp_group_objects_emit_f32', 'okp_group_objects_emit_bf16',
+    'okp_group_objects_emit_f32', 'okp_group_objects_emit_bf16', 'okp_extract_peaks_events_f32',
 ]
 
 
@@ -109,6 +109,8 @@ def lib():
     L.okp_extract_peaks_f32.restype = i32
     L.okp_extract_peaks_f32.argtypes = [vp, i32, i32, i32, i32, P(_abi.OkpDecodeParams), P(_abi.OkpDecodeTables),
                                         vp, sz, vp]
+    L.okp_extract_peaks_events_f32.restype = i32
+    L.okp_extract_peaks_events_f32.argtypes = L.okp_extract_peaks_f32.argtypes[:-1] + [vp, vp, vp]
     L.okp_group_objects_f32.restype = i32
     L.okp_group_objects_f32.argtypes = [vp, vp, i32, i32, i32, i32, P(ctypes.c_int32), P(_abi.OkpCamera),
                                         P(_abi.OkpDecodeParams), P(_abi.OkpDecodeTables), vp]

@@ -180,7 +180,8 @@ int launch_overflow(const T* heat_dev, const PeakCall& call, int maps, const Okp
 
 template <typename T>
 int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
-                  const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
+                  const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream,
+                  void* event_before = nullptr, void* event_after = nullptr) {
     int rc = check_params(params);
     if (rc != OKP_OK) return rc;
     rc = check_shape(N, C, H, W);
@@ -205,7 +206,8 @@ int extract_peaks(const T* heat_dev, int N, int C, int H, int W, const OkpDecode
         {
             OkpStreamPlan stream_plan;
             if (!okp_stream_plan(maps, C, H, W, K, (int)sizeof(T), 0, params->lean_tables, &stream_plan)) return OKP_E_UNSUPPORTED;
-            rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, call.group_counter, s);
+            rc = okp_stream_launch<T>(heat_dev, stream_plan, params->threshold, *tables, nullptr, call.group_counter, s,
+                                      (cudaEvent_t)event_before, (cudaEvent_t)event_after);
         }
         if (rc != OKP_OK) return rc;
         rc = launch_overflow<T>(heat_dev, call, maps, params, tables, s);
@@ -386,6 +388,12 @@ extern "C" {
 int okp_extract_peaks_f32(const float* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
                           const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* stream) {
     return extract_peaks<float>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream);
+}
+
+int okp_extract_peaks_events_f32(const float* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,
+                                 const OkpDecodeTables* tables, void* workspace_dev, size_t workspace_bytes, void* event_before,
+                                 void* event_after, void* stream) {
+    return extract_peaks<float>(heat_dev, N, C, H, W, params, tables, workspace_dev, workspace_bytes, stream, event_before, event_after);
 }
 
 int okp_extract_peaks_bf16(const void* heat_dev, int N, int C, int H, int W, const OkpDecodeParams* params,

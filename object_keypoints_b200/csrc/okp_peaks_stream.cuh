@@ -456,7 +456,9 @@ static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esi
         p.stage_bytes = p.halves * p.half_stride;
     };
     resize(fused ? p.M / C * C : p.M);
-    sp.edge_only = okp_env_int("OKP_STREAM_EDGE_ONLY", 0, 1, 0);
+    // small bfloat16 maps: every batch on the border-checked variant of the row step -- one variant instead of two in the
+    // instruction cache (a 64x64 map alternates between them every few batches; r02i: 505 -> 487 us; float32: 440 -> 472 us)
+    sp.edge_only = okp_env_int("OKP_STREAM_EDGE_ONLY", 0, 1, small_map && esize == 2 ? 1 : 0);
     sp.EW = okp_env_int("OKP_STREAM_EPILOGUE_WARPS", 0, 4, 0);    // 0: decided below, once M is known
     // the second candidate buffer costs PK * 8 bytes per map: give it back from the per-CTA budget by re-planning M
     const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;
@@ -493,7 +495,7 @@ static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esi
 template <typename T>
 static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, float threshold,
                                     const OkpDecodeTables& tables, const OkpGroupArgs* ga, int* group_counter_dev,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr) {
     const OkpStripPlan& p = sp.s;
     OkpEncodeTiledFn encode = okp_encode_tiled_fn();
     if (!encode) return OKP_E_CUDA;
@@ -522,8 +524,10 @@ static inline int okp_stream_launch(const T* heat, const OkpStreamPlan& sp, floa
     if (grid > sp.groups) grid = sp.groups;
     const float thr_lo = threshold - OKP_STRIP_THRESHOLD_SLACK * fabsf(threshold);
     OKP_CUDA_CHECK(cudaMemsetAsync(group_counter_dev, 0, sizeof(int), stream));
+    if (before) OKP_CUDA_CHECK(cudaEventRecord(before, stream));
     kernel<<<(unsigned)grid, sp.threads, sp.smem_bytes, stream>>>(tmap, heat, sp, threshold, thr_lo, tables, fused ? *ga : none,
                                                                   group_counter_dev);
     OKP_CUDA_CHECK(cudaGetLastError());
+    if (after) OKP_CUDA_CHECK(cudaEventRecord(after, stream));
     return OKP_OK;
 }

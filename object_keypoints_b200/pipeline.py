@@ -178,7 +178,9 @@ class KeypointDecoder:
         records: an ``_abi.OkpRecordSink`` (sharding.RecordExchange.begin()): the kernel also writes every frame's
         compact record into the sink's buffers while it decodes (the multi-GPU gather).
         peaks_done: a ``torch.cuda.Event`` recorded between the peak kernel (+ its overflow fix-up) and the grouping
-        kernel -- the two halves are then enqueued by two C calls instead of one (bench.py times K1 with it)."""
+        kernel -- the two halves are then enqueued by two C calls instead of one. A PAIR of timing events instead is
+        recorded by the library right before and right after the peak kernel itself (okp_extract_peaks_events_f32:
+        bench.py's roofline figure is the time between them)."""
         heat, heat_kind = _as_device_map(heat, self.device)
         self._check(heat)
         depth, depth_kind = _as_device_map(depth, self.device)
@@ -200,12 +202,23 @@ class KeypointDecoder:
                 ctypes.byref(records) if records is not None else None, _stream_handle(stream))
             _lib.check(rc, f'okp_decode_emit_{heat_kind}')
         else:                                                # e.g. bf16 heatmaps with float32 depth / centre maps
-            rc = getattr(self._lib, f'okp_extract_peaks_{heat_kind}')(
-                heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params), ctypes.byref(tables.struct),
-                ws.data_ptr(), ws.numel(), _stream_handle(stream))
-            _lib.check(rc, f'okp_extract_peaks_{heat_kind}')
-            if peaks_done is not None:
-                peaks_done.record(torch.cuda.current_stream(self.device) if stream is None else stream)
+            pair = peaks_done if isinstance(peaks_done, (tuple, list)) else None
+            if pair is not None and heat_kind == 'f32':
+                for event in pair:
+                    if not event.cuda_event:                 # torch creates the CUDA event at its first record
+                        event.record(torch.cuda.current_stream(self.device) if stream is None else stream)
+                rc = self._lib.okp_extract_peaks_events_f32(
+                    heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                    ws.data_ptr(), ws.numel(), ctypes.c_void_p(pair[0].cuda_event), ctypes.c_void_p(pair[1].cuda_event),
+                    _stream_handle(stream))
+                _lib.check(rc, 'okp_extract_peaks_events_f32')
+            else:
+                rc = getattr(self._lib, f'okp_extract_peaks_{heat_kind}')(
+                    heat.data_ptr(), N, self.C, self.H, self.W, ctypes.byref(self.params), ctypes.byref(tables.struct),
+                    ws.data_ptr(), ws.numel(), _stream_handle(stream))
+                _lib.check(rc, f'okp_extract_peaks_{heat_kind}')
+                for event in (pair if pair is not None else [peaks_done] if peaks_done is not None else []):
+                    event.record(torch.cuda.current_stream(self.device) if stream is None else stream)
             rc = getattr(self._lib, f'okp_group_objects_emit_{depth_kind}')(
                 depth.data_ptr(), centers.data_ptr(), N, self.C, self.H, self.W, self._cfg_array, cam,
                 ctypes.byref(self.params), ctypes.byref(tables.struct),
