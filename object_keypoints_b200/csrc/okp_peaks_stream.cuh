@@ -456,9 +456,10 @@ static inline bool okp_stream_plan(int maps, int C, int H, int W, int K, int esi
         p.stage_bytes = p.halves * p.half_stride;
     };
     resize(fused ? p.M / C * C : p.M);
-    // small bfloat16 maps: every batch on the border-checked variant of the row step -- one variant instead of two in the
-    // instruction cache (a 64x64 map alternates between them every few batches; r02i: 505 -> 487 us; float32: 440 -> 472 us)
-    sp.edge_only = okp_env_int("OKP_STREAM_EDGE_ONLY", 0, 1, small_map && esize == 2 ? 1 : 0);
+    // every batch on the border-checked variant of the row step (one variant instead of two in the instruction cache): helped
+    // small bfloat16 maps with the static group assignment (r02i: 505 -> 487 us), not with claimed groups (r02u: 448 -> 454 us)
+    // and never float32 (440 -> 472 us): off, kept as a knob of the tuning build
+    sp.edge_only = okp_env_int("OKP_STREAM_EDGE_ONLY", 0, 1, 0);
     sp.EW = okp_env_int("OKP_STREAM_EPILOGUE_WARPS", 0, 4, 0);    // 0: decided below, once M is known
     // the second candidate buffer costs PK * 8 bytes per map: give it back from the per-CTA budget by re-planning M
     const int budget = okp_env_int("OKP_STRIP_SMEM_KB", 16, 224, 110) * 1024;
