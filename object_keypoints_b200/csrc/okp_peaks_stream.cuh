@@ -291,12 +291,8 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
     constexpr int RB = OKP_STRIP_RB;
     const OkpStripPlan& p = sp.s;
     const int NS = p.NS;
-    OkpStripPeak* peaks = reinterpret_cast<OkpStripPeak*>(smem + sp.off_peaks);                // [M][PK] (epilogue only)
-    uint32_t* items = reinterpret_cast<uint32_t*>(smem + sp.off_items);                        // [IC]
-    int* n_peaks = reinterpret_cast<int*>(smem + sp.off_misc);                                 // [M]
-    int* n_items = n_peaks + p.M;                                                              // [1]
-    int* cand_start = n_items + 1;                                                             // [M + 1] prefix of candidate counts
-    int* pend = cand_start + p.M + 1;                                                          // [M] fused: frame f is left to the fix-up launches
+    int* n_peaks = reinterpret_cast<int*>(smem + sp.off_misc);              // [M] + n_items [1] + cand_start [M + 1] + pend [M]: the
+    int* pend = n_peaks + 2 * p.M + 2;                                      // epilogue's (okp_stream_epilogue), zeroed here
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.off_mbar);       // [NS] TMA landed
     uint64_t* done = full + OKP_STRIP_MAX_NS;                               // [NS] compute warps finished the batch
     uint64_t* cand_full = done + OKP_STRIP_MAX_NS;                          // [2] candidate buffer complete
@@ -327,8 +323,6 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
     // multi-GPU decode -- simply takes fewer groups. With the static round-robin of round 1 such a CTA delayed the whole
     // launch by its lag (K1 stretched 479 -> 518 us on 8 GPUs). The id travels to the compute warps behind the `full`
     // barrier of the group's first batch and to the epilogue warps behind `cand_full`; -1 ends the roles' loops.
-    const int my_groups = blockIdx.x < sp.groups ? (sp.groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-
     if (warp == compute_warps) {
         // ------------------------------- producer: one lane, batches of consecutive groups back to back ---
         if ((tid & 31) == 0) {
@@ -422,7 +416,7 @@ okp_peaks_stream_kernel(const __grid_constant__ CUtensorMap tmap, const T* __res
         }
     } else {
         // ------------------------------- epilogue warps: one finished candidate buffer at a time ---------
-        okp_stream_epilogue<T, FUSED>(smem, sp, heat, threshold, t, ga, tid - (compute_warps + 1) * 32, my_groups, true);
+        okp_stream_epilogue<T, FUSED>(smem, sp, heat, threshold, t, ga, tid - (compute_warps + 1) * 32, 0, true);
     }
 }
 

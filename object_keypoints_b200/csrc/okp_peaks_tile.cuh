@@ -1,5 +1,6 @@
-// okp_peaks_tile.cuh -- K1, third form (round 2): sparse tile kernel. Same results as okp_peaks_stream.cuh (and the same
-// epilogue), a fraction of its instructions on the maps a trained network writes.
+// okp_peaks_tile.cuh -- K1, third form (round 2): sparse tile kernel. EXPERIMENT, compiled into the tuning build only
+// (-DOKP_TUNING_KNOBS, OKP_PEAKS_TILE=1): same results as okp_peaks_stream.cuh (and the same epilogue), fewer thread
+// instructions on the maps a trained network writes -- and 3.6x slower, see profiles/r02e_tile_kernel.md for why.
 //
 // Replaces perception/pipeline.py:46-79 + perception/models.py:55-58 for every map of a batch.
 //
@@ -182,7 +183,6 @@ okp_peaks_tile_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restr
         uint32_t full_parity = 0;
         for (int it = 0; it < my_groups; ++it) {
             const int buf = it & 1;
-            const int first_map = (blockIdx.x + it * gridDim.x) * p.M;
             if (it >= 2) okp_mbar_wait(cand_free + buf, (uint32_t)(((it >> 1) - 1) & 1));   // the epilogue released the buffer
             int* count = reinterpret_cast<int*>(smem + sp.off_count[buf]);                  // [M] candidates, [M] redo
             OkpStripCandidate* pending = reinterpret_cast<OkpStripCandidate*>(smem + sp.off_pending[buf]);
