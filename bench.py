@@ -415,9 +415,14 @@ def run_ours(args):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
+    phase_events = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for i in k1_events}
     for i in range(args.steps):
+        if i in phase_events:
+            phase_events[i][0].record()                 # before the exchange's admission wait (N > 1) and the counter memset
         sink = exchange.begin() if world > 1 else None
         decoder.decode_batch(heat, depth, centers, tables=tables, records=sink, peaks_done=k1_events.get(i))
+        if i in phase_events:
+            phase_events[i][1].record()                 # behind the grouping kernel
         if world > 1:
             gathered, _ = exchange.end()
     if world > 1:
@@ -427,6 +432,10 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = start.elapsed_time(stop)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events.values()) / len(k1_events)
+    # where an instrumented step's time goes on this rank: in front of K1 (admission wait of the exchange, counter memset),
+    # K1, behind it (overflow fix-up, grouping + record stores, launch gaps)
+    lead_ms = sum(phase_events[i][0].elapsed_time(k1_events[i][0]) for i in k1_events) / len(k1_events)
+    tail_ms = sum(k1_events[i][1].elapsed_time(phase_events[i][1]) for i in k1_events) / len(k1_events)
 
     # ---- sustained behaviour: ~1 s of back-to-back steps (the K timed steps above last ~10 ms), clocks sampled throughout ----
     sustained = None
@@ -502,6 +511,11 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = end_to_end(args, decoder, heat, depth, centers, frames, world, rank, device, barrier)
 
+    phases = torch.tensor([lead_ms, k1_ms, tail_ms, elapsed_ms / args.steps], dtype=torch.float64, device=device)
+    per_rank = [torch.empty_like(phases) for _ in range(world)] if world > 1 else [phases]
+    if world > 1:
+        dist.all_gather(per_rank, phases)
+    per_rank = [[round(float(v), 4) for v in row.cpu()] for row in per_rank]
     times = torch.tensor([elapsed_ms, k1_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -552,6 +566,9 @@ def run_ours(args):
             line['strong'] = strong
         if sustained is not None:
             line['sustained'] = sustained
+        line['phases_per_rank'] = {'columns': ['ms in front of K1 (exchange admission wait, counter memset)', 'K1 ms',
+                                               'ms behind K1 (overflow fix-up, grouping + record stores, gaps)', 'ms per step'],
+                                   'instrumented_steps': sorted(k1_events), 'ranks': per_rank}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = baseline
         if world == 1 and not args.no_secondary:
