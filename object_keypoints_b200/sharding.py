@@ -138,13 +138,9 @@ class RecordExchange:
     stream after everything enqueued on the current stream so far, so the gather of step k overlaps the decode of step
     k + 1 (frames are independent). It returns the gathered ``[world * frames, record_bytes]`` uint8 tensor
     (``unpack_compact_records``) plus the event that marks it complete. ``begin`` makes the current stream wait for the
-    completion of step k - 3 before step k may write: no rank runs more than three steps ahead of the slowest, so with
-    ``depth`` = 6 buffers the result of step k stays valid until the decode of step k + 3 has been ISSUED on the reading
-    rank (consume it on the compute stream before that). Three, not two: the completion barrier of a step is a small kernel
-    that becomes runnable together with the next step's persistent peak kernel; when that one takes every SM slot first, the
-    barrier runs only after it -- with LAG = 2 every step then waited ~17 us for the barrier of step k - 2
-    (``phases_per_rank`` of profiles/r02y_bench_n4.json). The exchange stream also has high priority so that the barrier's
-    one CTA is dispatched first.
+    completion of step k - 2 before step k may write: no rank runs more than two steps ahead of the slowest, so with
+    ``depth`` = 4 buffers the result of step k stays valid until the decode of step k + 2 has been ISSUED on the reading
+    rank (consume it on the compute stream before that).
 
     Transports:
       'peer'  the gather buffers are symmetric (peer-mapped) memory; completion is a device-side barrier, no NCCL on the
@@ -161,9 +157,9 @@ class RecordExchange:
     integer = gather to that rank only (north_star: "a final NVLink gather of the 3D keypoints"): one store per record,
     into the root's buffer -- only the root's returned tensor is meaningful.
     """
-    LAG = 3
+    LAG = 2
 
-    def __init__(self, decoder, frames, world=None, rank=None, transport='auto', depth=6, group=None, root=None, staged=False):
+    def __init__(self, decoder, frames, world=None, rank=None, transport='auto', depth=4, group=None, root=None, staged=False):
         import ctypes
         from . import _abi
         self._ctypes, self._abi = ctypes, _abi
@@ -180,7 +176,7 @@ class RecordExchange:
         if self.depth < self.LAG + 2:
             raise ValueError(f"depth must be at least {self.LAG + 2}")
         self.root = None if root is None else int(root)
-        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.stream = torch.cuda.Stream(device=self.device)
         self.calls = 0
         self.handles = None
         shape = (self.world * self.N, self.record_bytes)
