@@ -144,3 +144,24 @@ def test_sparse_auto_looks_at_the_ranks_per_host(monkeypatch):
     assert pipeline._local_world() == 8 and pipeline._local_world() > pipeline.KeypointDecoder.SPARSE_MAX_LOCAL_WORLD
     monkeypatch.setenv('LOCAL_WORLD_SIZE', '2')
     assert pipeline._local_world() <= pipeline.KeypointDecoder.SPARSE_MAX_LOCAL_WORLD
+
+
+def test_bench_parity_rule_sees_a_single_wrong_value():
+    """bench.py refuses to print a line unless every timed frame equals the oracle: the comparison itself, on oracle tables."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from object_keypoints_b200 import synthetic
+    from oracle import c_oracle
+    cfg, size = [1, 3], (64, 64)
+    batch = synthetic.make_batch(6, cfg, size, seed=4, objects=(1, 2))
+    want = c_oracle.decode(batch.heat, batch.depth, batch.centers, cfg, synthetic.default_camera(size))
+    assert bench.parity_mismatches(want, want) == (6, 0)
+    for key, change in (('peak_yx', 1), ('kp_xy', None), ('kp_point', 1e-3), ('flags', 1)):     # None: one float32 ulp
+        got = {k: v.copy() for k, v in want.items()}
+        flat = got[key].reshape(6, -1)
+        column = int(np.argmax(np.abs(want[key].reshape(6, -1)[2]) > 0)) if key != 'flags' else 0
+        flat[2, column] = np.nextafter(flat[2, column], np.float32(np.inf)) if change is None else \
+            flat[2, column] + np.asarray(change, dtype=flat.dtype)
+        assert bench.parity_mismatches(got, want) == (6, 1), key
